@@ -1,0 +1,1008 @@
+// mcgpu_api.cu -- the extern "C" boundary (include/mcgpu.h) and the host-side engine
+// that sequences the fused step kernels: it replaces the control flow of
+// MCPar::run (reference src/mcpar.cc:17-214) with device-resident multi-step launches.
+//
+// There is no CPU compute path in this file: every numerical result comes from a
+// kernel in mh_fast.cu / mh_exact.cu, and every entry point fails with
+// MCGPU_ENODEVICE / MCGPU_ECUDA when no device is usable.
+#include "../../include/mcgpu.h"
+#include "mh_launch.h"
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace mcgpu;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+struct StreamSet { std::vector<double> Z, U; std::vector<int32_t> I; };
+
+}  // namespace
+
+struct mcgpu_engine {
+  mcgpu_config cfg;
+  int d = 0;
+  long long C = 0, ld = 0, N = 0;
+  bool sharded = false, verify = false, replay_local = false;
+  int dev = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, side = nullptr;
+  std::string err;
+
+  // likelihood
+  int lik = -1; int lik_k = 0; double lp[8] = {0}; double *lik_dev = nullptr;
+
+  // NORMAL / REPLAY_LOCAL state (SoA) or VERIFY state (AoS per rank)
+  double *x = nullptr, *ly = nullptr, *mu = nullptr, *ps = nullptr;
+  double *factor = nullptr;
+  unsigned long long *counts = nullptr;   // [0,1] window, [2,3] cumulative, [4,5] main-phase stats
+  double *pool[2] = {nullptr, nullptr}; int pool_cur = 0; int M = 0; long long stride = 1; bool pool_in_smem = true;
+  double *hist = nullptr; long long hist_cap = 0, hist_kept = 0;
+  int *overrun = nullptr;
+  double *Zd = nullptr, *Ud = nullptr; int *Id = nullptr; long long nz = 0, nu = 0, ni = 0;
+
+  // VERIFY extras
+  int Cr = 0, Rl = 0, R = 0, rank0 = 0;
+  double *ptrial = nullptr, *sig = nullptr, *mutrial = nullptr, *sigtrial = nullptr, *musig = nullptr;
+  double *snap[2] = {nullptr, nullptr}; int snap_cur = 0;
+  long long *soff = nullptr, *cursors = nullptr; int *irate_d = nullptr;
+  unsigned long long *rstats = nullptr;
+  std::vector<StreamSet> host_streams; bool streams_dirty = false;
+  uint8_t *tr_accept = nullptr, *tr_remote = nullptr; double *tr_trial_ly = nullptr, *tr_trial_p = nullptr, *tr_cfac = nullptr;
+  int *tr_iters = nullptr; int trace_cap = 0;
+
+  // schedule
+  bool have_state = false, have_factor = false, sampling = false, exchange_pending = false, tune_pending = false;
+  long long burn_done = 0, t_main = 0; int nsamp = 0; int irate = 50; int nburn_total = 0;
+  long long launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers; double ms_accum = 0.0;
+
+  // pinned staging for history reads
+  double *pin[2] = {nullptr, nullptr}; size_t pin_bytes = 0; cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t _s = (call);                                                             \
+    if (_s != cudaSuccess) {                                                             \
+      char _b[512];                                                                      \
+      snprintf(_b, sizeof _b, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_s)); \
+      e->err = _b;                                                                       \
+      return _s == cudaErrorMemoryAllocation ? MCGPU_ENOMEM : MCGPU_ECUDA;               \
+    }                                                                                    \
+  } while (0)
+
+int fail(mcgpu_engine *e, int code, const char *msg) { if (e) e->err = msg; else g_create_err = msg; return code; }
+
+template <class T> int dalloc(mcgpu_engine *e, T **p, size_t n, bool zero = true)
+{
+  CK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  if (zero) CK(cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(T), e->stream));
+  return 0;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void timer_begin(mcgpu_engine *e)
+{
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a, e->stream);
+  e->timers.emplace_back(a, b);
+}
+void timer_end(mcgpu_engine *e) { cudaEventRecord(e->timers.back().second, e->stream); }
+void timers_resolve(mcgpu_engine *e)
+{
+  for (auto &t : e->timers) {
+    float ms = 0;
+    cudaEventSynchronize(t.second);
+    if (cudaEventElapsedTime(&ms, t.first, t.second) == cudaSuccess) e->ms_accum += ms;
+    cudaEventDestroy(t.first); cudaEventDestroy(t.second);
+  }
+  e->timers.clear();
+}
+
+// lower Cholesky factor of a row-major SPD matrix in place (replaces spotrf('U') on the
+// column-major view, mcpar.cc:475-480); the strict upper triangle keeps its input
+int cholesky_lower(int d, double *a)
+{
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double sum = a[i * d + j];
+      for (int k = 0; k < j; ++k) sum -= a[i * d + k] * a[j * d + k];
+      if (i == j) { if (!(sum > 0)) return i + 1; a[i * d + i] = sqrt(sum); }
+      else a[i * d + j] = sum / a[j * d + j];
+    }
+  return 0;
+}
+
+void fill_step_params(mcgpu_engine *e, StepParams &p)
+{
+  memset(&p, 0, sizeof p);
+  p.x = e->x; p.ly = e->ly; p.mu = e->mu; p.ps = e->ps;
+  p.C = e->C; p.ld = e->ld; p.chain0 = e->cfg.chain0;
+  p.factor = e->factor;
+  p.key0 = (uint32_t)e->cfg.seed; p.key1 = (uint32_t)(e->cfg.seed >> 32);
+  p.sync = e->cfg.sync; p.coin_group = e->cfg.coin_group; p.pl = e->cfg.pl;
+  p.pool_m = e->M; p.pool_stride = e->stride; p.pool_in_smem = e->pool_in_smem;
+  p.thin = e->cfg.thin;
+  p.Z = e->Zd; p.U = e->Ud; p.nz = e->nz; p.nu = e->nu; p.overrun = e->overrun;
+  memcpy(p.lp, e->lp, sizeof p.lp); p.lik_dev = e->lik_dev; p.lik_k = e->lik_k;
+  p.nburn_total = e->nburn_total;
+}
+
+cudaError_t launch_steps_any(mcgpu_engine *e, bool main_phase, const StepParams &p)
+{
+  ++e->launches;
+  if (e->replay_local) return exact::launch_steps(e->lik, e->d, 1, main_phase, p, e->stream);
+  return fast::launch_steps(e->lik, e->d, 0, main_phase, p, e->stream);
+}
+
+int upload_streams(mcgpu_engine *e)
+{
+  if (!e->streams_dirty) return 0;
+  const int nr = (int)e->host_streams.size();
+  std::vector<long long> soff((size_t)nr * 6);
+  size_t tz = 0, tu = 0, ti = 0;
+  for (int r = 0; r < nr; ++r) {
+    auto &s = e->host_streams[r];
+    soff[r * 6 + 0] = (long long)tz; soff[r * 6 + 1] = (long long)s.Z.size(); tz += s.Z.size();
+    soff[r * 6 + 2] = (long long)tu; soff[r * 6 + 3] = (long long)s.U.size(); tu += s.U.size();
+    soff[r * 6 + 4] = (long long)ti; soff[r * 6 + 5] = (long long)s.I.size(); ti += s.I.size();
+  }
+  if (e->Zd) cudaFree(e->Zd);
+  if (e->Ud) cudaFree(e->Ud);
+  if (e->Id) cudaFree(e->Id);
+  e->Zd = e->Ud = nullptr; e->Id = nullptr;
+  CK(cudaMalloc((void**)&e->Zd, std::max<size_t>(tz, 1) * 8));
+  CK(cudaMalloc((void**)&e->Ud, std::max<size_t>(tu, 1) * 8));
+  CK(cudaMalloc((void**)&e->Id, std::max<size_t>(ti, 1) * 4));
+  for (int r = 0; r < nr; ++r) {
+    auto &s = e->host_streams[r];
+    if (!s.Z.empty()) CK(cudaMemcpyAsync(e->Zd + soff[r * 6], s.Z.data(), s.Z.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    if (!s.U.empty()) CK(cudaMemcpyAsync(e->Ud + soff[r * 6 + 2], s.U.data(), s.U.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    if (!s.I.empty()) CK(cudaMemcpyAsync(e->Id + soff[r * 6 + 4], s.I.data(), s.I.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  if (e->verify) CK(cudaMemcpyAsync(e->soff, soff.data(), soff.size() * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->nz = (long long)tz; e->nu = (long long)tu; e->ni = (long long)ti;
+  e->streams_dirty = false;
+  return 0;
+}
+
+void fill_verify_params(mcgpu_engine *e, VerifyParams &p)
+{
+  memset(&p, 0, sizeof p);
+  p.d = e->d; p.C = e->Cr; p.N = (int)e->N; p.rank0 = e->rank0; p.nsamp = e->nsamp;
+  p.L.lik = e->lik; p.L.d = e->d; p.L.k = e->lik_k; memcpy(p.L.lp, e->lp, sizeof p.L.lp); p.L.dev = e->lik_dev;
+  p.pvals = e->x; p.ptrial = e->ptrial; p.ly = e->ly; p.mu = e->mu; p.sig = e->sig; p.ps = e->ps;
+  p.mutrial = e->mutrial; p.sigtrial = e->sigtrial; p.factor = e->factor; p.musig = e->musig;
+  p.Z = e->Zd; p.U = e->Ud; p.I = e->Id; p.soff = e->soff; p.cursors = e->cursors;
+  p.counts = e->counts; p.irate = e->irate_d;
+  p.sync = e->cfg.sync; p.pl = e->cfg.pl; p.armin = e->cfg.armin; p.armax = e->cfg.armax;
+  p.dfac = e->cfg.dfac; p.ifac = e->cfg.ifac;
+  p.hist = e->hist; p.hist_chains = e->C;
+  p.tr_accept = e->tr_accept; p.tr_trial_ly = e->tr_trial_ly; p.tr_trial_p = e->tr_trial_p;
+  p.tr_cfac = e->tr_cfac; p.tr_remote = e->tr_remote; p.tr_iters = e->tr_iters; p.trace_cap = e->trace_cap;
+  p.overrun = e->overrun; p.rstats = e->rstats;
+}
+
+int check_overrun(mcgpu_engine *e)
+{
+  int flag = 0;
+  CK(cudaMemcpyAsync(&flag, e->overrun, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (flag) return fail(e, MCGPU_ESTREAM, "a replay stream ran dry (or a remote step was requested in REPLAY_LOCAL mode)");
+  return 0;
+}
+
+// ---- small utility kernels -------------------------------------------------
+__global__ void argmax_rows_kernel(const double *rows, long long nrows, int ncol, double *best_val, long long *best_row)
+{
+  __shared__ double sv[256]; __shared__ long long sr[256];
+  double bv = -INFINITY; long long br = -1;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (long long)gridDim.x * blockDim.x) {
+    const double v = rows[r * ncol + ncol - 1];
+    if (v > bv) { bv = v; br = r; }              // strict >: first occurrence wins (mcout.cc:138)
+  }
+  sv[threadIdx.x] = bv; sr[threadIdx.x] = br;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double v = sv[threadIdx.x + o]; const long long r = sr[threadIdx.x + o];
+      if (r >= 0 && (v > sv[threadIdx.x] || sr[threadIdx.x] < 0 || (v == sv[threadIdx.x] && r < sr[threadIdx.x]))) { sv[threadIdx.x] = v; sr[threadIdx.x] = r; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { best_val[blockIdx.x] = sv[0]; best_row[blockIdx.x] = sr[0]; }
+}
+
+// sums of x_i (pair index < d) and x_i*x_j over all rows; one quantity per blockIdx.y
+__global__ void moments_kernel(const double *rows, long long nrows, int d, double *out)
+{
+  __shared__ double ssum[256];
+  const int q = blockIdx.y;
+  int ci, cj = -1;
+  if (q < d) ci = q;
+  else { int k = q - d; ci = 0; while (k >= d - ci) { k -= d - ci; ++ci; } cj = ci + k; }
+  double s = 0.0;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (long long)gridDim.x * blockDim.x) {
+    const double a = rows[r * (d + 1) + ci];
+    s += cj < 0 ? a : a * rows[r * (d + 1) + cj];
+  }
+  ssum[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) { if (threadIdx.x < o) ssum[threadIdx.x] += ssum[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) atomicAdd(out + q, ssum[0]);
+}
+
+__global__ void sobol_box_kernel(const uint32_t *dirs, int d, unsigned long long first_scalar, int ntot,
+                                 const double *plo, const double *phi, double *pout)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= ntot) return;
+  const unsigned long long sc = first_scalar + (unsigned long long)q;
+  const unsigned long long n = sc / (unsigned long long)d; const int k = (int)(sc % (unsigned long long)d);
+  unsigned long long gray = n ^ (n >> 1);
+  uint32_t xv = 0;
+  for (int b = 0; gray; ++b, gray >>= 1) if (gray & 1ull) xv ^= dirs[k * 32 + b];
+  const double u = (double)xv * (1.0 / 4294967296.0);
+  const int i = q % d;
+  pout[q] = __dadd_rn(plo[i], __dmul_rn(u, __dsub_rn(phi[i], plo[i])));   // mcutil.cc:31, no contraction
+}
+
+__global__ void dfma_peak_kernel(double *out, int iters, double a, double b)
+{
+  double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+    v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+  }
+  const double s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+  if (s == 12345.678) out[0] = s;
+}
+
+__global__ void transpose_aos_to_soa(const double *aos, double *soa, long long C, long long ld, int d)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= C) return;
+  for (int i = 0; i < d; ++i) soa[i * ld + j] = aos[j * d + i];
+}
+__global__ void transpose_soa_to_aos(const double *soa, double *aos, long long C, long long ld, int d, double scale)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= C) return;
+  for (int i = 0; i < d; ++i) aos[j * d + i] = soa[i * ld + j] * scale;
+}
+
+// Sobol direction numbers, Joe & Kuo (2008), dimensions 1..16
+struct jk_t { int s; uint32_t a; uint32_t m[7]; };
+const jk_t JK[16] = {
+  {0,0,{0}}, {1,0,{1}}, {2,1,{1,3}}, {3,1,{1,3,1}}, {3,2,{1,1,1}}, {4,1,{1,1,3,3}},
+  {4,4,{1,3,5,13}}, {5,2,{1,1,5,5,17}}, {5,4,{1,1,5,5,5}}, {5,7,{1,1,7,11,19}},
+  {5,11,{1,1,5,1,1}}, {5,13,{1,1,1,3,11}}, {5,14,{1,3,5,5,31}}, {6,1,{1,3,3,9,7,49}},
+  {6,13,{1,1,1,15,21,21}}, {6,16,{1,3,1,13,27,49}},
+};
+void sobol_dirs(int dim, uint32_t *v)
+{
+  if (dim == 0) { for (int i = 0; i < 32; ++i) v[i] = 1u << (31 - i); return; }
+  const jk_t &p = JK[dim]; const int s = p.s;
+  for (int i = 0; i < 32; ++i) {
+    if (i < s) v[i] = p.m[i] << (31 - i);
+    else {
+      v[i] = v[i - s] ^ (v[i - s] >> s);
+      for (int k = 1; k < s; ++k) v[i] ^= (((p.a >> (s - 1 - k)) & 1u) * v[i - k]);
+    }
+  }
+}
+
+int prepare_lik(int lik, int d, const double *par, int npar, double lp[8], std::vector<double> &dev, int &K, std::string &err)
+{
+  memset(lp, 0, 8 * sizeof(double)); K = 0; dev.clear();
+  switch (lik) {
+    case MCGPU_ROSENBROCK1:
+      if (d < 2 || d % 2) { err = "N for Rosenbrock1 must be even and >= 2"; return MCGPU_EINVAL; }   // rosenbrock.hh:13-16
+      return 0;
+    case MCGPU_ROSENBROCK2:
+      if (d < 2) { err = "N for Rosenbrock2 must be >= 2"; return MCGPU_EINVAL; }                      // rosenbrock.hh:27-30
+      return 0;
+    case MCGPU_GAUSSIAN:
+      if (d != 2) { err = "Invalid specification.  N for Gaussian must == 2."; return MCGPU_EINVAL; }   // rosenbrock.hh:43
+      if (par && npar < 4) { err = "Gaussian needs mu[2], sig2[2]"; return MCGPU_EINVAL; }
+      for (int k = 0; k < 2; ++k) { lp[k] = par ? par[k] : 0.0; lp[2 + k] = par ? 1.0 / par[2 + k] : 1.0; }  // :44-47
+      return 0;
+    case MCGPU_DUALGAUSSIAN:
+      if (d != 2) { err = "DualGaussian has two parameters"; return MCGPU_EINVAL; }
+      lp[0] = (par && npar >= 1) ? par[0] : 5.0;
+      return 0;
+    case MCGPU_GAUSSMIX: {
+      if (!par || npar < 1) { err = "GaussMix needs par = K, mu, sig2, w"; return MCGPU_EINVAL; }
+      K = (int)par[0];
+      if (K < 1 || npar != 1 + 2 * K * d + K) { err = "GaussMix parameter block has the wrong length"; return MCGPU_EINVAL; }
+      dev.resize((size_t)2 * K * d + K);
+      const double *mu = par + 1, *s2 = mu + (size_t)K * d, *w = s2 + (size_t)K * d;
+      for (int i = 0; i < K * d; ++i) { dev[i] = mu[i]; dev[(size_t)K * d + i] = 1.0 / s2[i]; }
+      for (int k = 0; k < K; ++k) dev[(size_t)2 * K * d + k] = log(w[k]);
+      return 0;
+    }
+  }
+  err = "unknown likelihood id";
+  return MCGPU_EINVAL;
+}
+
+}  // namespace
+
+// ============================================================================
+extern "C" {
+
+const char *mcgpu_version(void) { return "mcpar-b200 0.1 (sm_100a, abi 1)"; }
+
+int mcgpu_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char *mcgpu_last_error(const mcgpu_engine *e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+int mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out)
+{
+  if (!cfg || !out) return fail(nullptr, MCGPU_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MCGPU_ABI_VERSION) return fail(nullptr, MCGPU_EINVAL, "abi_version mismatch");
+  if (cfg->nparam < 1 || cfg->nparam > MCGPU_MAX_D) return fail(nullptr, MCGPU_EINVAL, "nparam out of range (1..64)");
+  if (cfg->nchain < 1 || cfg->nchain_total < cfg->nchain || cfg->chain0 < 0 || cfg->chain0 + cfg->nchain > cfg->nchain_total)
+    return fail(nullptr, MCGPU_EINVAL, "inconsistent chain geometry");
+  if (cfg->sync < 1) return fail(nullptr, MCGPU_EINVAL, "sync must be >= 1");
+  if (cfg->thin < 1) return fail(nullptr, MCGPU_EINVAL, "thin must be >= 1");
+  if (mcgpu_device_count() <= cfg->device || cfg->device < 0) return fail(nullptr, MCGPU_ENODEVICE, "no usable CUDA device (this engine has no CPU path)");
+
+  mcgpu_engine *e = new mcgpu_engine();
+  e->cfg = *cfg; e->d = cfg->nparam; e->C = cfg->nchain; e->N = cfg->nchain_total; e->dev = cfg->device;
+  e->verify = cfg->mode == MCGPU_MODE_VERIFY; e->replay_local = cfg->mode == MCGPU_MODE_REPLAY_LOCAL;
+  e->sharded = cfg->nchain < cfg->nchain_total;
+  auto bail = [&](int code, const char *msg) { g_create_err = msg ? msg : e->err; mcgpu_destroy(e); return code; };
+  if (cudaSetDevice(e->dev) != cudaSuccess) return bail(MCGPU_ENODEVICE, "cudaSetDevice failed");
+  if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MCGPU_ECUDA, "stream create failed");
+  if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess) return bail(MCGPU_ECUDA, "stream create failed");
+  e->stream = e->own_stream;
+  const int d = e->d;
+  int rc = 0;
+#define TRY(x) do { rc = (x); if (rc) return bail(rc, nullptr); } while (0)
+  TRY(dalloc(e, &e->overrun, 1));
+  if (!e->verify) {
+    if (cfg->mode != MCGPU_MODE_NORMAL && cfg->mode != MCGPU_MODE_REPLAY_LOCAL) return bail(MCGPU_EINVAL, "unknown mode");
+    if (cfg->coin_group < 1 || cfg->coin_group > 32 || (cfg->coin_group & (cfg->coin_group - 1))) return bail(MCGPU_EINVAL, "coin_group must be a power of two in 1..32");
+    if (cfg->chain0 % 32) return bail(MCGPU_EINVAL, "chain0 must be a multiple of 32");
+    if (e->replay_local && e->sharded) return bail(MCGPU_EINVAL, "REPLAY_LOCAL hosts the whole rank");
+    e->ld = (e->C + 31) / 32 * 32;
+    e->M = (cfg->pool_m > 0 && cfg->pool_m < e->N) ? cfg->pool_m : (int)std::min<long long>(e->N, 1 << 20);
+    if (cfg->pool_m <= 0 && e->N > (1 << 20)) return bail(MCGPU_EINVAL, "pool_m = 0 (all chains) is limited to 2^20 chains; choose a pool size");
+    e->stride = e->N / e->M;
+    e->pool_in_smem = (size_t)e->M * d * 16 + (size_t)(d * d + cfg->sync) * 8 <= 200 * 1024;
+    TRY(dalloc(e, &e->x, (size_t)d * e->ld)); TRY(dalloc(e, &e->ly, (size_t)e->ld));
+    TRY(dalloc(e, &e->mu, (size_t)d * e->ld)); TRY(dalloc(e, &e->ps, (size_t)d * e->ld));
+    TRY(dalloc(e, &e->factor, (size_t)d * d)); TRY(dalloc(e, &e->counts, 6));
+    TRY(dalloc(e, &e->pool[0], (size_t)e->M * d * 2)); TRY(dalloc(e, &e->pool[1], (size_t)e->M * d * 2));
+    e->hist_cap = cfg->history_steps;
+    if (e->hist_cap > 0) TRY(dalloc(e, &e->hist, (size_t)e->hist_cap * e->C * (d + 1), false));
+    e->host_streams.resize(1);
+  } else {
+    e->Cr = cfg->chains_per_rank;
+    if (e->Cr < 1 || e->Cr > 1024) return bail(MCGPU_EINVAL, "VERIFY: chains_per_rank must be 1..1024");
+    if (e->C % e->Cr || e->N % e->Cr || cfg->chain0 % e->Cr) return bail(MCGPU_EINVAL, "VERIFY: chain counts must be multiples of chains_per_rank");
+    if (cfg->thin != 1) return bail(MCGPU_EINVAL, "VERIFY keeps every step (thin = 1)");
+    e->Rl = (int)(e->C / e->Cr); e->R = (int)(e->N / e->Cr); e->rank0 = (int)(cfg->chain0 / e->Cr);
+    const size_t nt = (size_t)e->Cr * d, nm = (size_t)2 * e->N * d;
+    TRY(dalloc(e, &e->x, e->Rl * nt)); TRY(dalloc(e, &e->ptrial, e->Rl * nt)); TRY(dalloc(e, &e->ly, (size_t)e->C));
+    TRY(dalloc(e, &e->mu, e->Rl * nt)); TRY(dalloc(e, &e->sig, e->Rl * nt)); TRY(dalloc(e, &e->ps, e->Rl * nt));
+    TRY(dalloc(e, &e->mutrial, e->Rl * nt)); TRY(dalloc(e, &e->sigtrial, e->Rl * nt));
+    TRY(dalloc(e, &e->factor, (size_t)e->Rl * d * d)); TRY(dalloc(e, &e->musig, e->Rl * nm));
+    TRY(dalloc(e, &e->snap[0], nm)); TRY(dalloc(e, &e->snap[1], nm));
+    TRY(dalloc(e, &e->soff, (size_t)e->Rl * 6)); TRY(dalloc(e, &e->cursors, (size_t)e->Rl * 3));
+    TRY(dalloc(e, &e->counts, (size_t)e->Rl * 2)); TRY(dalloc(e, &e->irate_d, (size_t)e->Rl)); TRY(dalloc(e, &e->rstats, 4));
+    e->hist_cap = cfg->history_steps;
+    if (e->hist_cap > 0) TRY(dalloc(e, &e->hist, (size_t)e->hist_cap * e->C * (d + 1), false));
+    e->host_streams.resize(e->Rl);
+    std::vector<int> ir(e->Rl, 50);                       // irate = 50, mcpar.cc:57
+    if (cudaMemcpyAsync(e->irate_d, ir.data(), ir.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream) != cudaSuccess) return bail(MCGPU_ECUDA, "memcpy failed");
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(MCGPU_ECUDA, "sync failed");
+  }
+#undef TRY
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(MCGPU_ECUDA, "sync failed after allocation");
+  *out = e;
+  return MCGPU_OK;
+}
+
+int mcgpu_destroy(mcgpu_engine *e)
+{
+  if (!e) return MCGPU_OK;
+  cudaSetDevice(e->dev);
+  if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+  timers_resolve(e);
+  void *ptrs[] = {e->x, e->ly, e->mu, e->ps, e->factor, e->counts, e->pool[0], e->pool[1], e->hist, e->overrun,
+                  e->Zd, e->Ud, e->Id, e->ptrial, e->sig, e->mutrial, e->sigtrial, e->musig, e->snap[0], e->snap[1],
+                  e->soff, e->cursors, e->irate_d, e->rstats, e->tr_accept, e->tr_remote, e->tr_trial_ly,
+                  e->tr_trial_p, e->tr_cfac, e->tr_iters, e->lik_dev};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  for (int i = 0; i < 2; ++i) { if (e->pin[i]) cudaFreeHost(e->pin[i]); if (e->pin_ev[i]) cudaEventDestroy(e->pin_ev[i]); }
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->side) cudaStreamDestroy(e->side);
+  delete e;
+  return MCGPU_OK;
+}
+
+int mcgpu_set_stream(mcgpu_engine *e, void *cuda_stream)
+{
+  if (!e) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  CK(cudaStreamSynchronize(e->stream));
+  e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  return MCGPU_OK;
+}
+
+int mcgpu_set_likelihood(mcgpu_engine *e, int lik, const double *par, int npar)
+{
+  if (!e) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  std::vector<double> dev; int K = 0; std::string err;
+  int rc = prepare_lik(lik, e->d, par, npar, e->lp, dev, K, err);
+  if (rc) { e->err = err; return rc; }
+  if (!e->verify) {
+    if (lik == MCGPU_ROSENBROCK2) return fail(e, MCGPU_EINVAL, "Rosenbrock2 couples neighbouring chains of a batch (rosenbrock.cc:32-33); available in VERIFY mode and mcgpu_loglik only");
+    if (!fast::steps_supported(lik, e->d)) return fail(e, MCGPU_EINVAL, "no step kernel instantiated for this (likelihood, nparam)");
+  }
+  if (e->lik_dev) { cudaFree(e->lik_dev); e->lik_dev = nullptr; }
+  if (!dev.empty()) {
+    CK(cudaMalloc((void**)&e->lik_dev, dev.size() * 8));
+    CK(cudaMemcpyAsync(e->lik_dev, dev.data(), dev.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  e->lik = lik; e->lik_k = K;
+  return MCGPU_OK;
+}
+
+int mcgpu_set_covariance(mcgpu_engine *e, const double *incov)
+{
+  if (!e) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  const int d = e->d;
+  std::vector<double> cov((size_t)d * d, 0.0);
+  if (incov) std::copy(incov, incov + (size_t)d * d, cov.begin());     // mcpar.cc:457-459
+  else for (int i = 0; i < d; ++i) cov[(size_t)i * (d + 1)] = 1.0;      // :460-467
+  (void)cholesky_lower(d, cov.data());                                  // :480 (info unchecked there too)
+  const int copies = e->verify ? e->Rl : 1;
+  for (int r = 0; r < copies; ++r)
+    CK(cudaMemcpyAsync(e->factor + (size_t)r * d * d, cov.data(), cov.size() * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->have_factor = true;
+  return MCGPU_OK;
+}
+
+int mcgpu_set_state(mcgpu_engine *e, const double *pinit)
+{
+  if (!e || !pinit) return MCGPU_EINVAL;
+  if (e->lik < 0) return fail(e, MCGPU_ESTATE, "set_likelihood first");
+  DeviceGuard g(e->dev);
+  const int d = e->d;
+  if (e->verify) {
+    CK(cudaMemcpyAsync(e->x, pinit, (size_t)e->C * d * 8, cudaMemcpyHostToDevice, e->stream));
+    // L(nchain, pvals, lylast) per rank batch (mcpar.cc:53)
+    LikSpec L; L.lik = e->lik; L.d = d; L.k = e->lik_k; memcpy(L.lp, e->lp, sizeof L.lp); L.dev = e->lik_dev;
+    for (int r = 0; r < e->Rl; ++r) {
+      ++e->launches;
+      CK(exact::launch_loglik_aos(L, e->x + (size_t)r * e->Cr * d, e->ly + (size_t)r * e->Cr, e->Cr, e->stream));
+    }
+  } else {
+    double *tmp = nullptr;
+    CK(cudaMallocAsync((void**)&tmp, (size_t)e->C * d * 8, e->stream));
+    CK(cudaMemcpyAsync(tmp, pinit, (size_t)e->C * d * 8, cudaMemcpyHostToDevice, e->stream));
+    transpose_aos_to_soa<<<(unsigned)((e->C + 255) / 256), 256, 0, e->stream>>>(tmp, e->x, e->C, e->ld, d);
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(tmp, e->stream));
+    StepParams p; fill_step_params(e, p);
+    e->launches += 2;
+    CK((e->replay_local ? exact::launch_init_loglik : fast::launch_init_loglik)(e->lik, d, p, e->stream));
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  e->have_state = true; e->burn_done = 0; e->t_main = 0; e->sampling = false; e->irate = 50;
+  return MCGPU_OK;
+}
+
+int mcgpu_set_streams(mcgpu_engine *e, int local_rank, const double *Z, size_t nz, const double *U, size_t nu,
+                      const int32_t *I, size_t ni)
+{
+  if (!e) return MCGPU_EINVAL;
+  if (!e->verify && !e->replay_local) return fail(e, MCGPU_ESTATE, "streams are only consumed in VERIFY / REPLAY_LOCAL mode");
+  if (local_rank < 0 || local_rank >= (int)e->host_streams.size()) return fail(e, MCGPU_EINVAL, "local_rank out of range");
+  StreamSet &s = e->host_streams[local_rank];
+  s.Z.assign(Z, Z + (Z ? nz : 0)); s.U.assign(U, U + (U ? nu : 0)); s.I.assign(I, I + (I ? ni : 0));
+  e->streams_dirty = true;
+  return MCGPU_OK;
+}
+
+static int ready_to_step(mcgpu_engine *e)
+{
+  if (!e->have_state) return fail(e, MCGPU_ESTATE, "set_state first");
+  if (!e->have_factor) { int rc = mcgpu_set_covariance(e, nullptr); if (rc) return rc; }
+  if (e->verify || e->replay_local) { int rc = upload_streams(e); if (rc) return rc; }
+  return 0;
+}
+
+// advance the burn-in by at most nmax steps without crossing a tuning boundary
+static int burnin_some(mcgpu_engine *e, int nmax, int *ndone)
+{
+  *ndone = 0;
+  if (nmax <= 0) return 0;
+  if (e->tune_pending) return fail(e, MCGPU_ESTATE, "a tuning boundary is pending: call mcgpu_tune");
+  const long long boundary = (long long)e->irate + 2;     // tune after step index irate+1 (isamp > irate, mcpar.cc:78)
+  const int n = (int)std::min<long long>(nmax, boundary - e->burn_done);
+  StepParams p; fill_step_params(e, p);
+  p.counts = e->counts; p.step0 = (uint32_t)e->burn_done; p.nsteps = n; p.t0 = 0;
+  CK(launch_steps_any(e, false, p));
+  e->burn_done += n; *ndone = n;
+  if (e->burn_done == boundary) e->tune_pending = true;
+  return 0;
+}
+
+int mcgpu_tune(mcgpu_engine *e)
+{
+  if (!e) return MCGPU_EINVAL;
+  if (!e->tune_pending) return MCGPU_OK;
+  DeviceGuard g(e->dev);
+  ++e->launches;
+  CK(fast::launch_tune(e->counts, e->counts + 2, e->factor, e->d * e->d, e->cfg.armin, e->cfg.armax, e->cfg.dfac, e->cfg.ifac, e->stream));
+  e->irate += 50; e->tune_pending = false;
+  return MCGPU_OK;
+}
+
+int mcgpu_burnin_some(mcgpu_engine *e, int nmax, int *ndone, int *tune_pending)
+{
+  if (!e || !ndone) return MCGPU_EINVAL;
+  if (e->verify) return fail(e, MCGPU_EINVAL, "VERIFY mode tunes inside the kernel: use mcgpu_burnin");
+  DeviceGuard g(e->dev);
+  int rc = ready_to_step(e); if (rc) return rc;
+  rc = burnin_some(e, nmax, ndone);
+  if (tune_pending) *tune_pending = e->tune_pending;
+  return rc;
+}
+
+int mcgpu_burnin(mcgpu_engine *e, int nburn)
+{
+  if (!e || nburn < 0) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  int rc = ready_to_step(e); if (rc) return rc;
+  if (e->sampling) return fail(e, MCGPU_ESTATE, "burn-in after sampling has begun");
+  timer_begin(e);
+  if (e->verify) {
+    if (nburn > 0) {
+      VerifyParams p; fill_verify_params(e, p);
+      p.phase = 0; p.s0 = (int)e->burn_done; p.nsteps = nburn; p.trace_base = (int)e->burn_done;
+      ++e->launches;
+      CK(exact::launch_verify(p, e->Rl, e->stream));
+      e->burn_done += nburn;
+    }
+  } else {
+    if (e->sharded) return fail(e, MCGPU_ESTATE, "sharded engines burn in with mcgpu_burnin_some + all-reduce + mcgpu_tune");
+    int left = nburn;
+    while (left > 0) {
+      int done = 0;
+      rc = burnin_some(e, left, &done); if (rc) return rc;
+      left -= done;
+      if (e->tune_pending) { rc = mcgpu_tune(e); if (rc) return rc; }
+    }
+  }
+  timer_end(e);
+  e->nburn_total = (int)e->burn_done;
+  if (e->verify || e->replay_local) return check_overrun(e);
+  return MCGPU_OK;
+}
+
+int mcgpu_sample_begin(mcgpu_engine *e, int nsamp)
+{
+  if (!e || nsamp < 0) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  int rc = ready_to_step(e); if (rc) return rc;
+  const int d = e->d;
+  e->nsamp = nsamp; e->t_main = 0; e->sampling = true; e->exchange_pending = false; e->hist_kept = 0;
+  e->nburn_total = (int)e->burn_done;
+  const long long need = (nsamp + e->cfg.thin - 1) / e->cfg.thin;
+  if (e->hist && need > e->hist_cap) return fail(e, MCGPU_EINVAL, "history_steps too small for nsamp/thin");
+  // mu = 0, psum2 = FPEPS (mcpar.cc:100-103)
+  const size_t n = e->verify ? (size_t)e->C * d : (size_t)d * e->ld;
+  std::vector<double> eps(n, MCGPU_FPEPS);
+  CK(cudaMemsetAsync(e->mu, 0, n * 8, e->stream));
+  CK(cudaMemcpyAsync(e->ps, eps.data(), n * 8, cudaMemcpyHostToDevice, e->stream));
+  if (!e->verify) CK(cudaMemsetAsync(e->counts + 4, 0, 16, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->verify && e->cfg.trace && !e->tr_accept) {
+    e->trace_cap = (int)(e->burn_done + nsamp);
+    const size_t T = (size_t)e->trace_cap * e->Rl;
+    rc = dalloc(e, &e->tr_accept, T * e->Cr); if (rc) return rc;
+    rc = dalloc(e, &e->tr_trial_ly, T * e->Cr); if (rc) return rc;
+    rc = dalloc(e, &e->tr_trial_p, T * e->Cr * d); if (rc) return rc;
+    rc = dalloc(e, &e->tr_cfac, T * e->Cr); if (rc) return rc;
+    rc = dalloc(e, &e->tr_remote, T); if (rc) return rc;
+    rc = dalloc(e, &e->tr_iters, T); if (rc) return rc;
+  }
+  return MCGPU_OK;
+}
+
+int mcgpu_sample(mcgpu_engine *e, int nsteps)
+{
+  if (!e || nsteps < 0) return MCGPU_EINVAL;
+  if (!e->sampling) return fail(e, MCGPU_ESTATE, "sample_begin first");
+  if (e->t_main + nsteps > e->nsamp) return fail(e, MCGPU_EINVAL, "more steps than sample_begin announced");
+  DeviceGuard g(e->dev);
+  const int sync = e->cfg.sync;
+  timer_begin(e);
+  int left = nsteps;
+  while (left > 0) {
+    if (e->exchange_pending) return fail(e, MCGPU_ESTATE, "exchange pending: call mcgpu_exchange_begin/end at every multiple of sync");
+    const long long to_boundary = sync - (e->t_main % sync);
+    const int n = (int)std::min<long long>(left, to_boundary);
+    if (e->verify) {
+      VerifyParams p; fill_verify_params(e, p);
+      p.phase = 1; p.s0 = (int)e->t_main; p.nsteps = n; p.trace_base = (int)(e->nburn_total + e->t_main);
+      p.refresh = (e->R > 1) && (e->t_main % sync == 0);
+      p.publish = 1;
+      p.snap_cur = e->snap[e->snap_cur]; p.snap_next = e->snap[e->snap_cur ^ 1];
+      ++e->launches;
+      CK(exact::launch_verify(p, e->Rl, e->stream));
+    } else {
+      StepParams p; fill_step_params(e, p);
+      p.counts = e->counts + 4;
+      p.step0 = (uint32_t)(e->nburn_total + e->t_main); p.nsteps = n; p.t0 = (int)e->t_main;
+      p.pool_cur = e->pool[e->pool_cur]; p.pool_next = e->pool[e->pool_cur ^ 1];
+      p.hist = e->hist; p.hist_step0 = 0;
+      CK(launch_steps_any(e, true, p));
+    }
+    e->t_main += n; left -= n;
+    e->hist_kept = (e->t_main + e->cfg.thin - 1) / e->cfg.thin;
+    if (e->t_main % sync == 0) {
+      if (e->sharded) e->exchange_pending = true;          // caller all-gathers the published slices
+      else if (e->verify) e->snap_cur ^= 1;
+      else e->pool_cur ^= 1;
+    }
+  }
+  timer_end(e);
+  if ((e->verify || e->replay_local) && e->t_main == e->nsamp) return check_overrun(e);
+  return MCGPU_OK;
+}
+
+int mcgpu_exchange_begin(mcgpu_engine *e, void **dev_buffer, size_t *total_bytes, size_t *own_offset, size_t *own_bytes)
+{
+  if (!e || !dev_buffer) return MCGPU_EINVAL;
+  const int d = e->d;
+  if (e->verify) {
+    *dev_buffer = e->snap[e->snap_cur ^ 1];
+    if (total_bytes) *total_bytes = (size_t)2 * e->N * d * 8;
+    if (own_offset) *own_offset = (size_t)2 * e->cfg.chain0 * d * 8;
+    if (own_bytes) *own_bytes = (size_t)2 * e->C * d * 8;
+  } else {
+    // own pool slots: s with chain0 <= s*stride < chain0 + C
+    const long long s0 = (e->cfg.chain0 + e->stride - 1) / e->stride;
+    const long long s1 = std::min<long long>(e->M, (e->cfg.chain0 + e->C + e->stride - 1) / e->stride);
+    *dev_buffer = e->pool[e->pool_cur ^ 1];
+    if (total_bytes) *total_bytes = (size_t)e->M * d * 16;
+    if (own_offset) *own_offset = (size_t)s0 * d * 16;
+    if (own_bytes) *own_bytes = (size_t)std::max<long long>(0, s1 - s0) * d * 16;
+  }
+  return MCGPU_OK;
+}
+
+int mcgpu_exchange_end(mcgpu_engine *e)
+{
+  if (!e) return MCGPU_EINVAL;
+  if (!e->exchange_pending) return MCGPU_OK;
+  if (e->verify) e->snap_cur ^= 1; else e->pool_cur ^= 1;
+  e->exchange_pending = false;
+  return MCGPU_OK;
+}
+
+int mcgpu_tuning_counters(mcgpu_engine *e, void **dev_counts)
+{
+  if (!e || !dev_counts) return MCGPU_EINVAL;
+  *dev_counts = e->counts;
+  return MCGPU_OK;
+}
+
+int mcgpu_synchronize(mcgpu_engine *e)
+{
+  if (!e) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  CK(cudaStreamSynchronize(e->stream));
+  return MCGPU_OK;
+}
+
+int mcgpu_get_state(mcgpu_engine *e, double *pvals, double *lylast, double *mu, double *sig, double *psum2)
+{
+  if (!e) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  const int d = e->d;
+  const size_t nb = (size_t)e->C * d * 8;
+  if (e->verify) {
+    if (pvals) CK(cudaMemcpyAsync(pvals, e->x, nb, cudaMemcpyDeviceToHost, e->stream));
+    if (mu) CK(cudaMemcpyAsync(mu, e->mu, nb, cudaMemcpyDeviceToHost, e->stream));
+    if (sig) CK(cudaMemcpyAsync(sig, e->sig, nb, cudaMemcpyDeviceToHost, e->stream));
+    if (psum2) CK(cudaMemcpyAsync(psum2, e->ps, nb, cudaMemcpyDeviceToHost, e->stream));
+  } else {
+    double *tmp = nullptr;
+    CK(cudaMallocAsync((void**)&tmp, nb, e->stream));
+    const unsigned grid = (unsigned)((e->C + 255) / 256);
+    struct { double *dst; const double *src; double scale; } jobs[4] = {
+      {pvals, e->x, 1.0}, {mu, e->mu, 1.0}, {psum2, e->ps, 1.0},
+      {sig, e->ps, e->t_main > 0 ? 1.0 / (double)e->t_main : 0.0}};   // sig = psum2 * winv (mcpar.cc:202)
+    for (auto &jb : jobs) {
+      if (!jb.dst) continue;
+      transpose_soa_to_aos<<<grid, 256, 0, e->stream>>>(jb.src, tmp, e->C, e->ld, d, jb.scale);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(jb.dst, tmp, nb, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaFreeAsync(tmp, e->stream));
+  }
+  if (lylast) CK(cudaMemcpyAsync(lylast, e->ly, (size_t)e->C * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return MCGPU_OK;
+}
+
+int mcgpu_get_factor(mcgpu_engine *e, int local_rank, double *factor)
+{
+  if (!e || !factor) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  const int nr = e->verify ? e->Rl : 1;
+  if (local_rank < 0 || local_rank >= nr) return fail(e, MCGPU_EINVAL, "local_rank out of range");
+  CK(cudaMemcpyAsync(factor, e->factor + (size_t)local_rank * e->d * e->d, (size_t)e->d * e->d * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return MCGPU_OK;
+}
+
+int mcgpu_get_musig(mcgpu_engine *e, int local_rank, double *musig)
+{
+  if (!e || !musig) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  if (e->verify) {
+    if (local_rank < 0 || local_rank >= e->Rl) return fail(e, MCGPU_EINVAL, "local_rank out of range");
+    const size_t nm = (size_t)2 * e->N * e->d;
+    CK(cudaMemcpyAsync(musig, e->musig + (size_t)local_rank * nm, nm * 8, cudaMemcpyDeviceToHost, e->stream));
+  } else {
+    CK(cudaMemcpyAsync(musig, e->pool[e->pool_cur], (size_t)e->M * e->d * 16, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return MCGPU_OK;
+}
+
+int mcgpu_get_trace(mcgpu_engine *e, int local_rank, uint8_t *accept, double *trial_ly, double *trial_p, double *cfac,
+                    uint8_t *remote, int32_t *iters, int64_t *cursors)
+{
+  if (!e) return MCGPU_EINVAL;
+  if (!e->verify) return fail(e, MCGPU_ESTATE, "traces exist in VERIFY mode only");
+  if (local_rank < 0 || local_rank >= e->Rl) return fail(e, MCGPU_EINVAL, "local_rank out of range");
+  DeviceGuard g(e->dev);
+  const size_t T = (size_t)e->trace_cap, C = (size_t)e->Cr, r = (size_t)local_rank;
+  if ((accept || trial_ly || trial_p || cfac || remote || iters) && !e->tr_accept) return fail(e, MCGPU_ESTATE, "engine was created with trace = 0");
+  if (accept) CK(cudaMemcpyAsync(accept, e->tr_accept + r * T * C, T * C, cudaMemcpyDeviceToHost, e->stream));
+  if (trial_ly) CK(cudaMemcpyAsync(trial_ly, e->tr_trial_ly + r * T * C, T * C * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (trial_p) CK(cudaMemcpyAsync(trial_p, e->tr_trial_p + r * T * C * e->d, T * C * e->d * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (cfac) CK(cudaMemcpyAsync(cfac, e->tr_cfac + r * T * C, T * C * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (remote) CK(cudaMemcpyAsync(remote, e->tr_remote + r * T, T, cudaMemcpyDeviceToHost, e->stream));
+  if (iters) CK(cudaMemcpyAsync(iters, e->tr_iters + r * T, T * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (cursors) CK(cudaMemcpyAsync(cursors, e->cursors + r * 3, 24, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return MCGPU_OK;
+}
+
+int mcgpu_history_read(mcgpu_engine *e, int64_t first_step, int64_t count, double *rows)
+{
+  if (!e || !rows || first_step < 0 || count < 0) return MCGPU_EINVAL;
+  if (!e->hist) return fail(e, MCGPU_ESTATE, "engine was created with history_steps = 0");
+  if (first_step + count > e->hist_kept) return fail(e, MCGPU_EINVAL, "history range not yet produced");
+  DeviceGuard g(e->dev);
+  const size_t row_bytes = (size_t)(e->d + 1) * 8;
+  const size_t total = (size_t)count * e->C * row_bytes;
+  const char *src = (const char*)e->hist + (size_t)first_step * e->C * row_bytes;
+  if (total == 0) return MCGPU_OK;
+  // drain on the side stream through two pinned staging buffers so the PCIe copy of
+  // chunk k overlaps the host memcpy of chunk k-1
+  const size_t chunk = (size_t)32 << 20;
+  if (!e->pin[0]) {
+    for (int i = 0; i < 2; ++i) { CK(cudaMallocHost((void**)&e->pin[i], chunk)); CK(cudaEventCreateWithFlags(&e->pin_ev[i], cudaEventDisableTiming)); }
+    e->pin_bytes = chunk;
+  }
+  cudaEvent_t produced; CK(cudaEventCreateWithFlags(&produced, cudaEventDisableTiming));
+  CK(cudaEventRecord(produced, e->stream));
+  CK(cudaStreamWaitEvent(e->side, produced, 0));
+  CK(cudaEventDestroy(produced));
+  const size_t nchunks = (total + chunk - 1) / chunk;
+  for (size_t k = 0; k <= nchunks; ++k) {
+    if (k < nchunks) {
+      const size_t off = k * chunk, nb = std::min(chunk, total - off);
+      if (k >= 2) CK(cudaEventSynchronize(e->pin_ev[k & 1]));   // buffer consumed below before reuse
+      CK(cudaMemcpyAsync(e->pin[k & 1], src + off, nb, cudaMemcpyDeviceToHost, e->side));
+      CK(cudaEventRecord(e->pin_ev[k & 1], e->side));
+    }
+    if (k >= 1) {
+      const size_t pk = k - 1, off = pk * chunk, nb = std::min(chunk, total - off);
+      CK(cudaEventSynchronize(e->pin_ev[pk & 1]));
+      memcpy((char*)rows + off, e->pin[pk & 1], nb);
+    }
+  }
+  return MCGPU_OK;
+}
+
+int mcgpu_history_maxlike(mcgpu_engine *e, double *out)
+{
+  if (!e || !out) return MCGPU_EINVAL;
+  if (!e->hist) return fail(e, MCGPU_ESTATE, "engine was created with history_steps = 0");
+  DeviceGuard g(e->dev);
+  const long long nrows = e->hist_kept * e->C;
+  if (nrows == 0) return fail(e, MCGPU_ESTATE, "history is empty");
+  const int nb = 296;
+  double *bv = nullptr; long long *br = nullptr;
+  CK(cudaMallocAsync((void**)&bv, nb * 8, e->stream)); CK(cudaMallocAsync((void**)&br, nb * 8, e->stream));
+  ++e->launches;
+  argmax_rows_kernel<<<nb, 256, 0, e->stream>>>(e->hist, nrows, e->d + 1, bv, br);
+  CK(cudaGetLastError());
+  std::vector<double> hv(nb); std::vector<long long> hr(nb);
+  CK(cudaMemcpyAsync(hv.data(), bv, nb * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(hr.data(), br, nb * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaFreeAsync(bv, e->stream)); CK(cudaFreeAsync(br, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  long long best = -1; double val = -INFINITY;
+  for (int i = 0; i < nb; ++i)
+    if (hr[i] >= 0 && (best < 0 || hv[i] > val || (hv[i] == val && hr[i] < best))) { best = hr[i]; val = hv[i]; }
+  if (best < 0) return fail(e, MCGPU_ESTATE, "history holds no finite log-likelihood");
+  CK(cudaMemcpy(out, e->hist + (size_t)best * (e->d + 1), (size_t)(e->d + 1) * 8, cudaMemcpyDeviceToHost));
+  return MCGPU_OK;
+}
+
+int mcgpu_history_moments(mcgpu_engine *e, double *mean, double *cov)
+{
+  if (!e || !mean || !cov) return MCGPU_EINVAL;
+  if (!e->hist) return fail(e, MCGPU_ESTATE, "engine was created with history_steps = 0");
+  DeviceGuard g(e->dev);
+  const int d = e->d; const int nq = d + d * (d + 1) / 2;
+  const long long nrows = e->hist_kept * e->C;
+  if (nrows == 0) return fail(e, MCGPU_ESTATE, "history is empty");
+  double *acc = nullptr;
+  CK(cudaMallocAsync((void**)&acc, nq * 8, e->stream));
+  CK(cudaMemsetAsync(acc, 0, nq * 8, e->stream));
+  ++e->launches;
+  moments_kernel<<<dim3(592, nq), 256, 0, e->stream>>>(e->hist, nrows, d, acc);
+  CK(cudaGetLastError());
+  std::vector<double> h(nq);
+  CK(cudaMemcpyAsync(h.data(), acc, nq * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaFreeAsync(acc, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const double n = (double)nrows;
+  for (int i = 0; i < d; ++i) mean[i] = h[i] / n;
+  int q = d;
+  for (int i = 0; i < d; ++i)
+    for (int j = i; j < d; ++j, ++q) { const double c = h[q] / n - mean[i] * mean[j]; cov[i * d + j] = c; cov[j * d + i] = c; }
+  return MCGPU_OK;
+}
+
+int mcgpu_get_stats(mcgpu_engine *e, mcgpu_stats *out)
+{
+  if (!e || !out) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  CK(cudaStreamSynchronize(e->stream));
+  timers_resolve(e);
+  memset(out, 0, sizeof *out);
+  out->burn_steps = e->burn_done; out->main_steps = e->t_main; out->kernel_launches = e->launches;
+  out->history_rows = e->hist_kept * e->C; out->device_ms = e->ms_accum;
+  unsigned long long h[6] = {0};
+  if (e->verify) {
+    CK(cudaMemcpy(h, e->rstats, 32, cudaMemcpyDeviceToHost));
+    out->remote_steps = (int64_t)h[0]; out->remote_iterations = (int64_t)h[1];
+    out->accepted = (int64_t)h[2]; out->tried = (int64_t)h[3];
+  } else {
+    CK(cudaMemcpy(h, e->counts, 48, cudaMemcpyDeviceToHost));
+    out->accepted = (int64_t)h[4]; out->tried = (int64_t)h[5];
+  }
+  return MCGPU_OK;
+}
+
+int mcgpu_device_ptr(mcgpu_engine *e, int which, void **ptr, size_t *bytes)
+{
+  if (!e || !ptr) return MCGPU_EINVAL;
+  const size_t st = e->verify ? (size_t)e->C * e->d * 8 : (size_t)e->d * e->ld * 8;
+  size_t nb = 0;
+  switch (which) {
+    case 0: *ptr = e->x; nb = st; break;
+    case 1: *ptr = e->ly; nb = (size_t)(e->verify ? e->C : e->ld) * 8; break;
+    case 2: *ptr = e->mu; nb = st; break;
+    case 3: *ptr = e->ps; nb = st; break;
+    case 4: *ptr = e->hist; nb = (size_t)e->hist_cap * e->C * (e->d + 1) * 8; break;
+    case 5: *ptr = e->verify ? e->snap[e->snap_cur] : e->pool[e->pool_cur]; nb = e->verify ? (size_t)2 * e->N * e->d * 8 : (size_t)e->M * e->d * 16; break;
+    default: return fail(e, MCGPU_EINVAL, "unknown buffer id");
+  }
+  if (bytes) *bytes = nb;
+  return MCGPU_OK;
+}
+
+// ---- stand-alone entry points (no engine) -----------------------------------
+#define CK0(call) do { cudaError_t _s = (call); if (_s != cudaSuccess) { g_create_err = std::string(#call) + " -> " + cudaGetErrorString(_s); return MCGPU_ECUDA; } } while (0)
+
+int mcgpu_loglik(int device, int lik, int nparam, const double *par, int npar, int npset, const double *x, double *y)
+{
+  if (!x || !y || npset < 0) return fail(nullptr, MCGPU_EINVAL, "null argument");
+  if (mcgpu_device_count() <= device || device < 0) return fail(nullptr, MCGPU_ENODEVICE, "no usable CUDA device (this engine has no CPU path)");
+  if (npset == 0) return MCGPU_OK;
+  DeviceGuard g(device);
+  LikSpec L; memset(&L, 0, sizeof L);
+  std::vector<double> dev; std::string err;
+  int rc = prepare_lik(lik, nparam, par, npar, L.lp, dev, L.k, err);
+  if (rc) { g_create_err = err; return rc; }
+  L.lik = lik; L.d = nparam;
+  double *dx = nullptr, *dy = nullptr, *dp = nullptr;
+  CK0(cudaMalloc((void**)&dx, (size_t)npset * nparam * 8)); CK0(cudaMalloc((void**)&dy, (size_t)npset * 8));
+  if (!dev.empty()) { CK0(cudaMalloc((void**)&dp, dev.size() * 8)); CK0(cudaMemcpy(dp, dev.data(), dev.size() * 8, cudaMemcpyHostToDevice)); }
+  L.dev = dp;
+  CK0(cudaMemcpy(dx, x, (size_t)npset * nparam * 8, cudaMemcpyHostToDevice));
+  CK0(exact::launch_loglik_aos(L, dx, dy, npset, 0));
+  CK0(cudaMemcpy(y, dy, (size_t)npset * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dy); if (dp) cudaFree(dp);
+  return MCGPU_OK;
+}
+
+int mcgpu_qriguess(int device, int rank, int npset, int nparam, const double *plo, const double *phi, double *pout)
+{
+  if (!plo || !phi || !pout || npset < 0 || rank < 0) return fail(nullptr, MCGPU_EINVAL, "bad argument");
+  if (nparam < 1 || nparam > 16) return fail(nullptr, MCGPU_EINVAL, "Sobol table covers 1..16 dimensions");
+  if (mcgpu_device_count() <= device || device < 0) return fail(nullptr, MCGPU_ENODEVICE, "no usable CUDA device (this engine has no CPU path)");
+  const int ntot = npset * nparam;                                  // mcutil.cc:19
+  if (ntot == 0) return MCGPU_OK;
+  DeviceGuard g(device);
+  std::vector<uint32_t> dirs((size_t)nparam * 32);
+  for (int k = 0; k < nparam; ++k) sobol_dirs(k, &dirs[(size_t)k * 32]);
+  uint32_t *dd = nullptr; double *dlo = nullptr, *dhi = nullptr, *dout = nullptr;
+  CK0(cudaMalloc((void**)&dd, dirs.size() * 4)); CK0(cudaMalloc((void**)&dlo, nparam * 8));
+  CK0(cudaMalloc((void**)&dhi, nparam * 8)); CK0(cudaMalloc((void**)&dout, (size_t)ntot * 8));
+  CK0(cudaMemcpy(dd, dirs.data(), dirs.size() * 4, cudaMemcpyHostToDevice));
+  CK0(cudaMemcpy(dlo, plo, nparam * 8, cudaMemcpyHostToDevice)); CK0(cudaMemcpy(dhi, phi, nparam * 8, cudaMemcpyHostToDevice));
+  const unsigned long long first = rank > 0 ? (unsigned long long)rank * (unsigned long long)ntot : 0ull;   // :22-23
+  sobol_box_kernel<<<(ntot + 255) / 256, 256>>>(dd, nparam, first, ntot, dlo, dhi, dout);
+  CK0(cudaGetLastError());
+  CK0(cudaMemcpy(pout, dout, (size_t)ntot * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dd); cudaFree(dlo); cudaFree(dhi); cudaFree(dout);
+  return MCGPU_OK;
+}
+
+int mcgpu_measure_fp64_peak(int device, double *tflops)
+{
+  if (!tflops) return MCGPU_EINVAL;
+  if (mcgpu_device_count() <= device || device < 0) return fail(nullptr, MCGPU_ENODEVICE, "no usable CUDA device");
+  DeviceGuard g(device);
+  cudaDeviceProp prop; CK0(cudaGetDeviceProperties(&prop, device));
+  double *out = nullptr; CK0(cudaMalloc((void**)&out, 8));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(a);
+    dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(b);
+    CK0(cudaEventSynchronize(b));
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    const double tf = (double)blocks * threads * (double)iters * 8 * 2 / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+  *tflops = best;
+  return MCGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// mcgpu_device.cuh -- device-side building blocks shared by the step kernels.
+//
+// Replaces, on the device, what the reference gets from MKL VSL on the host
+// (vsRngUniform / viRngUniform / vsRngGaussianMV; call sites src/mcpar.cc:63,146,
+// 163,306,337,348,401): a counter-based Philox4x32-10 generator keyed on
+// (global chain id, step, draw slot), and a replay reader for supplied streams.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MCGPU_FPEPS 1.0e-14          // src/mcpar.cc:15
+#define MCGPU_SLOT_ACCEPT 0x10000000u
+#define MCGPU_SLOT_REMOTE 0x40000000u
+#define MCGPU_MAX_D_REG 16           // thread-per-chain kernels keep the state in registers up to this d
+#define MCGPU_MAX_D 64
+
+namespace mcgpu {
+
+struct Words { uint32_t w0, w1, w2, w3; };
+
+// Philox4x32-10 (Salmon et al., SC'11).  10 rounds of two 32x32->64 multiplies.
+__device__ __forceinline__ Words philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  Words w; w.w0 = c0; w.w1 = c1; w.w2 = c2; w.w3 = c3;
+  return w;
+}
+
+// 53-bit uniform in [0,1) from two words
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo)
+{
+  const unsigned long long b = ((unsigned long long)hi << 32) | lo;
+  return (double)(b >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// Box-Muller pair, MKL BOXMULLER2 convention: z0 = r sin(2 pi u2), z1 = r cos(2 pi u2)
+__device__ __forceinline__ void normal_pair(const Words &w, double &z0, double &z1)
+{
+  const double u1 = u53(w.w0, w.w1), u2 = u53(w.w2, w.w3);
+  const double r = sqrt(-2.0 * log(1.0 - u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z0 = r * s; z1 = r * c;
+}
+
+// One launch worth of arguments for the fused step kernels.
+struct StepParams {
+  // chain state, structure-of-arrays over the hosted chains: x[i*ld + j] etc.
+  double *x, *ly, *mu, *ps;
+  long long C, ld, chain0;
+  const double *factor;            // [d*d] row-major lower Cholesky factor (scaled by tuning)
+  unsigned long long *counts;      // {accepted, tried} of the current tuning / stats window
+  // schedule
+  uint32_t key0, key1;             // Philox key = seed
+  uint32_t step0;                  // global step index of the first step of this launch
+  int nsteps;                      // steps in this launch
+  int t0;                          // main-phase index of the first step (main kernels)
+  int nburn_total;                 // replay offsets: burn-in length of the run
+  int sync, coin_group;
+  double pl;
+  // remote-proposal pool: [pool_m][d][2] (mu, sigma^2); slot s is global chain s*pool_stride
+  const double *pool_cur; double *pool_next;
+  int pool_m; long long pool_stride;
+  int pool_in_smem;
+  // sample history: rows (p..., logL), kept step major, then hosted chain
+  double *hist; int thin; long long hist_step0;   // kept-step index base of the history buffer
+  // replay-local streams
+  const double *Z, *U; long long nz, nu; int *overrun;
+  // likelihood parameters
+  double lp[8]; const double *lik_dev; int lik_k;
+};
+
+// runtime-dispatched likelihood description (verification mode, batched evaluation)
+struct LikSpec { int lik, d, k; double lp[8]; const double *dev; };
+
+// One launch worth of arguments for the verification-mode kernel.
+struct VerifyParams {
+  int d, C, N, rank0, nsamp;
+  LikSpec L;
+  double *pvals, *ptrial, *ly, *mu, *sig, *ps, *mutrial, *sigtrial;   // [Rl][C*d] / [Rl][C]
+  double *factor;                    // [Rl][d*d]
+  double *musig;                     // [Rl][2*N*d]  each rank's private musigall
+  const double *snap_cur; double *snap_next;      // [2*N*d] what the all-gather delivers
+  const double *Z, *U; const int *I;
+  const long long *soff;             // [Rl][6] = zoff,zlen,uoff,ulen,ioff,ilen
+  long long *cursors;                // [Rl][3]
+  unsigned long long *counts;        // [Rl][2]
+  int *irate;                        // [Rl]
+  int phase, s0, nsteps, sync, refresh, publish;
+  double pl, armin, armax, dfac, ifac;
+  double *hist;                      // [t][Rl*C][d+1]
+  long long hist_chains;
+  uint8_t *tr_accept; double *tr_trial_ly, *tr_trial_p, *tr_cfac; uint8_t *tr_remote; int *tr_iters;
+  int trace_cap, trace_base;
+  int *overrun;
+  unsigned long long *rstats;        // {remote rank-steps, rejection iterations, accepted(main), tried(main)}
+};
+
+}  // namespace mcgpu

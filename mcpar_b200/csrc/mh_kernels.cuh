@@ -1,0 +1,606 @@
+// mh_kernels.cuh -- the fused Metropolis-Hastings step kernels (sm_100a).
+//
+// Included by two translation units:
+//   mh_fast.cu   (default FMA contraction)           -> namespace mcgpu::fast
+//   mh_exact.cu  (-fmad=false, MCGPU_EXACT_TU)       -> namespace mcgpu::exact
+// The exact unit evaluates every expression operation by operation exactly as the
+// reference's C++ does (src/mcpar.cc, src/rosenbrock.cc), so states and polynomial
+// log-likelihoods are bit-identical to the CPU oracle on shared streams.
+//
+// Kernel 1  mh_steps_kernel<LIK,D,RNG,MAIN>   production path: one thread per chain,
+//           K steps per launch, state in registers; fuses proposal generation
+//           (genLocal mcpar.cc:302-312 / genRemote :315-451), likelihood
+//           (VLFunc, rosenbrock.cc), accept + update (:65-75,:165-175), running
+//           moments (:186-209), publication to the exchange pool (:205-208) and the
+//           sample store (MCout::add, mcout.cc:129-145).
+// Kernel 2  mh_verify_kernel                  verification mode: one CTA per emulated
+//           MPI rank, the reference's lock-step stream protocol.
+#pragma once
+#include "mcgpu_device.cuh"
+#include "../../include/mcgpu.h"
+
+namespace mcgpu {
+namespace MCGPU_NS {
+
+enum { RNG_PHILOX = 0, RNG_REPLAY = 1 };
+
+// ----------------------------------------------------------------------------
+// likelihood functors (device side of the VLFunc plugin surface)
+// ----------------------------------------------------------------------------
+template <int LIK, int D> struct Lik;
+
+// Rosenbrock1::operator(), rosenbrock.cc:4-21: non-overlapping pairs
+template <int D> struct Lik<MCGPU_ROSENBROCK1, D> {
+  static __device__ __forceinline__ double eval(const double (&x)[D], const StepParams &) {
+    double y = 0.0;
+#pragma unroll
+    for (int i = 0; i + 1 < D; i += 2) {
+      const double t1 = 1 - x[i];
+      const double t2 = x[i + 1] - x[i] * x[i];
+      y -= t1 * t1 + 100.0 * t2 * t2;
+    }
+    return y;
+  }
+};
+
+// Gaussian::operator(), rosenbrock.cc:44-61; lp = {mu0, mu1, 1/sig2_0, 1/sig2_1}
+template <> struct Lik<MCGPU_GAUSSIAN, 2> {
+  static __device__ __forceinline__ double eval(const double (&x)[2], const StepParams &p) {
+    double y = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double arg = x[k] - p.lp[k];
+      y -= 0.5 * arg * arg * p.lp[2 + k];
+    }
+    return y;
+  }
+};
+
+// DualGaussian::operator(), rosenbrock.cc:63-78; lp = {w}.  No log-sum-exp guard,
+// as in the reference: far from both modes this is log(0) = -inf.
+template <> struct Lik<MCGPU_DUALGAUSSIAN, 2> {
+  static __device__ __forceinline__ double eval(const double (&x)[2], const StepParams &p) {
+    const double arg1 = 0.5 * (x[0] * x[0] + x[1] * x[1]);
+    const double t2a = x[0] - 5.0, t2b = x[1] - 5.0;
+    const double arg2 = 0.5 * (t2a * t2a + t2b * t2b);
+    return log(p.lp[0] * exp(-arg1) + exp(-arg2));
+  }
+};
+
+// GaussMix (new): log sum_k w_k exp(-1/2 sum_i (x_i-mu_ki)^2/s2_ki)
+// with log-sum-exp.  lik_dev = {mu[K][d], 1/s2[K][d], log w[K]} (prepared on upload).
+template <int D> struct Lik<MCGPU_GAUSSMIX, D> {
+  static __device__ __forceinline__ double eval(const double (&x)[D], const StepParams &p) {
+    const int K = p.lik_k;
+    const double *mu = p.lik_dev, *is2 = mu + (size_t)K * D, *lw = is2 + (size_t)K * D;
+    double m = -INFINITY, s = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double q = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) { const double xm = x[i] - mu[k * D + i]; q += xm * xm * is2[k * D + i]; }
+      const double a = lw[k] - 0.5 * q;
+      if (a > m) { s = s * exp(m - a) + 1.0; m = a; } else s += exp(a - m);
+    }
+    return m + log(s);
+  }
+};
+
+// un-normalised diagonal Gaussian Q(x) of mcpar.cc:367-387 / :424-436
+template <int D>
+__device__ __forceinline__ double q_value(const double *ms, const double (&x)[D]) {
+  double arg = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const double xm = ms[2 * i] - x[i];
+    arg += xm * xm / ms[2 * i + 1];
+  }
+  return exp(-0.5 * arg);
+}
+
+// ----------------------------------------------------------------------------
+// Kernel 1: production path
+// ----------------------------------------------------------------------------
+template <int LIK, int D, int RNGK, bool MAIN>
+__global__ void __launch_bounds__(128)
+mh_steps_kernel(const StepParams p)
+{
+  extern __shared__ double smem[];
+  // smem: [0, D*D) factor | [D*D, D*D+nsteps) 1/pwgt table | pool copy
+  double *sT = smem;
+  double *sW = smem + D * D;
+  const double *pool = p.pool_cur;
+
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = j < p.C;
+  const long long jc = live ? j : p.C - 1;           // idle lanes shadow the last chain, never store
+  const unsigned long long g = (unsigned long long)(p.chain0 + jc);
+  const uint32_t glo = (uint32_t)g, ghi = (uint32_t)(g >> 32);
+  const int lane = threadIdx.x & 31;
+  const int leader = lane & ~(p.coin_group - 1);
+
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) sT[i] = p.factor[i];
+  if (MAIN) {
+    for (int k = threadIdx.x; k < p.nsteps; k += blockDim.x) sW[k] = 1.0 / (double)(p.t0 + k + 1);
+    if (p.pool_in_smem && p.t0 + p.nsteps > p.sync) {
+      double *sP = sW + p.nsteps;
+      for (int i = threadIdx.x; i < p.pool_m * D * 2; i += blockDim.x) sP[i] = p.pool_cur[i];
+      pool = sP;
+    }
+  }
+  __syncthreads();
+
+  double x[D], mu[D], ps[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) x[i] = p.x[i * p.ld + jc];
+  double ly = p.ly[jc];
+  if (MAIN) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) { mu[i] = p.mu[i * p.ld + jc]; ps[i] = p.ps[i * p.ld + jc]; }
+  }
+  unsigned int nacc = 0;
+
+  for (int k = 0; k < p.nsteps; ++k) {
+    const uint32_t step = p.step0 + (uint32_t)k;
+    const int t = p.t0 + k;
+    double u_acc;
+    bool remote = false;
+    long long zoff = 0;
+    if (RNGK == RNG_PHILOX) {
+      const Words wa = philox4x32_10(glo, ghi, step, MCGPU_SLOT_ACCEPT, p.key0, p.key1);
+      u_acc = u53(wa.w0, wa.w1);
+      if (MAIN && t >= p.sync) {                       // one coin per group: the leader's spare words
+        double coin = u53(wa.w2, wa.w3);
+        coin = __shfl_sync(0xffffffffu, coin, leader);
+        remote = !(coin <= p.pl);                      // mcpar.cc:152
+      }
+    } else {
+      // reference stream offsets for an all-local run of ONE rank hosting the C chains
+      const long long s = MAIN ? (long long)p.nburn_total + t : (long long)step;
+      const long long ncoin = (MAIN && t >= p.sync) ? (long long)(t - p.sync + 1) : 0;
+      const long long uoff = s * p.C + ncoin + jc;
+      zoff = (s * p.C + jc) * D;
+      bool bad = uoff >= p.nu || zoff + D > p.nz;
+      u_acc = bad ? 2.0 : p.U[uoff];
+      if (MAIN && t >= p.sync) {
+        const double coin = p.U[s * p.C + ncoin - 1];
+        if (!(coin <= p.pl)) bad = true;               // a remote step cannot be replayed here
+      }
+      if (bad) *p.overrun = 1;
+    }
+
+    double xt[D];
+    double cfac = 1.0;
+    int cpick = 0;                                     // component the accepted remote draw came from
+    if (!remote) {
+      // genLocal: x' = x + T z, T row-major lower (mcpar.cc:302-312)
+      double z[D + 1];
+      if (RNGK == RNG_PHILOX) {
+#pragma unroll
+        for (int q = 0; 2 * q < D; ++q) {
+          const Words w = philox4x32_10(glo, ghi, step, (uint32_t)q, p.key0, p.key1);
+          normal_pair(w, z[2 * q], z[2 * q + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) z[i] = (zoff + D <= p.nz) ? p.Z[zoff + i] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double acc = x[i];
+#pragma unroll
+        for (int q = 0; q <= i; ++q) acc += sT[i * D + q] * z[q];
+        xt[i] = acc;
+      }
+    } else {
+      // genRemote over the pool: rejection-sample max_i Q_i from sum_i Q_i (mcpar.cc:333-443),
+      // each chain running its own loop
+      double qmax = MCGPU_FPEPS;
+      for (uint32_t it = 0;; ++it) {
+        const uint32_t slot = MCGPU_SLOT_REMOTE | (it << 6);
+        const Words w = philox4x32_10(glo, ghi, step, slot, p.key0, p.key1);
+        cpick = (int)__umulhi(w.w0, (uint32_t)p.pool_m);
+        const double u = u53(w.w2, w.w3);
+        double z[D + 1];
+#pragma unroll
+        for (int q = 0; 2 * q < D; ++q) {
+          const Words wz = philox4x32_10(glo, ghi, step, slot | (uint32_t)(1 + q), p.key0, p.key1);
+          normal_pair(wz, z[2 * q], z[2 * q + 1]);
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+          xt[i] = pool[(cpick * D + i) * 2] + sqrt(pool[(cpick * D + i) * 2 + 1]) * z[i];
+        qmax = MCGPU_FPEPS;
+        double qsum = MCGPU_FPEPS;
+        for (int s = 0; s < p.pool_m; ++s) {
+          const double gv = q_value<D>(pool + (size_t)s * D * 2, xt);
+          qsum += gv;
+          qmax = gv > qmax ? gv : qmax;
+        }
+        if (u < qmax / qsum) break;
+        if (it >= (1u << 24) - 1) break;
+      }
+      double qold = 0.0;
+      for (int s = 0; s < p.pool_m; ++s) {
+        const double gv = q_value<D>(pool + (size_t)s * D * 2, x);
+        qold = gv > qold ? gv : qold;
+      }
+      cfac = qold / qmax;                              // mcpar.cc:412-439
+    }
+
+    const double lyt = Lik<LIK, D>::eval(xt, p);
+    double pac = exp(lyt - ly);                        // mcpar.cc:67 / :167
+    if (MAIN) pac *= cfac;
+    const bool a = u_acc < pac;
+    if (a) {
+      ly = lyt;
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = xt[i];
+    }
+    nacc += a ? 1u : 0u;
+
+    if (MAIN) {
+      if (p.hist && live && (t % p.thin) == 0) {       // MCout::add, mcout.cc:129-145
+        double *row = p.hist + (((long long)(t / p.thin) - p.hist_step0) * p.C + j) * (D + 1);
+#pragma unroll
+        for (int i = 0; i < D; ++i) row[i] = x[i];
+        row[D] = ly;
+      }
+      const double pwgt = (double)(t + 1), winv = sW[k];
+      const bool adopt = remote && a;                  // mcpar.cc:190-197
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        if (adopt) {                                   // sigma -> sigma^2 round trip of :346,:447-448
+          const double sd = sqrt(pool[(cpick * D + i) * 2 + 1]);
+          mu[i] = pool[(cpick * D + i) * 2];
+          ps[i] = (sd * sd) * (pwgt - 1.0);
+        }
+        const double delta = x[i] - mu[i];
+        mu[i] += delta * winv;
+        ps[i] += delta * (x[i] - mu[i]);
+      }
+    }
+  }
+
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) p.x[i * p.ld + j] = x[i];
+    p.ly[j] = ly;
+    if (MAIN) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) { p.mu[i * p.ld + j] = mu[i]; p.ps[i * p.ld + j] = ps[i]; }
+      // publish to the next exchange pool (musigall slot rule, mcpar.cc:205-208)
+      const long long gg = p.chain0 + j;
+      if (p.pool_next && gg % p.pool_stride == 0 && gg / p.pool_stride < p.pool_m) {
+        const long long s = gg / p.pool_stride;
+        const double winv = 1.0 / (double)(p.t0 + p.nsteps);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          p.pool_next[(s * D + i) * 2] = mu[i];
+          p.pool_next[(s * D + i) * 2 + 1] = ps[i] * winv;
+        }
+      }
+    }
+  }
+  // acceptance counters of this window
+  unsigned int wacc = live ? nacc : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wacc += __shfl_xor_sync(0xffffffffu, wacc, o);
+  const unsigned int nlive = __popc(__ballot_sync(0xffffffffu, live));
+  if (lane == 0) {
+    atomicAdd(p.counts, (unsigned long long)wacc);
+    atomicAdd(p.counts + 1, (unsigned long long)nlive * (unsigned long long)p.nsteps);
+  }
+}
+
+// Burn-in tuning, mcpar.cc:78-96, applied at a window boundary.
+// counts = {accepted, tried} of the window just finished (already summed over
+// engines when sharded); cum = cumulative pair since the last rescale.
+static __global__ void tune_kernel(unsigned long long *counts, unsigned long long *cum, double *factor,
+                                   int dd, double armin, double armax, double dfac, double ifac)
+{
+  __shared__ double s_f;
+  if (threadIdx.x == 0) {
+    cum[0] += counts[0]; cum[1] += counts[1];
+    counts[0] = 0; counts[1] = 0;
+    const double arate = (double)cum[0] / (double)cum[1];
+    double f = 1.0;
+    if (arate < armin) { f = dfac; cum[0] = cum[1] = 0; }
+    else if (arate > armax) { f = ifac; cum[0] = cum[1] = 0; }
+    s_f = f;
+  }
+  __syncthreads();
+  const double f = s_f;
+  if (f != 1.0)
+    for (int i = threadIdx.x; i < dd; i += blockDim.x) factor[i] *= f;
+}
+
+// initial log-likelihoods L(nchain, pvals, lylast), mcpar.cc:53, on the SoA state
+template <int LIK, int D>
+__global__ void init_loglik_kernel(const StepParams p)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.C) return;
+  double x[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) x[i] = p.x[i * p.ld + j];
+  p.ly[j] = Lik<LIK, D>::eval(x, p);
+}
+
+#ifdef MCGPU_EXACT_TU
+// ----------------------------------------------------------------------------
+// generic (runtime d, runtime likelihood) batched evaluation on AoS data:
+// VLFunc::operator()(npset, x, y) for chain j of a batch of npset
+// ----------------------------------------------------------------------------
+
+static __device__ double loglik_aos(const LikSpec &L, const double *x, int npset, int j)
+{
+  const int d = L.d;
+  const double *xj = x + (size_t)j * d;
+  switch (L.lik) {
+  case MCGPU_ROSENBROCK1: {
+    double y = 0.0;
+    for (int i = 0; i + 1 < d; i += 2) {
+      const double t1 = 1 - xj[i];
+      const double t2 = xj[i + 1] - xj[i] * xj[i];
+      y -= t1 * t1 + 100.0 * t2 * t2;
+    }
+    return y;
+  }
+  case MCGPU_ROSENBROCK2: {
+    // rosenbrock.cc:25-41 runs over the FLAT batch: set j's last parameter pairs with
+    // set j+1's first; the last set of the batch has d-1 terms
+    double y = 0.0;
+    const int last = (j == npset - 1) ? d - 1 : d;
+    for (int i = 0; i < last; ++i) {
+      const double t1 = 1 - xj[i];
+      const double t2 = xj[i + 1] - xj[i] * xj[i];
+      y -= t1 * t1 - 100.0 * t2 * t2;
+    }
+    return y;
+  }
+  case MCGPU_GAUSSIAN: {
+    double y = 0.0;
+    for (int k = 0; k < 2; ++k) { const double arg = xj[k] - L.lp[k]; y -= 0.5 * arg * arg * L.lp[2 + k]; }
+    return y;
+  }
+  case MCGPU_DUALGAUSSIAN: {
+    const double arg1 = 0.5 * (xj[0] * xj[0] + xj[1] * xj[1]);
+    const double t2a = xj[0] - 5.0, t2b = xj[1] - 5.0;
+    const double arg2 = 0.5 * (t2a * t2a + t2b * t2b);
+    return log(L.lp[0] * exp(-arg1) + exp(-arg2));
+  }
+  case MCGPU_GAUSSMIX: {
+    const int K = L.k;
+    const double *mu = L.dev, *is2 = mu + (size_t)K * d, *lw = is2 + (size_t)K * d;
+    double m = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      double q = 0.0;
+      for (int i = 0; i < d; ++i) { const double xm = xj[i] - mu[k * d + i]; q += xm * xm * is2[k * d + i]; }
+      const double a = lw[k] - 0.5 * q;
+      m = a > m ? a : m;
+    }
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double q = 0.0;
+      for (int i = 0; i < d; ++i) { const double xm = xj[i] - mu[k * d + i]; q += xm * xm * is2[k * d + i]; }
+      s += exp(lw[k] - 0.5 * q - m);
+    }
+    return m + log(s);
+  }
+  }
+  return 0.0;
+}
+
+static __global__ void loglik_aos_kernel(LikSpec L, const double *x, double *y, int npset)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < npset) y[j] = loglik_aos(L, x, npset, j);
+}
+
+// ----------------------------------------------------------------------------
+// Kernel 2: verification mode -- one CTA per emulated MPI rank
+// ----------------------------------------------------------------------------
+
+static __device__ __forceinline__ int block_excl_scan(int flag, int *s_warp, int &total)
+{
+  const unsigned int b = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const int within = __popc(b & ((1u << lane) - 1u));
+  __syncthreads();
+  if (lane == 0) s_warp[w] = __popc(b);
+  __syncthreads();
+  int before = 0; total = 0;
+  for (int i = 0; i < nw; ++i) { const int c = s_warp[i]; if (i < w) before += c; total += c; }
+  return before + within;
+}
+
+static __global__ void __launch_bounds__(1024)
+mh_verify_kernel(const VerifyParams p)
+{
+  __shared__ int s_warp[32];
+  __shared__ double s_scale;
+  const int r = blockIdx.x, j = threadIdx.x, d = p.d, C = p.C, N = p.N;
+  const bool live = j < C;
+  const int nt = C * d;
+  double *pv = p.pvals + (size_t)r * nt, *pt = p.ptrial + (size_t)r * nt;
+  double *lyv = p.ly + (size_t)r * C;
+  double *muv = p.mu + (size_t)r * nt, *sgv = p.sig + (size_t)r * nt, *psv = p.ps + (size_t)r * nt;
+  double *mtv = p.mutrial + (size_t)r * nt, *stv = p.sigtrial + (size_t)r * nt;
+  double *T = p.factor + (size_t)r * d * d;
+  double *ms = p.musig + (size_t)r * 2 * N * d;
+  const long long *so = p.soff + (size_t)r * 6;
+  const double *Zr = p.Z + so[0]; const long long nz = so[1];
+  const double *Ur = p.U + so[2]; const long long nu = so[3];
+  const int *Ir = p.I + so[4];    const long long ni = so[5];
+  long long iz = p.cursors[r * 3], iu = p.cursors[r * 3 + 1], ii = p.cursors[r * 3 + 2];
+  unsigned long long nacc = p.counts[r * 2], ntry = p.counts[r * 2 + 1];
+  int irate = p.irate[r];
+  const int grank = p.rank0 + r;
+  bool bad = false;
+#define RDZ(k) ((k) < nz ? Zr[(k)] : (bad = true, 0.0))
+#define RDU(k) ((k) < nu ? Ur[(k)] : (bad = true, 0.0))
+#define RDI(k) ((k) < ni ? Ir[(k)] : (bad = true, 0))
+
+  // the in-place all-gather of mcpar.cc:127-140: other ranks' slots come from the snapshot
+  if (p.phase == 1 && p.refresh) {
+    for (int q = j; q < 2 * N * d; q += blockDim.x) {
+      const int owner = q / (2 * nt);
+      if (owner != grank) ms[q] = p.snap_cur[q];
+    }
+  }
+  __syncthreads();
+
+  double mut[MCGPU_MAX_D], sgt[MCGPU_MAX_D], xt[MCGPU_MAX_D];
+  unsigned long long racc = 0;
+
+  for (int k = 0; k < p.nsteps; ++k) {
+    const int isamp = p.s0 + k;
+    bool remote = false;
+    int iters = 0;
+    double cfac = 1.0;
+    if (p.phase == 1 && isamp >= p.sync) {             // mcpar.cc:142-146
+      const double rnd = RDU(iu); iu += 1;
+      remote = !(rnd <= p.pl);
+    }
+    if (!remote) {                                      // genLocal, mcpar.cc:302-312
+      if (live) {
+        for (int i = 0; i < d; ++i) {
+          double acc = pv[j * d + i];
+          for (int q = 0; q <= i; ++q) acc += T[i * d + q] * RDZ(iz + (long long)j * d + q);
+          xt[i] = acc;
+        }
+      }
+      iz += (long long)C * d;
+    } else {                                            // genRemote, mcpar.cc:315-451
+      int rjct = live ? 1 : 0;
+      double qimax = 0.0;
+      int any;
+      do {
+        ++iters;
+        const int chn = live ? RDI(ii + j) : 0; ii += C;                  // :337
+        int total;
+        const int before = block_excl_scan(rjct, s_warp, total);
+        if (rjct) {                                                       // :339-352
+          for (int i = 0; i < d; ++i) {
+            const int tix = 2 * (d * chn + i);
+            mut[i] = ms[tix];
+            sgt[i] = sqrt(ms[tix + 1]);
+            xt[i] = mut[i] + sgt[i] * RDZ(iz + (long long)before * d + i);
+          }
+        }
+        iz += (long long)total * d;
+        double pacpt = 0.0;
+        if (rjct) {                                                       // :355-398
+          qimax = MCGPU_FPEPS; double qisum = MCGPU_FPEPS;
+          for (int qi = 0; qi < N; ++qi) {
+            double arg = 0.0;
+            for (int i = 0; i < d; ++i) {
+              const double xm = ms[2 * (qi * d + i)] - xt[i];
+              arg += xm * xm / ms[2 * (qi * d + i) + 1];
+            }
+            const double gv = exp(-0.5 * arg);
+            qisum += gv; qimax = gv > qimax ? gv : qimax;
+          }
+          pacpt = qimax / qisum;
+        }
+        const double u = live ? RDU(iu + j) : 1.0; iu += C;               // :401
+        if (rjct && u < pacpt) {                                          // :405-440
+          rjct = 0;
+          cfac = 0.0;
+          for (int qi = 0; qi < N; ++qi) {
+            double arg = 0.0;
+            for (int i = 0; i < d; ++i) {
+              const double xm = ms[2 * (qi * d + i)] - pv[j * d + i];
+              arg += xm * xm / ms[2 * (qi * d + i) + 1];
+            }
+            const double gv = exp(-0.5 * arg);
+            cfac = gv > cfac ? gv : cfac;
+          }
+          cfac /= qimax;
+        }
+        any = __syncthreads_or(rjct);
+      } while (any);
+      if (live) for (int i = 0; i < d; ++i) { sgt[i] *= sgt[i]; mtv[j * d + i] = mut[i]; stv[j * d + i] = sgt[i]; }
+    }
+    if (live) for (int i = 0; i < d; ++i) pt[j * d + i] = xt[i];
+    __syncthreads();
+    double lyt = 0.0, u = 1.0;
+    if (live) lyt = loglik_aos(p.L, pt, C, j);           // L(nchain,ptrial,lytrial) :60/:160
+    if (live) u = RDU(iu + j);
+    iu += C;                                             // :63/:163
+    bool a = false;
+    if (live) {
+      double pac = exp(lyt - lyv[j]);                    // :67/:167
+      if (p.phase == 1) pac *= cfac;
+      a = u < pac;
+      if (a) { lyv[j] = lyt; for (int i = 0; i < d; ++i) pv[j * d + i] = xt[i]; }
+    }
+    const int na = __syncthreads_count(a);
+    nacc += na; ntry += C; racc += na;
+
+    const int tix = p.trace_base + k;
+    if (p.tr_accept && tix < p.trace_cap) {
+      if (live) {
+        const size_t o = ((size_t)r * p.trace_cap + tix) * C + j;
+        p.tr_accept[o] = a; p.tr_trial_ly[o] = lyt; p.tr_cfac[o] = cfac;
+        for (int i = 0; i < d; ++i) p.tr_trial_p[o * d + i] = xt[i];
+      }
+      if (j == 0) { p.tr_remote[(size_t)r * p.trace_cap + tix] = remote; p.tr_iters[(size_t)r * p.trace_cap + tix] = iters; }
+    }
+
+    if (p.phase == 0) {                                  // tuning, mcpar.cc:78-96
+      if (isamp > irate) {
+        const double arate = (double)nacc / (double)ntry;
+        double f = 1.0;
+        if (arate < p.armin) { f = p.dfac; nacc = ntry = 0; }
+        else if (arate > p.armax) { f = p.ifac; nacc = ntry = 0; }
+        if (f != 1.0) for (int i = j; i < d * d; i += blockDim.x) T[i] *= f;
+        irate += 50;
+      }
+      __syncthreads();
+    } else {
+      if (j == 0 && remote) { atomicAdd(p.rstats, 1ull); atomicAdd(p.rstats + 1, (unsigned long long)iters); }
+      if (live) {
+        if (p.hist) {                                    // MCout::add
+          double *row = p.hist + ((size_t)isamp * p.hist_chains + (size_t)r * C + j) * (d + 1);
+          for (int i = 0; i < d; ++i) row[i] = pv[j * d + i];
+          row[d] = lyv[j];
+        }
+        const double pwgt = (double)(isamp + 1), winv = 1.0 / pwgt;       // :186-187
+        const bool adopt = remote && a;
+        for (int i = 0; i < d; ++i) {                                      // :188-209
+          const int ix = j * d + i;
+          if (adopt) { muv[ix] = mtv[ix]; sgv[ix] = stv[ix]; psv[ix] = sgv[ix] * (pwgt - 1.0); }
+          const double pvi = pv[ix];
+          const double delta = pvi - muv[ix];
+          muv[ix] += delta * winv;
+          psv[ix] += delta * (pvi - muv[ix]);
+          sgv[ix] = psv[ix] * winv;
+          const size_t islot = 2 * ((size_t)grank * nt + ix);
+          ms[islot] = muv[ix]; ms[islot + 1] = sgv[ix];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  (void)s_scale;
+  if (p.phase == 1 && p.publish && live)
+    for (int i = 0; i < d; ++i) {
+      const size_t islot = 2 * ((size_t)grank * nt + (size_t)j * d + i);
+      p.snap_next[islot] = ms[islot]; p.snap_next[islot + 1] = ms[islot + 1];
+    }
+  if (j == 0) {
+    p.cursors[r * 3] = iz; p.cursors[r * 3 + 1] = iu; p.cursors[r * 3 + 2] = ii;
+    p.counts[r * 2] = nacc; p.counts[r * 2 + 1] = ntry;
+    p.irate[r] = irate;
+    if (p.phase == 1) { atomicAdd(p.rstats + 2, racc); atomicAdd(p.rstats + 3, (unsigned long long)C * p.nsteps); }
+  }
+  if (bad) *p.overrun = 1;
+#undef RDZ
+#undef RDU
+#undef RDI
+}
+#endif  // MCGPU_EXACT_TU
+
+}  // namespace MCGPU_NS
+}  // namespace mcgpu

@@ -1,0 +1,23 @@
+// mh_launch.h -- host-visible launcher prototypes of the two kernel translation units.
+#pragma once
+#include "mcgpu_device.cuh"
+namespace mcgpu {
+namespace fast {
+bool steps_supported(int lik, int d);
+size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem);
+cudaError_t launch_steps(int lik, int d, int rngk, bool main_phase, const StepParams &p, cudaStream_t st);
+cudaError_t launch_init_loglik(int lik, int d, const StepParams &p, cudaStream_t st);
+cudaError_t launch_tune(unsigned long long *counts, unsigned long long *cum, double *factor, int dd,
+                        double armin, double armax, double dfac, double ifac, cudaStream_t st);
+}
+namespace exact {
+bool steps_supported(int lik, int d);
+size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem);
+cudaError_t launch_steps(int lik, int d, int rngk, bool main_phase, const StepParams &p, cudaStream_t st);
+cudaError_t launch_init_loglik(int lik, int d, const StepParams &p, cudaStream_t st);
+cudaError_t launch_tune(unsigned long long *counts, unsigned long long *cum, double *factor, int dd,
+                        double armin, double armax, double dfac, double ifac, cudaStream_t st);
+cudaError_t launch_verify(const VerifyParams &p, int nranks_local, cudaStream_t st);
+cudaError_t launch_loglik_aos(const LikSpec &L, const double *x, double *y, int npset, cudaStream_t st);
+}
+}

@@ -1,0 +1,295 @@
+"""ctypes binding of include/mcgpu.h -- the only way Python reaches the CUDA engine.
+
+Host-side mirror of the reference's interface for the hot path: `Engine` plays the
+role of `MCPar` (src/mcpar.hh:10-91) + `MCout` (src/mcout.hh:13-51) for one GPU.
+There is no CPU path here: if libmcgpu.so is missing, or no CUDA device is visible,
+construction raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmcgpu.so")
+
+LIK = {"rosenbrock1": 0, "rosenbrock2": 1, "gaussian": 2, "dualgaussian": 3, "gaussmix": 4}
+MODE = {"normal": 0, "verify": 1, "replay_local": 2}
+ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ECUDA", -4: "ESTATE", -5: "ENOMEM", -6: "ESTREAM"}
+
+EXPORTS = [
+    "mcgpu_version", "mcgpu_device_count", "mcgpu_last_error", "mcgpu_create", "mcgpu_destroy",
+    "mcgpu_set_stream", "mcgpu_set_likelihood", "mcgpu_set_covariance", "mcgpu_set_state",
+    "mcgpu_set_streams", "mcgpu_burnin", "mcgpu_sample_begin", "mcgpu_sample",
+    "mcgpu_exchange_begin", "mcgpu_exchange_end", "mcgpu_tuning_counters", "mcgpu_burnin_some",
+    "mcgpu_tune", "mcgpu_synchronize", "mcgpu_get_state", "mcgpu_get_factor", "mcgpu_get_musig",
+    "mcgpu_get_trace", "mcgpu_history_read", "mcgpu_history_maxlike", "mcgpu_history_moments",
+    "mcgpu_get_stats", "mcgpu_device_ptr", "mcgpu_loglik", "mcgpu_qriguess",
+    "mcgpu_measure_fp64_peak",
+]
+
+
+class McgpuError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("mode", C.c_int32),
+                ("nparam", C.c_int32), ("nchain", C.c_int64), ("chain0", C.c_int64),
+                ("nchain_total", C.c_int64), ("chains_per_rank", C.c_int32), ("sync", C.c_int32),
+                ("pl", C.c_double), ("armin", C.c_double), ("armax", C.c_double),
+                ("dfac", C.c_double), ("ifac", C.c_double), ("seed", C.c_uint64),
+                ("coin_group", C.c_int32), ("pool_m", C.c_int32), ("thin", C.c_int32),
+                ("trace", C.c_int32), ("history_steps", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("burn_steps", C.c_int64), ("main_steps", C.c_int64), ("accepted", C.c_int64),
+                ("tried", C.c_int64), ("kernel_launches", C.c_int64), ("remote_steps", C.c_int64),
+                ("remote_iterations", C.c_int64), ("history_rows", C.c_int64),
+                ("device_ms", C.c_double)]
+
+
+_lib = None
+
+
+def load():
+    """dlopen libmcgpu.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise McgpuError("libmcgpu.so is not built: run `python -m mcpar_b200.build` "
+                             "(or __graft_entry__.build()); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.mcgpu_version.restype = C.c_char_p
+        lib.mcgpu_last_error.restype = C.c_char_p
+        lib.mcgpu_last_error.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc, handle=None):
+    if rc != 0:
+        msg = load().mcgpu_last_error(handle)
+        raise McgpuError("%s: %s" % (ERRORS.get(rc, rc), msg.decode() if msg else ""))
+
+
+def device_count():
+    return load().mcgpu_device_count()
+
+
+def loglik(lik, nparam, x, par=None, device=0):
+    """VLFunc::operator()(npset, x, y) on the GPU (src/vlfunc.hh:11)."""
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, nparam)
+    y = np.empty(x.shape[0], dtype=np.float64)
+    par_a = None if par is None else np.ascontiguousarray(par, dtype=np.float64)
+    _check(load().mcgpu_loglik(device, LIK[lik], nparam, _p(par_a), 0 if par is None else par_a.size,
+                               x.shape[0], _p(x), _p(y)))
+    return y
+
+
+def qriguess(rank, npset, nparam, plo, phi, device=0):
+    """mcutil::qriguess (src/mcutil.cc:3-34) on the GPU."""
+    plo = np.ascontiguousarray(plo, dtype=np.float64); phi = np.ascontiguousarray(phi, dtype=np.float64)
+    out = np.empty(npset * nparam, dtype=np.float64)
+    _check(load().mcgpu_qriguess(device, rank, npset, nparam, _p(plo), _p(phi), _p(out)))
+    return out.reshape(npset, nparam)
+
+
+def measure_fp64_peak(device=0):
+    v = C.c_double(0)
+    _check(load().mcgpu_measure_fp64_peak(device, C.byref(v)))
+    return v.value
+
+
+class DevicePtr:
+    """A raw device range exposing __cuda_array_interface__ so torch can alias it
+    (torch.as_tensor(ptr, device='cuda')) for the NCCL exchange."""
+
+    def __init__(self, ptr, nbytes, dtype="<f8"):
+        item = np.dtype(dtype).itemsize
+        self.__cuda_array_interface__ = {"shape": (nbytes // item,), "typestr": dtype,
+                                         "data": (ptr, False), "version": 2}
+        self.ptr, self.nbytes = ptr, nbytes
+
+
+class Engine:
+    """One GPU's share of an MCPar run.
+
+    Mirrors MCPar(np, nc, mpisiz, mpirank, pl, armin, armax, dfac, ifac, sync)
+    (src/mcpar.hh:32-33); `run` mirrors MCPar::run(nsamp, nburn, pinit, L, out, incov).
+    """
+
+    def __init__(self, nparam, nchain, *, mode="normal", nchain_total=None, chain0=0,
+                 chains_per_rank=0, pl=0.9, armin=0.2, armax=0.5, dfac=0.2, ifac=1.5, sync=10,
+                 seed=8675309, coin_group=32, pool_m=0, thin=1, trace=False, history_steps=0,
+                 device=0):
+        self.lib = load()
+        cfg = Config()
+        cfg.abi_version = 1
+        cfg.device, cfg.mode, cfg.nparam = device, MODE[mode], nparam
+        cfg.nchain, cfg.chain0 = nchain, chain0
+        cfg.nchain_total = nchain if nchain_total is None else nchain_total
+        cfg.chains_per_rank, cfg.sync = chains_per_rank, sync
+        cfg.pl, cfg.armin, cfg.armax, cfg.dfac, cfg.ifac = pl, armin, armax, dfac, ifac
+        cfg.seed, cfg.coin_group, cfg.pool_m, cfg.thin = seed, coin_group, pool_m, thin
+        cfg.trace, cfg.history_steps = int(trace), history_steps
+        self.cfg = cfg
+        self.d, self.C, self.mode = nparam, nchain, mode
+        self.h = C.c_void_p()
+        _check(self.lib.mcgpu_create(C.byref(cfg), C.byref(self.h)))
+
+    # -- lifetime -------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.mcgpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        _check(rc, self.h)
+
+    # -- set-up ---------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.mcgpu_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def set_likelihood(self, lik, par=None):
+        par_a = None if par is None else np.ascontiguousarray(par, dtype=np.float64)
+        self._ck(self.lib.mcgpu_set_likelihood(self.h, LIK[lik], _p(par_a), 0 if par is None else par_a.size))
+
+    def set_covariance(self, incov=None):
+        inc = None if incov is None else np.ascontiguousarray(incov, dtype=np.float64).ravel()
+        if inc is not None:
+            assert inc.size == self.d * self.d
+        self._ck(self.lib.mcgpu_set_covariance(self.h, _p(inc)))
+
+    def set_state(self, pinit):
+        pinit = np.ascontiguousarray(pinit, dtype=np.float64)
+        assert pinit.size == self.C * self.d, "pinit must hold nchain*nparam values"
+        self._ck(self.lib.mcgpu_set_state(self.h, _p(pinit)))
+
+    def set_streams(self, local_rank, Z, U, I=None):
+        Z = np.ascontiguousarray(Z, dtype=np.float64).ravel()
+        U = np.ascontiguousarray(U, dtype=np.float64).ravel()
+        I = np.zeros(0, dtype=np.int32) if I is None else np.ascontiguousarray(I, dtype=np.int32).ravel()
+        self._ck(self.lib.mcgpu_set_streams(self.h, local_rank, _p(Z), C.c_size_t(Z.size), _p(U),
+                                            C.c_size_t(U.size), _p(I), C.c_size_t(I.size)))
+
+    # -- stepping -------------------------------------------------------------
+    def burnin(self, nburn):
+        self._ck(self.lib.mcgpu_burnin(self.h, nburn))
+
+    def burnin_some(self, nmax):
+        done, pend = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.mcgpu_burnin_some(self.h, nmax, C.byref(done), C.byref(pend)))
+        return done.value, bool(pend.value)
+
+    def tune(self):
+        self._ck(self.lib.mcgpu_tune(self.h))
+
+    def tuning_counters(self):
+        p = C.c_void_p()
+        self._ck(self.lib.mcgpu_tuning_counters(self.h, C.byref(p)))
+        return DevicePtr(p.value, 16, "<i8")
+
+    def sample_begin(self, nsamp):
+        self._ck(self.lib.mcgpu_sample_begin(self.h, nsamp))
+
+    def sample(self, nsteps):
+        self._ck(self.lib.mcgpu_sample(self.h, nsteps))
+
+    def exchange_begin(self):
+        p = C.c_void_p(); tot = C.c_size_t(); off = C.c_size_t(); own = C.c_size_t()
+        self._ck(self.lib.mcgpu_exchange_begin(self.h, C.byref(p), C.byref(tot), C.byref(off), C.byref(own)))
+        return DevicePtr(p.value, tot.value), off.value, own.value
+
+    def exchange_end(self):
+        self._ck(self.lib.mcgpu_exchange_end(self.h))
+
+    def synchronize(self):
+        self._ck(self.lib.mcgpu_synchronize(self.h))
+
+    def run(self, nsamp, nburn, pinit, lik, par=None, incov=None):
+        """MCPar::run on this engine's chains (single engine: exchange is internal)."""
+        self.set_likelihood(lik, par)
+        self.set_covariance(incov)
+        self.set_state(pinit)
+        self.burnin(nburn)
+        self.sample_begin(nsamp)
+        self.sample(nsamp)
+        self.synchronize()
+
+    # -- read-back ------------------------------------------------------------
+    def state(self):
+        C_, d = self.C, self.d
+        out = {k: np.empty((C_, d)) for k in ("p", "mu", "sig", "psum2")}
+        out["ly"] = np.empty(C_)
+        self._ck(self.lib.mcgpu_get_state(self.h, _p(out["p"]), _p(out["ly"]), _p(out["mu"]),
+                                          _p(out["sig"]), _p(out["psum2"])))
+        return out
+
+    def factor(self, local_rank=0):
+        f = np.empty((self.d, self.d))
+        self._ck(self.lib.mcgpu_get_factor(self.h, local_rank, _p(f)))
+        return f
+
+    def musig(self, local_rank=0):
+        n = self.cfg.nchain_total if self.mode == "verify" else (
+            self.cfg.pool_m if 0 < self.cfg.pool_m < self.cfg.nchain_total else self.cfg.nchain_total)
+        m = np.empty((n, self.d, 2))
+        self._ck(self.lib.mcgpu_get_musig(self.h, local_rank, _p(m)))
+        return m
+
+    def trace(self, local_rank, nsteps):
+        Cr, d = self.cfg.chains_per_rank, self.d
+        t = {"accept": np.zeros((nsteps, Cr), dtype=np.uint8), "trial_ly": np.zeros((nsteps, Cr)),
+             "trial_p": np.zeros((nsteps, Cr, d)), "cfac": np.zeros((nsteps, Cr)),
+             "remote": np.zeros(nsteps, dtype=np.uint8), "iters": np.zeros(nsteps, dtype=np.int32),
+             "cursors": np.zeros(3, dtype=np.int64)}
+        self._ck(self.lib.mcgpu_get_trace(self.h, local_rank, _p(t["accept"]), _p(t["trial_ly"]),
+                                          _p(t["trial_p"]), _p(t["cfac"]), _p(t["remote"]),
+                                          _p(t["iters"]), _p(t["cursors"])))
+        return t
+
+    def history(self, first=0, count=None, out=None):
+        st = self.stats()
+        kept = st["history_rows"] // self.C
+        if count is None:
+            count = kept - first
+        rows = out if out is not None else np.empty((count, self.C, self.d + 1))
+        self._ck(self.lib.mcgpu_history_read(self.h, C.c_int64(first), C.c_int64(count), _p(rows)))
+        return rows
+
+    def maxlike(self):
+        out = np.empty(self.d + 1)
+        self._ck(self.lib.mcgpu_history_maxlike(self.h, _p(out)))
+        return out[:-1], out[-1]
+
+    def moments(self):
+        mean = np.empty(self.d); cov = np.empty((self.d, self.d))
+        self._ck(self.lib.mcgpu_history_moments(self.h, _p(mean), _p(cov)))
+        return mean, cov
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.lib.mcgpu_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def device_ptr(self, which):
+        p = C.c_void_p(); n = C.c_size_t()
+        self._ck(self.lib.mcgpu_device_ptr(self.h, which, C.byref(p), C.byref(n)))
+        return DevicePtr(p.value, n.value)

@@ -1,0 +1,229 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (libmcgpu.so via ctypes),
+against the CPU oracle (oracle/mh_oracle.c, itself pinned to the reference build).
+
+Bar: verification mode -- identical accept/reject sequences, identical stream
+consumption, states and polynomial log-likelihoods bit-identical, transcendental
+log-likelihoods within 1e-12 relative (north star).
+"""
+import numpy as np
+import pytest
+
+from conftest import make_streams, tiled_pinit
+from oracle import mh
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def _engine():
+    from mcpar_b200 import engine
+    return engine
+
+
+def _close(a, b, rtol=RTOL, atol=0.0):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    ok = both_inf | (np.abs(a - b) <= atol + rtol * np.abs(b))
+    return bool(np.all(ok))
+
+
+# ---------------------------------------------------------------- likelihoods
+@pytest.mark.parametrize("lik,d,par", [
+    ("rosenbrock1", 2, None), ("rosenbrock1", 16, None), ("rosenbrock2", 4, None),
+    ("gaussian", 2, [1.0, -1.0, 0.5, 2.0]), ("dualgaussian", 2, [5.0]),
+])
+def test_loglik_matches_oracle(lik, d, par):
+    eng = _engine()
+    rng = np.random.default_rng(7)
+    x = rng.normal(1.0, 2.0, size=(100003, d))
+    y = eng.loglik(lik, d, x, par)
+    yo = mh.loglik(lik, d, x, par)
+    if lik.startswith("rosenbrock") or lik == "gaussian":
+        assert np.array_equal(y, yo)          # polynomial: bit-identical
+    else:
+        assert _close(y, yo)
+
+
+def test_loglik_known_answers():
+    eng = _engine()
+    assert np.array_equal(eng.loglik("rosenbrock1", 2, [[1, 1], [0, 0], [2, 2]]), [0.0, -1.0, -401.0])
+    y = eng.loglik("dualgaussian", 2, [[0, 0], [5, 5], [100, 100]], [5.0])
+    assert _close(y[:2], [np.log(5 + np.exp(-25)), np.log(5 * np.exp(-25) + 1)])
+    assert y[2] == -np.inf                    # no log-sum-exp guard, as in the reference
+
+
+def test_loglik_gaussmix():
+    eng = _engine()
+    rng = np.random.default_rng(3)
+    K, d = 5, 4
+    par = mh.gaussmix_params(K, d, rng.normal(0, 3, (K, d)), rng.uniform(0.5, 2, (K, d)), rng.uniform(0.5, 2, K))
+    x = rng.normal(0, 4, size=(5000, d))
+    assert _close(eng.loglik("gaussmix", d, x, par), mh.loglik("gaussmix", d, x, par), rtol=1e-11)
+
+
+def test_loglik_rejects_bad_shapes():
+    eng = _engine()
+    with pytest.raises(eng.McgpuError):
+        eng.loglik("rosenbrock1", 3, np.zeros((2, 3)))
+    with pytest.raises(eng.McgpuError):
+        eng.loglik("gaussian", 3, np.zeros((2, 3)))
+
+
+# ---------------------------------------------------------------- verification mode
+def _run_verify(lik, d, C, R, nsamp, nburn, par=None, incov=None, pl=0.9, sync=10, seed=1, split=None):
+    eng = _engine()
+    pin = tiled_pinit(C, d)
+    Z, U, I = make_streams(R, C, d, nsamp + nburn, seed)
+    o = mh.run_replay(lik, d, C, R, nsamp, nburn, pin, Z, U, I, incov=incov, par=par, pl=pl, sync=sync, trace=True)
+    e = eng.Engine(d, R * C, mode="verify", chains_per_rank=C, pl=pl, sync=sync, trace=True,
+                   history_steps=nsamp)
+    e.set_likelihood(lik, par)
+    e.set_covariance(incov)
+    e.set_state(np.tile(pin, (R, 1)))
+    for r in range(R):
+        e.set_streams(r, Z[r], U[r], I[r])
+    e.burnin(nburn)
+    e.sample_begin(nsamp)
+    if split:
+        done = 0
+        for n in split:
+            e.sample(n); done += n
+        e.sample(nsamp - done)
+    else:
+        e.sample(nsamp)
+    e.synchronize()
+    return o, e
+
+
+@pytest.mark.parametrize("lik,d,C,R,nsamp,nburn,par,incov,pl,sync", [
+    ("rosenbrock1", 2, 4, 1, 200, 120, None, None, 0.9, 10),
+    ("rosenbrock1", 2, 4, 3, 300, 200, None, None, 0.9, 10),
+    ("dualgaussian", 2, 4, 2, 200, 120, [5.0], None, 0.9, 10),
+    ("gaussian", 2, 8, 2, 100, 120, [1.0, -1.0, 0.5, 2.0], None, 0.9, 10),
+    ("rosenbrock2", 4, 4, 2, 100, 120, None, None, 0.9, 10),
+    ("rosenbrock1", 4, 5, 2, 100, 520, None, "spd4", 0.9, 10),
+    ("rosenbrock1", 2, 1, 1, 100, 120, None, None, 0.9, 10),
+    ("rosenbrock1", 2, 4, 2, 55, 0, None, None, 0.5, 3),
+    ("rosenbrock1", 2, 40, 2, 60, 60, None, None, 0.7, 10),
+])
+def test_verify_mode_matches_oracle(lik, d, C, R, nsamp, nburn, par, incov, pl, sync):
+    if incov == "spd4":
+        incov = np.diag([0.5, 2, 0.5, 2.0]) + 0.1
+    o, e = _run_verify(lik, d, C, R, nsamp, nburn, par, incov, pl, sync)
+    T = nburn + nsamp
+    poly = lik in ("rosenbrock1", "rosenbrock2", "gaussian")
+    st = e.state()
+    for r in range(R):
+        tr = e.trace(r, T)
+        otr = o["trace"]
+        assert np.array_equal(tr["accept"].astype(bool), o["accept"][r]), "accept/reject sequence differs"
+        assert np.array_equal(tr["remote"], otr["remote"][r])
+        assert np.array_equal(tr["iters"], otr["iters"][r])
+        assert np.array_equal(tr["cursors"], o["used"][r][:3]), "stream consumption differs"
+        assert np.array_equal(tr["trial_p"], otr["trial_p"][r]), "trial points are not bit-identical"
+        if poly:
+            assert np.array_equal(tr["trial_ly"], otr["trial_ly"][r])
+        else:
+            assert _close(tr["trial_ly"], otr["trial_ly"][r])
+        assert _close(tr["cfac"], otr["cfac"][r], rtol=1e-11)
+        assert np.array_equal(e.factor(r), o["cov"][r])
+        sl = slice(r * C, (r + 1) * C)
+        assert np.array_equal(st["p"][sl], o["p"][r])
+        assert np.array_equal(st["mu"][sl], o["mu"][r]) and np.array_equal(st["psum2"][sl], o["psum2"][r])
+        assert np.array_equal(st["sig"][sl], o["sig"][r])
+        assert np.array_equal(e.musig(r), o["musig"][r])
+        (np.testing.assert_array_equal if poly else np.testing.assert_allclose)(st["ly"][sl], o["ly"][r])
+    # MCout contents: [step][rank*C + chain][d+1]  ->  reference per-rank row order
+    h = e.history().reshape(nsamp, R, C, d + 1).transpose(1, 0, 2, 3).reshape(R, nsamp * C, d + 1)
+    assert np.array_equal(h[..., :d], o["rows"][..., :d])
+    assert _close(h[..., d], o["rows"][..., d])
+    pm, lm = e.maxlike()
+    assert _close(lm, o["maxl"][d]) and (not poly or np.array_equal(pm, o["maxl"][:d]))
+    s = e.stats()
+    assert s["remote_steps"] == int(otr["remote"].sum()) and s["remote_iterations"] == int(otr["iters"].sum())
+    e.close()
+
+
+def test_verify_mode_split_sample_calls():
+    """Advancing in uneven pieces must not change anything (exchange boundaries are internal)."""
+    o, e = _run_verify("rosenbrock1", 2, 4, 2, 95, 60, split=[3, 7, 15, 4])
+    st = e.state()
+    assert np.array_equal(st["p"].reshape(2, 4, 2), o["p"])
+    assert np.array_equal(e.musig(1), o["musig"][1])
+    e.close()
+
+
+def test_stream_overrun_is_an_error():
+    eng = _engine()
+    e = eng.Engine(2, 4, mode="verify", chains_per_rank=4, trace=False, history_steps=0)
+    e.set_likelihood("rosenbrock1")
+    e.set_state(tiled_pinit(4, 2))
+    e.set_streams(0, np.zeros(10), np.full(10, 0.5), np.zeros(10, np.int32))
+    with pytest.raises(eng.McgpuError, match="ESTREAM"):
+        e.burnin(50)
+    e.close()
+
+
+# ---------------------------------------------------------------- production kernel, replayed
+@pytest.mark.parametrize("lik,d,C,par,incov", [
+    ("rosenbrock1", 2, 96, None, None),
+    ("dualgaussian", 2, 200, [5.0], None),
+    ("rosenbrock1", 16, 64, None, "rosen16"),
+    ("gaussian", 2, 33, [0.5, -0.5, 1.5, 0.7], None),
+])
+def test_production_kernel_replay_local(lik, d, C, par, incov):
+    """The production step kernel (exact-arithmetic instantiation) fed the reference's
+    streams at the reference's offsets, all-local run (pl = 1): one rank of C chains."""
+    eng = _engine()
+    if incov == "rosen16":
+        blk = (2.38 ** 2 / 16) * np.array([[0.5, 1.0], [1.0, 2.505]])
+        incov = np.kron(np.eye(8), blk)
+    nburn, nsamp = 230, 75
+    pin = tiled_pinit(C, d)
+    Z, U, I = make_streams(1, C, d, nsamp + nburn, 11, mult=2)
+    o = mh.run_replay(lik, d, C, 1, nsamp, nburn, pin, Z, U, I, incov=incov, par=par, pl=1.0, trace=True)
+    e = eng.Engine(d, C, mode="replay_local", pl=1.0, history_steps=nsamp)
+    e.set_likelihood(lik, par); e.set_covariance(incov); e.set_state(pin)
+    e.set_streams(0, Z[0], U[0])
+    e.burnin(nburn); e.sample_begin(nsamp); e.sample(nsamp); e.synchronize()
+    st = e.state()
+    poly = lik != "dualgaussian"
+    assert np.array_equal(st["p"], o["p"][0])
+    assert np.array_equal(e.factor(), o["cov"][0]), "burn-in tuning history differs"
+    assert np.array_equal(st["mu"], o["mu"][0]) and np.array_equal(st["psum2"], o["psum2"][0])
+    h = e.history().reshape(nsamp * C, d + 1)
+    assert np.array_equal(h[:, :d], o["rows"][0][:, :d])
+    assert np.array_equal(h[:, d], o["rows"][0][:, d]) if poly else _close(h[:, d], o["rows"][0][:, d])
+    s = e.stats()
+    assert s["accepted"] == int(o["accept"][0][nburn:].sum()) and s["tried"] == nsamp * C
+    e.close()
+
+
+# ---------------------------------------------------------------- normal mode vs counter oracle
+@pytest.mark.parametrize("lik,d,N,par,pool_m,pl", [
+    ("rosenbrock1", 2, 256, None, 0, 0.9),
+    ("rosenbrock1", 2, 512, None, 16, 0.7),
+    ("dualgaussian", 2, 256, [5.0], 8, 0.8),
+    ("rosenbrock1", 4, 128, None, 8, 0.8),
+])
+def test_normal_mode_matches_counter_oracle(lik, d, N, par, pool_m, pl):
+    """Same Philox draws on both sides: identical accept sequences; values agree to
+    rounding (host libm vs CUDA libm differ in the last ulp of log/sin/cos/exp)."""
+    eng = _engine()
+    nburn, nsamp = 120, 60
+    pin = tiled_pinit(N, d)
+    o = mh.run_counter(lik, d, N, nsamp, nburn, pin, par=par, pool_m=pool_m, pl=pl, trace=True)
+    e = eng.Engine(d, N, mode="normal", pool_m=pool_m, pl=pl, history_steps=nsamp)
+    e.run(nsamp, nburn, pin, lik, par)
+    st = e.state()
+    h = e.history()
+    # accept pattern of the main phase from the history: a row changed iff accepted
+    same_state = np.all(np.isclose(h[:, :, :d], o["rows"][:, :, :d], rtol=1e-7, atol=1e-9), axis=-1)
+    assert same_state.mean() > 0.999, "trajectories diverged: %.4f agree" % same_state.mean()
+    assert np.allclose(st["p"], o["p"], rtol=1e-6, atol=1e-8) or same_state[-1].mean() > 0.995
+    assert np.allclose(e.factor(), o["cov"]), "global burn-in tuning differs"
+    s = e.stats()
+    assert abs(s["accepted"] - int(o["counts"][0])) <= max(2, nsamp * N // 5000)
+    assert o["remote"][nburn:].any(), "test must exercise the remote branch"
+    e.close()
