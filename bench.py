@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- MH chain-steps/s of the B200 engine (and of the reference on the host cores).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dgauss|rosen2d|rosen16]
+  python bench.py --impl reference ...        # the reference's own CPU loop (oracle/_ref)
+
+A "step" is one exchange window of the hot path: `sync` (=10) Metropolis-Hastings
+steps of every chain (proposal, likelihood, accept, update, running moments), the
+thinned sample-history store and the publication of the exchange pool; under
+torchrun the NCCL all-gather of the pool is part of the step.  Workload at N=1 is
+BASELINE.json configs[1] (mcpar-dgauss: DualGaussian(5), 2^20 chains, one B200);
+SURVEY.md 8(d) C2 fixes the rest (identity incov, PLOCAL 0.9, SYNCSTEP 10, thin 10).
+Weak scaling: 2^20 chains per GPU.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "mh_chain_steps_per_sec"
+UNIT = "chain-steps/s"
+SEED = 8675309                      # reference seed, src/mcpar.cc:271
+
+# hardware-equivalent fp64 flops per chain-step (calls weighted
+# log~50, sqrt~14, sincos~40, exp~30, div~18) and textbook flops
+WORKLOADS = {
+    "dgauss":  dict(lik="dualgaussian", par=[5.0], d=2, F_hw=280.0, F_alg=46.0, name="mcpar-dgauss"),
+    "rosen2d": dict(lik="rosenbrock1", par=None, d=2, F_hw=167.0, F_alg=38.0, name="mcpar-rosen1 shape, 2-D Rosenbrock"),
+    "rosen16": dict(lik="rosenbrock1", par=None, d=16, F_hw=1350.0, F_alg=516.0, name="mcpar-rosen2 (d=16)"),
+}
+
+
+def incov_for(wl):
+    import numpy as np
+    if wl == "rosen16":             # analytic target covariance, Roberts-Rosenthal scale
+        blk = (2.38 ** 2 / 16) * np.array([[0.5, 1.0], [1.0, 2.505]])
+        return np.kron(np.eye(8), blk)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_run(wl, nranks, nchain, nburn, nsamp, pl=0.9, bits=64):
+    """Time the reference's own MCPar::run (oracle/_ref: its unmodified sources on shim
+    MPI/MKL, thread ranks) on the host cores.  Returns chain-steps/s."""
+    import numpy as np
+    from oracle.ref import Ref, available
+    from conftest import tiled_pinit
+    if not available(bits):
+        return None
+    W = WORKLOADS[wl]
+    ref = Ref(bits)
+    pin = tiled_pinit(nchain, W["d"])
+    o = ref.run(W["lik"], W["d"], nchain, nranks, nsamp, nburn, pin, incov=incov_for(wl), par=W["par"],
+                seed=SEED, pl=pl, want_rows=False, want_maxl=False)
+    return nranks * nchain * (nburn + nsamp) / o["seconds"]
+
+
+def cpu_baseline(wl):
+    """Bounded sample of the same workload on all host cores: the reference's own launch
+    shape (one rank per core, 4 chains per rank as in mcpar-dgauss.cc:31)."""
+    cores = os.cpu_count() or 1
+    R = min(cores, 64)              # remote proposals cost O(N^2) in the reference: bound the rank count
+    t0 = time.time()
+    v = cpu_reference_run(wl, R, 4, 500, 1000)
+    if v is None:
+        return {"value": None, "unit": UNIT, "cores": R, "kind": "reference", "sample": "oracle/_ref not built"}
+    v_local = cpu_reference_run(wl, R, 4, 500, 20000, pl=1.0)
+    return {"value": v, "unit": UNIT, "cores": R, "kind": "reference",
+            "sample": "reference MCPar::run (own sources, shim RNG/MPI, fp64 build), %d thread-ranks x 4 chains, "
+                      "nburn 500 + nsamp 1000, PLOCAL 0.9 (all-pairs remote proposals over %d chains)" % (R, 4 * R),
+            "value_local_only": v_local,
+            "sample_local_only": "same, PLOCAL 1.0, nsamp 20000", "host_cores": cores,
+            "seconds": round(time.time() - t0, 1)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    cores = os.cpu_count() or 1
+    R = min(cores, 64)
+    for _ in range(args.warmup):
+        cpu_reference_run(wl, R, 4, 50, 50)
+    vals, t0 = [], time.time()
+    nburn, nsamp = 500, 1000
+    for _ in range(args.steps):
+        vals.append(cpu_reference_run(wl, R, 4, nburn, nsamp))
+    if vals and vals[0] is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built on this box"}))
+        return
+    total_steps = R * 4 * (nburn + nsamp) * len(vals)
+    secs = sum(R * 4 * (nburn + nsamp) / v for v in vals)
+    value = total_steps / secs
+    sample = ("each step = one reference MCPar::run (own unmodified sources, shim RNG/MPI, fp64 build) on %d "
+              "thread-ranks x 4 chains, nburn 500 + nsamp 1000, PLOCAL 0.9" % R)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(vals)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": WORKLOADS[wl]["name"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": R, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": round(time.time() - t0, 2)}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dgauss", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=1 << 20, help="chains per GPU")
+    ap.add_argument("--pool", type=int, default=16, help="remote-mixture pool size M")
+    ap.add_argument("--pl", type=float, default=0.9)
+    ap.add_argument("--thin", type=int, default=10)
+    ap.add_argument("--sync", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3                         # timing rule: W >= 3
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mcpar_b200 import engine
+    from conftest import tiled_pinit
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = WORKLOADS[args.workload]
+    d, Cg, sync, thin = W["d"], args.chains, args.sync, args.thin
+    N = Cg * world
+    K, Wu = args.steps, args.warmup
+    nburn = 500
+    nsamp = (K + Wu) * sync
+    kept = (nsamp + thin - 1) // thin
+
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)                 # engine kernels, NCCL ops and timing events share it
+    e = engine.Engine(d, Cg, mode="normal", nchain_total=N, chain0=rank * Cg, pl=args.pl, sync=sync,
+                      seed=SEED, pool_m=args.pool, thin=thin, history_steps=kept, device=local)
+    e.set_stream(stream.cuda_stream)
+    e.set_likelihood(W["lik"], W["par"]); e.set_covariance(incov_for(args.workload))
+    pin = tiled_pinit(N, d)[rank * Cg:(rank + 1) * Cg]
+    e.set_state(pin)
+
+    # ---- sharded helpers: the pool all-gather and the tuning all-reduce over NCCL
+    pool_views = {}
+
+    def exchange():
+        buf, off, own = e.exchange_begin()
+        key = buf.ptr
+        if key not in pool_views:
+            full = torch.as_tensor(buf, device=dev)
+            pool_views[key] = (full, full[off // 8:(off + own) // 8])
+        full, mine = pool_views[key]
+        dist.all_gather_into_tensor(full, mine)
+        e.exchange_end()
+
+    def burn(n):
+        if world == 1:
+            e.burnin(n); return
+        cnt = torch.as_tensor(e.tuning_counters(), device=dev)
+        left = n
+        while left > 0:
+            done, pend = e.burnin_some(left)
+            left -= done
+            if pend:
+                dist.all_reduce(cnt)
+                e.tune()
+
+    def window():
+        e.sample(sync)
+        if world > 1:
+            exchange()
+
+    burn(nburn)
+    e.sample_begin(nsamp)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    for _ in range(Wu):
+        window()
+    torch.cuda.synchronize()
+    l0 = e.stats()["kernel_launches"]
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local) if rank == 0 else None
+    evs = []
+    for _ in range(K):
+        flush.zero_()                                                    # L2 flush, outside the event pair
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(stream); window(); b.record(stream)
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ck = clocks.stop() if clocks else None
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    st = e.stats()
+    launches = st["kernel_launches"] - l0 + (K if world > 1 else 0)      # + NCCL all-gathers
+    value = N * sync * K / (ms * 1e-3)
+    acc_rate = st["accepted"] / max(1, st["tried"])
+    mean, cov = e.moments()
+
+    # ---- end to end: MCPar::run-shaped job through the C ABI with HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        nb_e, ns_e = 500, 1000
+        kept_e = (ns_e + thin - 1) // thin
+        e.close(); del flush; torch.cuda.empty_cache()
+        host_rows = torch.empty((kept_e, Cg, d + 1), dtype=torch.float64).pin_memory().numpy()
+        host_pin = torch.from_numpy(np.ascontiguousarray(pin)).pin_memory().numpy()
+        best = None
+        for rep in range(3):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e = engine.Engine(d, Cg, mode="normal", nchain_total=N, chain0=rank * Cg, pl=args.pl, sync=sync,
+                              seed=SEED, pool_m=args.pool, thin=thin, history_steps=kept_e, device=local)
+            e.set_stream(stream.cuda_stream)
+            e.set_likelihood(W["lik"], W["par"]); e.set_covariance(incov_for(args.workload))
+            t1 = time.perf_counter()
+            e.set_state(host_pin)                                       # H2D inside the timed region
+            e.attach_host_sink(host_rows)                               # D2H drains on a side stream per window
+            pool_views.clear()
+            burn(nb_e)
+            e.sample_begin(ns_e)
+            for _ in range(ns_e // sync):
+                window()
+            fin = e.state()["ly"]
+            e.synchronize()                                              # compute + drain finished
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            e.close()
+            tt = torch.tensor([t2 - t1], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sec = float(tt.item())
+            if best is None or sec < best:
+                best = sec
+        nwin = (nb_e + ns_e) // sync
+        e2e = {"value": N * (nb_e + ns_e) / best, "unit": UNIT,
+               "h2d_bytes_per_step": int(pin.nbytes // nwin),
+               "d2h_bytes_per_step": int((host_rows.nbytes + fin.nbytes) // nwin),
+               "job": "set_state(host pinit) + burnin 500 + 1000 steps + history(thin %d) and final logL to pinned host; "
+                      "bytes are per 10-step window of the 150-window job; best of 3" % thin,
+               "seconds": best}
+
+    if rank == 0:
+        peak = engine.measure_fp64_peak(local)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        per_gpu = value / world
+        bytes_step = 2 * (3 * d + 1) * 8 / sync + (d + 1) * 8 / thin     # state round trip + history, SURVEY 8(d)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        except Exception:
+            pass
+        ach = per_gpu * W["F_hw"] / 1e12
+        roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                "traffic": traffic,
+                "note": "achieved = chain-steps/s/GPU x F_hw (%g hardware-equivalent fp64 flops per chain-step, SURVEY.md 8d); "
+                        "peak = DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no fp64 figure); "
+                        "kernel time = CUDA events around each window launch" % W["F_hw"],
+                "achieved_textbook_tflops": per_gpu * W["F_alg"] / 1e12,
+                "hbm": {"achieved": per_gpu * bytes_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": per_gpu * bytes_step / 1e9 / hbm_peak, "bytes_per_chain_step": bytes_step,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+        cpu = None if args.no_cpu else cpu_baseline(args.workload)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s: %s d=%d, %d chains/GPU x %d GPU, PLOCAL %.2f, SYNCSTEP %d, pool M=%d, thin %d, "
+                                       "seed %d; step = one %d-step exchange window" % (
+                                           W["name"], W["lik"], d, Cg, world, args.pl, sync, args.pool, thin, SEED, sync),
+                           "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                           "parallelism": "chains sharded by global id, pool all-gather over NCCL each window" if world > 1 else "single GPU"},
+                "clocks": ck, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "accept_rate": acc_rate, "posterior_mean": [float(x) for x in mean],
+                "posterior_var": [float(cov[i, i]) for i in range(d)]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

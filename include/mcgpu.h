@@ -79,7 +79,7 @@ typedef struct mcgpu_config {
   int32_t coin_group;       /* NORMAL: chains sharing the local/remote coin (1..32, power of 2) */
   int32_t pool_m;           /* NORMAL: remote-mixture pool size; 0 = all chains      */
   int32_t thin;             /* keep every thin-th main step in the sample history    */
-  int32_t trace;            /* VERIFY: record per-step accept/trial traces           */
+  int32_t trace;            /* VERIFY: steps of per-step accept/trial trace to keep (0 = none) */
   int64_t history_steps;    /* kept steps the history must hold (0 = moments only)   */
 } mcgpu_config;
 
@@ -100,8 +100,9 @@ const char *mcgpu_last_error(const mcgpu_engine *e);    /* e may be NULL: last c
 int  mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out);
 int  mcgpu_destroy(mcgpu_engine *e);
 
-/* Run everything on the caller's CUDA stream (a cudaStream_t passed as void*);
- * NULL restores the engine's own stream. */
+/* Run everything on the caller's CUDA stream (a cudaStream_t passed as void*; NULL is
+ * the legacy default stream).  Without this call the engine uses a private
+ * non-blocking stream. */
 int  mcgpu_set_stream(mcgpu_engine *e, void *cuda_stream);
 
 /* VLFunc &L argument of MCPar::run. */
@@ -168,6 +169,12 @@ int  mcgpu_get_trace(mcgpu_engine *e, int local_rank, uint8_t *accept, double *t
  * step major, then hosted chain.  read copies kept steps [first, first+count) to the
  * host through pinned staging buffers on a side stream. */
 int  mcgpu_history_read(mcgpu_engine *e, int64_t first_step, int64_t count, double *rows);
+/* Attach a host sink [capacity_steps][nchain][nparam+1] (pinned, or page-locked here):
+ * from now on every mcgpu_sample call drains the rows it produced to the sink with
+ * asynchronous copies on a side stream, overlapping the next window's compute (what
+ * MCout::output/collect do with MPI_Gather, mcout.cc:30-94).  mcgpu_synchronize waits
+ * for the drain.  NULL detaches. */
+int  mcgpu_history_attach_host(mcgpu_engine *e, double *rows, size_t capacity_steps);
 /* MCout::maxlike's local part (mcout.cc:96-127): arg-max of logL over the stored
  * history; out = nparam parameters then the value. */
 int  mcgpu_history_maxlike(mcgpu_engine *e, double *out);

@@ -64,6 +64,10 @@ struct mcgpu_engine {
 
   // pinned staging for history reads
   double *pin[2] = {nullptr, nullptr}; size_t pin_bytes = 0; cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+
+  // host sink of the sample history: rows drain to it on the side stream as windows finish
+  double *sink = nullptr; size_t sink_rows_cap = 0; long long sink_sent = 0; bool sink_registered = false;
+  cudaEvent_t sink_ev = nullptr;
 };
 
 namespace {
@@ -391,7 +395,8 @@ int mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out)
     e->M = (cfg->pool_m > 0 && cfg->pool_m < e->N) ? cfg->pool_m : (int)std::min<long long>(e->N, 1 << 20);
     if (cfg->pool_m <= 0 && e->N > (1 << 20)) return bail(MCGPU_EINVAL, "pool_m = 0 (all chains) is limited to 2^20 chains; choose a pool size");
     e->stride = e->N / e->M;
-    e->pool_in_smem = (size_t)e->M * d * 16 + (size_t)(d * d + cfg->sync) * 8 <= 200 * 1024;
+    e->pool_in_smem = true;
+    if ((size_t)e->M * d * 24 + (size_t)(d * d + cfg->sync) * 8 > 200 * 1024) return bail(MCGPU_EINVAL, "remote-mixture pool does not fit in shared memory: choose pool_m with pool_m*nparam <= 8192");
     TRY(dalloc(e, &e->x, (size_t)d * e->ld)); TRY(dalloc(e, &e->ly, (size_t)e->ld));
     TRY(dalloc(e, &e->mu, (size_t)d * e->ld)); TRY(dalloc(e, &e->ps, (size_t)d * e->ld));
     TRY(dalloc(e, &e->factor, (size_t)d * d)); TRY(dalloc(e, &e->counts, 6));
@@ -416,6 +421,13 @@ int mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out)
     e->hist_cap = cfg->history_steps;
     if (e->hist_cap > 0) TRY(dalloc(e, &e->hist, (size_t)e->hist_cap * e->C * (d + 1), false));
     e->host_streams.resize(e->Rl);
+    if (cfg->trace > 0) {                                  // per-step trace of cfg->trace steps
+      e->trace_cap = cfg->trace;
+      const size_t T = (size_t)e->trace_cap * e->Rl;
+      TRY(dalloc(e, &e->tr_accept, T * e->Cr)); TRY(dalloc(e, &e->tr_trial_ly, T * e->Cr));
+      TRY(dalloc(e, &e->tr_trial_p, T * e->Cr * d)); TRY(dalloc(e, &e->tr_cfac, T * e->Cr));
+      TRY(dalloc(e, &e->tr_remote, T)); TRY(dalloc(e, &e->tr_iters, T));
+    }
     std::vector<int> ir(e->Rl, 50);                       // irate = 50, mcpar.cc:57
     if (cudaMemcpyAsync(e->irate_d, ir.data(), ir.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream) != cudaSuccess) return bail(MCGPU_ECUDA, "memcpy failed");
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(MCGPU_ECUDA, "sync failed");
@@ -438,6 +450,9 @@ int mcgpu_destroy(mcgpu_engine *e)
                   e->tr_trial_p, e->tr_cfac, e->tr_iters, e->lik_dev};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) { if (e->pin[i]) cudaFreeHost(e->pin[i]); if (e->pin_ev[i]) cudaEventDestroy(e->pin_ev[i]); }
+  if (e->side) cudaStreamSynchronize(e->side);
+  if (e->sink && e->sink_registered) cudaHostUnregister(e->sink);
+  if (e->sink_ev) cudaEventDestroy(e->sink_ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->side) cudaStreamDestroy(e->side);
   delete e;
@@ -449,7 +464,7 @@ int mcgpu_set_stream(mcgpu_engine *e, void *cuda_stream)
   if (!e) return MCGPU_EINVAL;
   DeviceGuard g(e->dev);
   CK(cudaStreamSynchronize(e->stream));
-  e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  e->stream = (cudaStream_t)cuda_stream;                 // NULL is the legacy default stream
   return MCGPU_OK;
 }
 
@@ -616,7 +631,7 @@ int mcgpu_sample_begin(mcgpu_engine *e, int nsamp)
   DeviceGuard g(e->dev);
   int rc = ready_to_step(e); if (rc) return rc;
   const int d = e->d;
-  e->nsamp = nsamp; e->t_main = 0; e->sampling = true; e->exchange_pending = false; e->hist_kept = 0;
+  e->nsamp = nsamp; e->t_main = 0; e->sampling = true; e->exchange_pending = false; e->hist_kept = 0; e->sink_sent = 0;
   e->nburn_total = (int)e->burn_done;
   const long long need = (nsamp + e->cfg.thin - 1) / e->cfg.thin;
   if (e->hist && need > e->hist_cap) return fail(e, MCGPU_EINVAL, "history_steps too small for nsamp/thin");
@@ -627,16 +642,6 @@ int mcgpu_sample_begin(mcgpu_engine *e, int nsamp)
   CK(cudaMemcpyAsync(e->ps, eps.data(), n * 8, cudaMemcpyHostToDevice, e->stream));
   if (!e->verify) CK(cudaMemsetAsync(e->counts + 4, 0, 16, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  if (e->verify && e->cfg.trace && !e->tr_accept) {
-    e->trace_cap = (int)(e->burn_done + nsamp);
-    const size_t T = (size_t)e->trace_cap * e->Rl;
-    rc = dalloc(e, &e->tr_accept, T * e->Cr); if (rc) return rc;
-    rc = dalloc(e, &e->tr_trial_ly, T * e->Cr); if (rc) return rc;
-    rc = dalloc(e, &e->tr_trial_p, T * e->Cr * d); if (rc) return rc;
-    rc = dalloc(e, &e->tr_cfac, T * e->Cr); if (rc) return rc;
-    rc = dalloc(e, &e->tr_remote, T); if (rc) return rc;
-    rc = dalloc(e, &e->tr_iters, T); if (rc) return rc;
-  }
   return MCGPU_OK;
 }
 
@@ -671,6 +676,14 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
     }
     e->t_main += n; left -= n;
     e->hist_kept = (e->t_main + e->cfg.thin - 1) / e->cfg.thin;
+    if (e->sink && e->hist_kept > e->sink_sent) {          // MCout drain: async D2H on the side stream
+      const size_t row_bytes = (size_t)(e->d + 1) * 8 * e->C;
+      CK(cudaEventRecord(e->sink_ev, e->stream));
+      CK(cudaStreamWaitEvent(e->side, e->sink_ev, 0));
+      CK(cudaMemcpyAsync((char*)e->sink + (size_t)e->sink_sent * row_bytes, (const char*)e->hist + (size_t)e->sink_sent * row_bytes,
+                         (size_t)(e->hist_kept - e->sink_sent) * row_bytes, cudaMemcpyDeviceToHost, e->side));
+      e->sink_sent = e->hist_kept;
+    }
     if (e->t_main % sync == 0) {
       if (e->sharded) e->exchange_pending = true;          // caller all-gathers the published slices
       else if (e->verify) e->snap_cur ^= 1;
@@ -724,6 +737,29 @@ int mcgpu_synchronize(mcgpu_engine *e)
   if (!e) return MCGPU_EINVAL;
   DeviceGuard g(e->dev);
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->side));
+  return MCGPU_OK;
+}
+
+int mcgpu_history_attach_host(mcgpu_engine *e, double *rows, size_t capacity_steps)
+{
+  if (!e) return MCGPU_EINVAL;
+  DeviceGuard g(e->dev);
+  CK(cudaStreamSynchronize(e->side));
+  if (e->sink && e->sink_registered) { cudaHostUnregister(e->sink); e->sink_registered = false; }
+  e->sink = nullptr; e->sink_rows_cap = 0;
+  if (!rows) return MCGPU_OK;
+  if (!e->hist) return fail(e, MCGPU_ESTATE, "engine was created with history_steps = 0");
+  if ((long long)capacity_steps < e->hist_cap) return fail(e, MCGPU_EINVAL, "host sink smaller than history_steps");
+  cudaPointerAttributes at;
+  const bool pinned = cudaPointerGetAttributes(&at, rows) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!pinned) {                                           // page-lock the caller's buffer for DMA
+    CK(cudaHostRegister(rows, capacity_steps * (size_t)e->C * (e->d + 1) * 8, cudaHostRegisterDefault));
+    e->sink_registered = true;
+  }
+  if (!e->sink_ev) CK(cudaEventCreateWithFlags(&e->sink_ev, cudaEventDisableTiming));
+  e->sink = rows; e->sink_rows_cap = capacity_steps; e->sink_sent = e->hist_kept;
   return MCGPU_OK;
 }
 
@@ -814,6 +850,16 @@ int mcgpu_history_read(mcgpu_engine *e, int64_t first_step, int64_t count, doubl
   const size_t total = (size_t)count * e->C * row_bytes;
   const char *src = (const char*)e->hist + (size_t)first_step * e->C * row_bytes;
   if (total == 0) return MCGPU_OK;
+  {
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, rows) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {                                          // page-locked destination: one DMA, no staging
+      CK(cudaMemcpyAsync(rows, src, total, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      return MCGPU_OK;
+    }
+  }
   // drain on the side stream through two pinned staging buffers so the PCIe copy of
   // chunk k overlaps the host memcpy of chunk k-1
   const size_t chunk = (size_t)32 << 20;

@@ -13,9 +13,10 @@ static cudaError_t launch_lik_d(int rngk, bool main_phase, const StepParams &p, 
       cudaFuncSetAttribute(mh_steps_kernel<LIK, D, R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     mh_steps_kernel<LIK, D, R, M><<<grid, MCGPU_BLOCK, smem, st>>>(p);                          \
   } while (0)
-  if (rngk == RNG_PHILOX) { if (main_phase) MCGPU_GO(RNG_PHILOX, true); else MCGPU_GO(RNG_PHILOX, false); }
 #ifdef MCGPU_EXACT_TU
-  else if (rngk == RNG_REPLAY) { if (main_phase) MCGPU_GO(RNG_REPLAY, true); else MCGPU_GO(RNG_REPLAY, false); }
+  if (rngk == RNG_REPLAY) { if (main_phase) MCGPU_GO(RNG_REPLAY, true); else MCGPU_GO(RNG_REPLAY, false); }
+#else
+  if (rngk == RNG_PHILOX) { if (main_phase) MCGPU_GO(RNG_PHILOX, true); else MCGPU_GO(RNG_PHILOX, false); }
 #endif
   else return cudaErrorInvalidValue;
 #undef MCGPU_GO
@@ -43,7 +44,7 @@ bool steps_supported(int lik, int d)
 
 size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem)
 {
-  return sizeof(double) * ((size_t)d * d + (size_t)nsteps + (pool_in_smem ? (size_t)pool_m * d * 2 : 0));
+  return sizeof(double) * ((size_t)d * d + (size_t)nsteps + (pool_in_smem ? (size_t)pool_m * d * 3 : 0));
 }
 
 cudaError_t launch_steps(int lik, int d, int rngk, bool main_phase, const StepParams &p, cudaStream_t st)

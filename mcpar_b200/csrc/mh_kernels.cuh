@@ -85,30 +85,105 @@ template <int D> struct Lik<MCGPU_GAUSSMIX, D> {
   }
 };
 
-// un-normalised diagonal Gaussian Q(x) of mcpar.cc:367-387 / :424-436
-template <int D>
-__device__ __forceinline__ double q_value(const double *ms, const double (&x)[D]) {
-  double arg = 0.0;
-#pragma unroll
-  for (int i = 0; i < D; ++i) {
-    const double xm = ms[2 * i] - x[i];
-    arg += xm * xm / ms[2 * i + 1];
-  }
-  return exp(-0.5 * arg);
-}
-
 // ----------------------------------------------------------------------------
 // Kernel 1: production path
 // ----------------------------------------------------------------------------
+
+// exp2 on the SFU (fp32): used only to BOUND quantities whose exact value is not
+// needed -- decisions fall back to fp64 whenever a bound does not settle them.
+__device__ __forceinline__ float ex2_approx(float x)
+{
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// The accept test  u < exp(delta) * cfac  (mcpar.cc:67-69 / :167-169).  Only the
+// decision is needed, so it is settled by rigorous fp32 bounds on exp(delta) and
+// computed exactly (fp64 exp) only when u falls between the bounds (~1e-4 of cases).
+__device__ __forceinline__ bool accept_test(double u, double delta, double cfac)
+{
+#ifdef MCGPU_EXACT_TU
+  return u < exp(delta) * cfac;
+#else
+  const float dc = fminf(fmaxf((float)delta, -80.0f), 80.0f);
+  const double e = (double)ex2_approx(dc * 1.4426950408889634f);
+  const double lo = (delta >= -80.0) ? e * cfac * (1.0 - 1.0e-4) : 0.0;   // valid lower bound (clamped above 80)
+  const double hi = (delta <= 80.0) ? e * cfac * (1.0 + 1.0e-4) : INFINITY;
+  if (u < lo) return true;
+  if (u >= hi) return false;
+  return u < exp(delta) * cfac;                       // also the NaN path: comparisons above are false
+#endif
+}
+
+// One candidate iteration `it` of genRemote's rejection loop (mcpar.cc:333-443) for the
+// chain with counter (glo,ghi): pick a pool component, draw x' from it, and decide
+// u < max_s Q_s(x') / sum_s Q_s(x').  Pool arrays in shared memory: sPm = mu,
+// sPh = -1/(2 sigma^2), sPs = sigma.  The sum is bounded in fp32 (SFU exp2, online
+// rescaling); the exact fp64 sum is evaluated only if the bounds do not settle u.
+template <int D>
+__device__ __forceinline__ bool remote_candidate(const double *sPm, const double *sPh, const double *sPs, int M,
+                                                 uint32_t glo, uint32_t ghi, uint32_t step, uint32_t it,
+                                                 uint32_t k0, uint32_t k1, int &c, double &amax, double (&xc)[D])
+{
+  const uint32_t slot = MCGPU_SLOT_REMOTE | (it << 6);
+  const Words w = philox4x32_10(glo, ghi, step, slot, k0, k1);
+  c = (int)__umulhi(w.w0, (uint32_t)M);                // viRngUniform(0, tchains), mcpar.cc:337
+  const double u = u53(w.w2, w.w3);                    // vsRngUniform, mcpar.cc:401
+  double z[D + 1];
+#pragma unroll
+  for (int q = 0; 2 * q < D; ++q) {
+    const Words wz = philox4x32_10(glo, ghi, step, slot | (uint32_t)(1 + q), k0, k1);
+    normal_pair(wz, z[2 * q], z[2 * q + 1]);
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) xc[i] = sPm[c * D + i] + sPs[c * D + i] * z[i];   // DIAGONAL storage, :348-350
+
+  double m = -INFINITY;                                // running max of a_s = log Q_s(x')
+  float S = 0.0f;                                      // sum_s exp(a_s - m), fp32
+  for (int s = 0; s < M; ++s) {
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { const double xm = sPm[s * D + i] - xc[i]; a += xm * xm * sPh[s * D + i]; }
+    const double dlt = a - m;
+    const bool gt = dlt > 0.0;
+    const float e = ex2_approx(-fabsf((float)dlt) * 1.4426950408889634f);   // exp(-|a - m|)
+    S = gt ? fmaf(S, e, 1.0f) : S + e;
+    m = gt ? a : m;
+  }
+  amax = m;
+  bool decided = false, acc = false;
+  if (m > -10.0) {                                     // then FPEPS/qmax < 2.3e-10 (mcpar.cc:357-358 offsets)
+    const double eps = 1.0e-4 + 2.0e-5 * (double)M;
+    const double Sd = (double)S;
+    const double r_lo = 1.0 / (Sd * (1.0 + eps) + 3.0e-10);
+    const double r_hi = 1.0 / (Sd * (1.0 - eps));
+    if (u < r_lo) { decided = true; acc = true; }
+    else if (u >= r_hi) { decided = true; acc = false; }
+  }
+  if (!decided) {                                      // exact: pacpt = qimax / qisum, :355-398
+    double qmax = MCGPU_FPEPS, qsum = MCGPU_FPEPS;
+    for (int s = 0; s < M; ++s) {
+      double a = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) { const double xm = sPm[s * D + i] - xc[i]; a += xm * xm * sPh[s * D + i]; }
+      const double gv = exp(a);
+      qsum += gv; qmax = gv > qmax ? gv : qmax;
+    }
+    acc = u < qmax / qsum;
+  }
+  return acc;
+}
+
 template <int LIK, int D, int RNGK, bool MAIN>
 __global__ void __launch_bounds__(128)
 mh_steps_kernel(const StepParams p)
 {
   extern __shared__ double smem[];
-  // smem: [0, D*D) factor | [D*D, D*D+nsteps) 1/pwgt table | pool copy
+  // smem: [0, D*D) factor | [D*D, D*D+nsteps) 1/pwgt table | pool: mu, -1/(2 sig^2), sigma
   double *sT = smem;
   double *sW = smem + D * D;
-  const double *pool = p.pool_cur;
+  double *sPm = sW + p.nsteps, *sPh = sPm + p.pool_m * D, *sPs = sPh + p.pool_m * D;
 
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = j < p.C;
@@ -121,11 +196,11 @@ mh_steps_kernel(const StepParams p)
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) sT[i] = p.factor[i];
   if (MAIN) {
     for (int k = threadIdx.x; k < p.nsteps; k += blockDim.x) sW[k] = 1.0 / (double)(p.t0 + k + 1);
-    if (p.pool_in_smem && p.t0 + p.nsteps > p.sync) {
-      double *sP = sW + p.nsteps;
-      for (int i = threadIdx.x; i < p.pool_m * D * 2; i += blockDim.x) sP[i] = p.pool_cur[i];
-      pool = sP;
-    }
+    if (RNGK == RNG_PHILOX && p.t0 + p.nsteps > p.sync)
+      for (int i = threadIdx.x; i < p.pool_m * D; i += blockDim.x) {
+        const double s2 = p.pool_cur[i * 2 + 1];
+        sPm[i] = p.pool_cur[i * 2]; sPh[i] = -0.5 / s2; sPs[i] = sqrt(s2);     // sigma = sqrt(sig^2), mcpar.cc:346
+      }
   }
   __syncthreads();
 
@@ -171,6 +246,62 @@ mh_steps_kernel(const StepParams p)
     double xt[D];
     double cfac = 1.0;
     int cpick = 0;                                     // component the accepted remote draw came from
+
+    if constexpr (RNGK == RNG_PHILOX && MAIN) {
+      // ---- genRemote over the pool (mcpar.cc:315-451), warp-cooperative ----------------
+      // The reference's rejection loop tries candidate iterations it = 0,1,2,... until one
+      // is accepted.  Candidates are independent counter-based draws, so the warp evaluates
+      // 32 of them per round, spread over the chains still looping (finished chains' lanes
+      // help the stragglers), and each chain takes its FIRST accepted candidate in
+      // iteration order: the same outcome as the sequential loop, without divergence.
+      unsigned rm = __ballot_sync(0xffffffffu, remote && live);
+      if (rm) {
+        uint32_t it_next = 0;
+        bool pending = remote && live;
+        double amax_acc = 0.0;
+        while (rm) {
+          const int n = __popc(rm);
+          const int r = lane % n, kk = lane / n;
+          const int tgt = __fns(rm, 0, r + 1);                       // lane owning the r-th unfinished chain
+          const uint32_t it = __shfl_sync(0xffffffffu, it_next, tgt) + (uint32_t)kk;
+          const uint32_t tlo = __shfl_sync(0xffffffffu, glo, tgt), thi = __shfl_sync(0xffffffffu, ghi, tgt);
+          int c; double am; double xc[D];
+          const bool acc = remote_candidate<D>(sPm, sPh, sPs, p.pool_m, tlo, thi, step, it, p.key0, p.key1, c, am, xc);
+          const unsigned accmask = __ballot_sync(0xffffffffu, acc);
+          unsigned pat = 0;                                           // lanes r, r+n, r+2n, ... serve chain rank r
+          for (int l = 0; l < 32; l += n) pat |= 1u << l;
+          int src = lane;
+          bool fin = false;
+          if (pending) {
+            const int my_r = __popc(rm & ((1u << lane) - 1u));
+            const unsigned cm = pat << my_r;
+            const unsigned hit = accmask & cm;
+            if (hit) { src = __ffs(hit) - 1; fin = true; }           // lowest lane = lowest iteration index
+            else it_next += (uint32_t)__popc(cm);
+          }
+          const int c_s = __shfl_sync(0xffffffffu, c, src);
+          const double am_s = __shfl_sync(0xffffffffu, am, src);
+#pragma unroll
+          for (int i = 0; i < D; ++i) { const double v = __shfl_sync(0xffffffffu, xc[i], src); if (fin) xt[i] = v; }
+          if (fin) { cpick = c_s; amax_acc = am_s; pending = false; }
+          if (it_next >= (1u << 24) - 64u) pending = false;          // slot space exhausted (never in practice)
+          rm = __ballot_sync(0xffffffffu, pending);
+        }
+        if (remote) {
+          // cfac = max_i Q_i(x_old) / max_i Q_i(x'), mcpar.cc:412-439
+          double aold = -INFINITY;
+          for (int s = 0; s < p.pool_m; ++s) {
+            double a = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) { const double xm = sPm[s * D + i] - x[i]; a += xm * xm * sPh[s * D + i]; }
+            aold = a > aold ? a : aold;
+          }
+          double qmax = exp(amax_acc);
+          qmax = qmax > MCGPU_FPEPS ? qmax : MCGPU_FPEPS;              // qimax starts at FPEPS, :357
+          cfac = exp(aold) / qmax;
+        }
+      }
+    }
     if (!remote) {
       // genLocal: x' = x + T z, T row-major lower (mcpar.cc:302-312)
       double z[D + 1];
@@ -191,46 +322,10 @@ mh_steps_kernel(const StepParams p)
         for (int q = 0; q <= i; ++q) acc += sT[i * D + q] * z[q];
         xt[i] = acc;
       }
-    } else {
-      // genRemote over the pool: rejection-sample max_i Q_i from sum_i Q_i (mcpar.cc:333-443),
-      // each chain running its own loop
-      double qmax = MCGPU_FPEPS;
-      for (uint32_t it = 0;; ++it) {
-        const uint32_t slot = MCGPU_SLOT_REMOTE | (it << 6);
-        const Words w = philox4x32_10(glo, ghi, step, slot, p.key0, p.key1);
-        cpick = (int)__umulhi(w.w0, (uint32_t)p.pool_m);
-        const double u = u53(w.w2, w.w3);
-        double z[D + 1];
-#pragma unroll
-        for (int q = 0; 2 * q < D; ++q) {
-          const Words wz = philox4x32_10(glo, ghi, step, slot | (uint32_t)(1 + q), p.key0, p.key1);
-          normal_pair(wz, z[2 * q], z[2 * q + 1]);
-        }
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-          xt[i] = pool[(cpick * D + i) * 2] + sqrt(pool[(cpick * D + i) * 2 + 1]) * z[i];
-        qmax = MCGPU_FPEPS;
-        double qsum = MCGPU_FPEPS;
-        for (int s = 0; s < p.pool_m; ++s) {
-          const double gv = q_value<D>(pool + (size_t)s * D * 2, xt);
-          qsum += gv;
-          qmax = gv > qmax ? gv : qmax;
-        }
-        if (u < qmax / qsum) break;
-        if (it >= (1u << 24) - 1) break;
-      }
-      double qold = 0.0;
-      for (int s = 0; s < p.pool_m; ++s) {
-        const double gv = q_value<D>(pool + (size_t)s * D * 2, x);
-        qold = gv > qold ? gv : qold;
-      }
-      cfac = qold / qmax;                              // mcpar.cc:412-439
     }
 
     const double lyt = Lik<LIK, D>::eval(xt, p);
-    double pac = exp(lyt - ly);                        // mcpar.cc:67 / :167
-    if (MAIN) pac *= cfac;
-    const bool a = u_acc < pac;
+    const bool a = accept_test(u_acc, lyt - ly, MAIN ? cfac : 1.0);   // mcpar.cc:67-69 / :167-169
     if (a) {
       ly = lyt;
 #pragma unroll
@@ -250,8 +345,8 @@ mh_steps_kernel(const StepParams p)
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         if (adopt) {                                   // sigma -> sigma^2 round trip of :346,:447-448
-          const double sd = sqrt(pool[(cpick * D + i) * 2 + 1]);
-          mu[i] = pool[(cpick * D + i) * 2];
+          const double sd = sPs[cpick * D + i];
+          mu[i] = sPm[cpick * D + i];
           ps[i] = (sd * sd) * (pwgt - 1.0);
         }
         const double delta = x[i] - mu[i];

@@ -22,7 +22,7 @@ EXPORTS = [
     "mcgpu_set_streams", "mcgpu_burnin", "mcgpu_sample_begin", "mcgpu_sample",
     "mcgpu_exchange_begin", "mcgpu_exchange_end", "mcgpu_tuning_counters", "mcgpu_burnin_some",
     "mcgpu_tune", "mcgpu_synchronize", "mcgpu_get_state", "mcgpu_get_factor", "mcgpu_get_musig",
-    "mcgpu_get_trace", "mcgpu_history_read", "mcgpu_history_maxlike", "mcgpu_history_moments",
+    "mcgpu_get_trace", "mcgpu_history_read", "mcgpu_history_attach_host", "mcgpu_history_maxlike", "mcgpu_history_moments",
     "mcgpu_get_stats", "mcgpu_device_ptr", "mcgpu_loglik", "mcgpu_qriguess",
     "mcgpu_measure_fp64_peak",
 ]
@@ -125,7 +125,7 @@ class Engine:
 
     def __init__(self, nparam, nchain, *, mode="normal", nchain_total=None, chain0=0,
                  chains_per_rank=0, pl=0.9, armin=0.2, armax=0.5, dfac=0.2, ifac=1.5, sync=10,
-                 seed=8675309, coin_group=32, pool_m=0, thin=1, trace=False, history_steps=0,
+                 seed=8675309, coin_group=32, pool_m=0, thin=1, trace=0, history_steps=0,
                  device=0):
         self.lib = load()
         cfg = Config()
@@ -273,6 +273,17 @@ class Engine:
         rows = out if out is not None else np.empty((count, self.C, self.d + 1))
         self._ck(self.lib.mcgpu_history_read(self.h, C.c_int64(first), C.c_int64(count), _p(rows)))
         return rows
+
+    def attach_host_sink(self, rows):
+        """rows: C-contiguous float64 [capacity_steps][nchain][nparam+1] host array (kept alive
+        by the caller); subsequent sample() calls drain into it asynchronously."""
+        if rows is None:
+            self._ck(self.lib.mcgpu_history_attach_host(self.h, None, C.c_size_t(0)))
+            self._sink = None
+            return
+        assert rows.dtype == np.float64 and rows.flags.c_contiguous and rows.shape[1:] == (self.C, self.d + 1)
+        self._sink = rows
+        self._ck(self.lib.mcgpu_history_attach_host(self.h, _p(rows), C.c_size_t(rows.shape[0])))
 
     def maxlike(self):
         out = np.empty(self.d + 1)
