@@ -207,35 +207,22 @@ def main():
     pin = tiled_pinit(N, d)[rank * Cg:(rank + 1) * Cg]
     e.set_state(pin)
 
-    # ---- sharded helpers: the pool all-gather and the tuning all-reduce over NCCL
-    pool_views = {}
-
-    def exchange():
-        buf, off, own = e.exchange_begin()
-        key = buf.ptr
-        if key not in pool_views:
-            full = torch.as_tensor(buf, device=dev)
-            pool_views[key] = (full, full[off // 8:(off + own) // 8])
-        full, mine = pool_views[key]
-        dist.all_gather_into_tensor(full, mine)
-        e.exchange_end()
+    # ---- sharded runs: pool all-gather + tuning all-reduce over NCCL (mcpar_b200/sharded.py)
+    from mcpar_b200.sharded import ShardedRunner, DistGroup
+    as_tensor = lambda ptr: torch.as_tensor(ptr, device=dev)
+    runner = [ShardedRunner(e, DistGroup(dist), as_tensor) if world > 1 else None]
 
     def burn(n):
         if world == 1:
-            e.burnin(n); return
-        cnt = torch.as_tensor(e.tuning_counters(), device=dev)
-        left = n
-        while left > 0:
-            done, pend = e.burnin_some(left)
-            left -= done
-            if pend:
-                dist.all_reduce(cnt)
-                e.tune()
+            e.burnin(n)
+        else:
+            runner[0].burnin(n)
 
     def window():
-        e.sample(sync)
-        if world > 1:
-            exchange()
+        if world == 1:
+            e.sample(sync)
+        else:
+            runner[0].window(sync)
 
     burn(nburn)
     e.sample_begin(nsamp)
@@ -292,7 +279,7 @@ def main():
             t1 = time.perf_counter()
             e.set_state(host_pin)                                       # H2D inside the timed region
             e.attach_host_sink(host_rows)                               # D2H drains on a side stream per window
-            pool_views.clear()
+            runner[0] = ShardedRunner(e, DistGroup(dist), as_tensor) if world > 1 else None
             burn(nb_e)
             e.sample_begin(ns_e)
             for _ in range(ns_e // sync):

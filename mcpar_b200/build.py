@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
     def cc(item):
         src, extra = item
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [NVCC] + ARCH + COMMON + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + ARCH + COMMON + extra + os.environ.get("MCGPU_NVCC_FLAGS", "").split() + \
+            ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,0 +1,135 @@
+// mcgpu_math.cuh -- fp64 exp / log / sincos(2 pi u) for the production step kernels.
+//
+// Why not CUDA's libm: its double routines carry every polynomial coefficient as an
+// immediate (two UMOV per constant, ~90 issue slots per MH step) and evaluate long
+// minimax polynomials.  These routines reduce the argument with small lookup tables
+// held in SHARED memory (3.5 KB per CTA) so that degree-5/6 Taylor kernels suffice
+// (~10 DFMA for exp and log, ~16 for the sin/cos pair), at <= 1.5 ulp.
+// They serve the normal (Philox) mode only; the verification instantiations keep
+// CUDA's libm so that they stay an independent check.
+//
+// All functions are __host__ __device__ so tests/test_math_host.cu can measure their
+// accuracy on the CPU against long-double references.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+
+#ifdef __CUDACC__
+#define MCGPU_HD __host__ __device__ __forceinline__
+#else
+#define MCGPU_HD inline
+#endif
+
+namespace mcgpu {
+
+struct MathTables { const double *exp_tab, *log_tab, *trig_tab; };
+
+MCGPU_HD int mc_hi(double x) {
+#ifdef __CUDA_ARCH__
+  return __double2hiint(x);
+#else
+  uint64_t b; memcpy(&b, &x, 8); return (int)(b >> 32);
+#endif
+}
+MCGPU_HD int mc_lo(double x) {
+#ifdef __CUDA_ARCH__
+  return __double2loint(x);
+#else
+  uint64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)b;
+#endif
+}
+MCGPU_HD double mc_make(int hi, int lo) {
+#ifdef __CUDA_ARCH__
+  return __hiloint2double(hi, lo);
+#else
+  uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+
+#define MCGPU_MAGIC 6755399441055744.0      /* 1.5 * 2^52: adding it leaves rint(x) in the low word */
+
+// Scalar coefficients live in CONSTANT memory on the device so that DFMA takes them as
+// c[bank][offset] operands; as literals each would cost two UMOV issue slots per use.
+#define MCGPU_COEF_LIST                                                                         \
+  MCGPU_64_OVER_LN2, -MCGPU_LN2_64_HI, -MCGPU_LN2_64_LO, MCGPU_MAGIC,       /* 0-3  exp reduce */ \
+  1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0,                              /* 4-8  exp poly   */ \
+  -1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, -0.5, -1.0,                             /* 9-14 log poly   */ \
+  MCGPU_LN2_HI, MCGPU_LN2_LO,                                                /* 15-16           */ \
+  64.0, -1.0 / 64.0, MCGPU_TWO_PI,                                           /* 17-19 trig red. */ \
+  -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0,                                    /* 20-22 sin       */ \
+  1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -0.5,                             /* 23-26 cos       */ \
+  -708.0, 709.0, -2.0, 0.0                                                   /* 27-30 misc      */
+#if defined(__CUDACC__) && !defined(MCGPU_MATH_HOST_ONLY)
+static __constant__ double mc_coef_dev[] = {MCGPU_COEF_LIST};
+#endif
+static const double mc_coef_host[] = {MCGPU_COEF_LIST};
+#ifdef __CUDA_ARCH__
+#define MCK(i) mc_coef_dev[i]
+#else
+#define MCK(i) mc_coef_host[i]
+#endif
+
+// exp(x).  x < -708 flushes to 0 (the true value is below the normal range);
+// x > 709 gives +inf; NaN propagates.
+MCGPU_HD double mc_exp(double x, const MathTables &T)
+{
+  if (x < MCK(27)) return 0.0;
+  if (x > MCK(28)) return INFINITY;
+  const double nd = fma(x, MCK(0), MCK(3));
+  const int n = mc_lo(nd);
+  const double nf = nd - MCK(3);
+  double r = fma(nf, MCK(1), x);
+  r = fma(nf, MCK(2), r);                             // |r| <= ln2/128
+  const double t = T.exp_tab[n & 63];
+  double p = fma(r, MCK(4), MCK(5));                  // Taylor, error r^6/720 < 4e-17
+  p = fma(p, r, MCK(6));
+  p = fma(p, r, MCK(7));
+  p = fma(p, r, MCK(8));
+  const double res = fma(t, p * r, t);                // 2^(j/64) * e^r
+  return mc_make(mc_hi(res) + ((n >> 6) << 20), mc_lo(res));   // * 2^k, k in [-1022, 1023]
+}
+
+// log(x) for normal positive x; everything else goes to libm.
+MCGPU_HD double mc_log(double x, const MathTables &T)
+{
+  const int hi = mc_hi(x);
+  if (hi < 0x00100000 || hi >= 0x7ff00000) return log(x);   // <= 0, subnormal, inf, NaN
+  const int idx = (hi >> 13) & 127;
+  const int big = idx >= 53;                           // m >= 1.4140625: use m/2, exponent + 1
+  const int e = (hi >> 20) - 1023 + big;
+  const double m = mc_make((hi & 0x000fffff) | (big ? 0x3fe00000 : 0x3ff00000), mc_lo(x));
+  const double c = T.log_tab[2 * idx], l = T.log_tab[2 * idx + 1];
+  const double r = fma(m, c, MCK(14));                 // |r| < 2^-8
+  double p = fma(r, MCK(9), MCK(10));                  // log1p(r) = r + r^2 p(r), error r^7/7 < 2e-18
+  p = fma(p, r, MCK(11));
+  p = fma(p, r, MCK(12));
+  p = fma(p, r, MCK(13));
+  const double lg = fma(r * r, p, r);
+  const double ef = (double)e;
+  double res = fma(ef, MCK(15), l);                    // exact-ish: LN2_HI has 26 trailing zero bits
+  res += lg;
+  return fma(ef, MCK(16), res);
+}
+
+// (sin, cos)(2 pi u) for u in [0, 1]
+MCGPU_HD void mc_sincos2pi(double u, double &s, double &c, const MathTables &T)
+{
+  const double kd = fma(u, MCK(17), MCK(3));
+  const int k = mc_lo(kd);
+  const double f = fma(kd - MCK(3), MCK(18), u);               // exact, |f| <= 1/128
+  const double b = f * MCK(19);                                // |b| <= pi/64
+  const double sa = T.trig_tab[2 * (k & 63)], ca = T.trig_tab[2 * (k & 63) + 1];
+  const double b2 = b * b;
+  double ps = fma(b2, MCK(20), MCK(21));                       // sin b = b + b^3 ps, error b^9/9!
+  ps = fma(ps, b2, MCK(22));
+  const double sb = fma(b * b2, ps, b);
+  double pc = fma(b2, MCK(23), MCK(24));                       // cos b - 1 = b^2 pc, error b^10/10!
+  pc = fma(pc, b2, MCK(25));
+  pc = fma(pc, b2, MCK(26));
+  const double cm1 = pc * b2;
+  s = fma(ca, sb, fma(sa, cm1, sa));
+  c = fma(-sa, sb, fma(ca, cm1, ca));
+}
+
+}  // namespace mcgpu

@@ -1,11 +1,18 @@
 // mh_dispatch.inl -- (likelihood, d, rng, phase) -> kernel instantiation table.
 // Included inside namespace mcgpu::MCGPU_NS by mh_fast.cu and mh_exact.cu.
 
-#define MCGPU_BLOCK 128
+// CTA size of the step kernels (<= 128, the kernels' launch bound); MCGPU_BLOCK env overrides for tuning
+static int step_block()
+{
+  static int b = 0;
+  if (!b) { const char *e = getenv("MCGPU_BLOCK"); b = e ? atoi(e) : 64; if (b != 32 && b != 64 && b != 128) b = 64; }
+  return b;
+}
 
 template <int LIK, int D>
 static cudaError_t launch_lik_d(int rngk, bool main_phase, const StepParams &p, size_t smem, cudaStream_t st)
 {
+  const int MCGPU_BLOCK = step_block();
   const unsigned grid = (unsigned)((p.C + MCGPU_BLOCK - 1) / MCGPU_BLOCK);
 #define MCGPU_GO(R, M)                                                                          \
   do {                                                                                          \
@@ -44,7 +51,7 @@ bool steps_supported(int lik, int d)
 
 size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem)
 {
-  return sizeof(double) * ((size_t)d * d + (size_t)nsteps + (pool_in_smem ? (size_t)pool_m * d * 3 : 0));
+  return sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)d * d + (size_t)((nsteps + 1) & ~1) + (pool_in_smem ? (size_t)pool_m * d * 3 : 0));
 }
 
 cudaError_t launch_steps(int lik, int d, int rngk, bool main_phase, const StepParams &p, cudaStream_t st)

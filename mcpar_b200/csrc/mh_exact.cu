@@ -3,6 +3,7 @@
 // batched likelihood evaluation.  Bit-comparable with the CPU oracle.
 #define MCGPU_NS exact
 #define MCGPU_EXACT_TU 1
+#include <stdlib.h>
 #include "mh_kernels.cuh"
 namespace mcgpu { namespace exact {
 #include "mh_dispatch.inl"

@@ -18,11 +18,49 @@
 #pragma once
 #include "mcgpu_device.cuh"
 #include "../../include/mcgpu.h"
+#ifndef MCGPU_EXACT_TU
+#define MCGPU_TABLE_QUAL static __device__
+#include "mcgpu_tables.h"
+#else
+#define MCGPU_64_OVER_LN2 0.0
+#define MCGPU_LN2_64_HI 0.0
+#define MCGPU_LN2_64_LO 0.0
+#define MCGPU_LN2_HI 0.0
+#define MCGPU_LN2_LO 0.0
+#define MCGPU_TWO_PI 0.0
+#endif
+#include "mcgpu_math.cuh"
 
 namespace mcgpu {
 namespace MCGPU_NS {
 
 enum { RNG_PHILOX = 0, RNG_REPLAY = 1 };
+
+// transcendental calls of the step kernels: table-driven routines in the production
+// unit, CUDA libm in the exact (verification) unit
+#ifdef MCGPU_EXACT_TU
+#define MC_EXP(x) exp(x)
+#define MC_LOG(x) log(x)
+#define MCGPU_MATH_SMEM 0
+#else
+#define MC_EXP(x) mc_exp((x), T)
+#define MC_LOG(x) mc_log((x), T)
+#define MCGPU_MATH_SMEM (MCGPU_EXP_TAB + 2 * MCGPU_LOG_TAB + 2 * MCGPU_TRIG_TAB)   /* doubles */
+#endif
+
+// Box-Muller pair, MKL BOXMULLER2 convention: z0 = r sin(2 pi u2), z1 = r cos(2 pi u2)
+__device__ __forceinline__ void normal_pair_t(const Words &w, double &z0, double &z1, const MathTables &T)
+{
+#ifdef MCGPU_EXACT_TU
+  normal_pair(w, z0, z1);
+#else
+  const double u1 = u53(w.w0, w.w1), u2 = u53(w.w2, w.w3);
+  const double r = sqrt(fmax(-2.0 * mc_log(1.0 - u1, T), 0.0));
+  double s, c;
+  mc_sincos2pi(u2, s, c, T);
+  z0 = r * s; z1 = r * c;
+#endif
+}
 
 // ----------------------------------------------------------------------------
 // likelihood functors (device side of the VLFunc plugin surface)
@@ -31,7 +69,7 @@ template <int LIK, int D> struct Lik;
 
 // Rosenbrock1::operator(), rosenbrock.cc:4-21: non-overlapping pairs
 template <int D> struct Lik<MCGPU_ROSENBROCK1, D> {
-  static __device__ __forceinline__ double eval(const double (&x)[D], const StepParams &) {
+  static __device__ __forceinline__ double eval(const double (&x)[D], const StepParams &, const MathTables &) {
     double y = 0.0;
 #pragma unroll
     for (int i = 0; i + 1 < D; i += 2) {
@@ -45,7 +83,7 @@ template <int D> struct Lik<MCGPU_ROSENBROCK1, D> {
 
 // Gaussian::operator(), rosenbrock.cc:44-61; lp = {mu0, mu1, 1/sig2_0, 1/sig2_1}
 template <> struct Lik<MCGPU_GAUSSIAN, 2> {
-  static __device__ __forceinline__ double eval(const double (&x)[2], const StepParams &p) {
+  static __device__ __forceinline__ double eval(const double (&x)[2], const StepParams &p, const MathTables &T) {
     double y = 0.0;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -59,18 +97,18 @@ template <> struct Lik<MCGPU_GAUSSIAN, 2> {
 // DualGaussian::operator(), rosenbrock.cc:63-78; lp = {w}.  No log-sum-exp guard,
 // as in the reference: far from both modes this is log(0) = -inf.
 template <> struct Lik<MCGPU_DUALGAUSSIAN, 2> {
-  static __device__ __forceinline__ double eval(const double (&x)[2], const StepParams &p) {
+  static __device__ __forceinline__ double eval(const double (&x)[2], const StepParams &p, const MathTables &T) {
     const double arg1 = 0.5 * (x[0] * x[0] + x[1] * x[1]);
     const double t2a = x[0] - 5.0, t2b = x[1] - 5.0;
     const double arg2 = 0.5 * (t2a * t2a + t2b * t2b);
-    return log(p.lp[0] * exp(-arg1) + exp(-arg2));
+    return MC_LOG(p.lp[0] * MC_EXP(-arg1) + MC_EXP(-arg2));
   }
 };
 
 // GaussMix (new): log sum_k w_k exp(-1/2 sum_i (x_i-mu_ki)^2/s2_ki)
 // with log-sum-exp.  lik_dev = {mu[K][d], 1/s2[K][d], log w[K]} (prepared on upload).
 template <int D> struct Lik<MCGPU_GAUSSMIX, D> {
-  static __device__ __forceinline__ double eval(const double (&x)[D], const StepParams &p) {
+  static __device__ __forceinline__ double eval(const double (&x)[D], const StepParams &p, const MathTables &T) {
     const int K = p.lik_k;
     const double *mu = p.lik_dev, *is2 = mu + (size_t)K * D, *lw = is2 + (size_t)K * D;
     double m = -INFINITY, s = 0.0;
@@ -79,9 +117,9 @@ template <int D> struct Lik<MCGPU_GAUSSMIX, D> {
 #pragma unroll
       for (int i = 0; i < D; ++i) { const double xm = x[i] - mu[k * D + i]; q += xm * xm * is2[k * D + i]; }
       const double a = lw[k] - 0.5 * q;
-      if (a > m) { s = s * exp(m - a) + 1.0; m = a; } else s += exp(a - m);
+      if (a > m) { s = s * MC_EXP(m - a) + 1.0; m = a; } else s += MC_EXP(a - m);
     }
-    return m + log(s);
+    return m + MC_LOG(s);
   }
 };
 
@@ -122,9 +160,10 @@ __device__ __forceinline__ bool accept_test(double u, double delta, double cfac)
 // sPh = -1/(2 sigma^2), sPs = sigma.  The sum is bounded in fp32 (SFU exp2, online
 // rescaling); the exact fp64 sum is evaluated only if the bounds do not settle u.
 template <int D>
-__device__ __forceinline__ bool remote_candidate(const double *sPm, const double *sPh, const double *sPs, int M,
+__device__ __forceinline__ bool remote_candidate(const double2 *sPmh, const double *sPs, int M,
                                                  uint32_t glo, uint32_t ghi, uint32_t step, uint32_t it,
-                                                 uint32_t k0, uint32_t k1, int &c, double &amax, double (&xc)[D])
+                                                 uint32_t k0, uint32_t k1, int &c, double &amax, double (&xc)[D],
+                                                 const MathTables &T)
 {
   const uint32_t slot = MCGPU_SLOT_REMOTE | (it << 6);
   const Words w = philox4x32_10(glo, ghi, step, slot, k0, k1);
@@ -134,22 +173,39 @@ __device__ __forceinline__ bool remote_candidate(const double *sPm, const double
 #pragma unroll
   for (int q = 0; 2 * q < D; ++q) {
     const Words wz = philox4x32_10(glo, ghi, step, slot | (uint32_t)(1 + q), k0, k1);
-    normal_pair(wz, z[2 * q], z[2 * q + 1]);
+    normal_pair_t(wz, z[2 * q], z[2 * q + 1], T);
   }
 #pragma unroll
-  for (int i = 0; i < D; ++i) xc[i] = sPm[c * D + i] + sPs[c * D + i] * z[i];   // DIAGONAL storage, :348-350
+  for (int i = 0; i < D; ++i) xc[i] = sPmh[c * D + i].x + sPs[c * D + i] * z[i];   // DIAGONAL storage, :348-350
 
-  double m = -INFINITY;                                // running max of a_s = log Q_s(x')
+  // a_s = log Q_s(x') for the pool in chunks of 8: the 8 quadratic forms, their max and
+  // their fp32 exp-sum are independent instruction streams (ILP), chunks are merged by
+  // one rescale each.  fp32 enters only through S (a bound); m stays exact fp64.
+  constexpr int CH = 8;
+  constexpr float L2E = 1.4426950408889634f;
+  double m = -INFINITY;                                // running max of a_s
   float S = 0.0f;                                      // sum_s exp(a_s - m), fp32
-  for (int s = 0; s < M; ++s) {
-    double a = 0.0;
+  for (int s0 = 0; s0 < M; s0 += CH) {
+    double a[CH];
 #pragma unroll
-    for (int i = 0; i < D; ++i) { const double xm = sPm[s * D + i] - xc[i]; a += xm * xm * sPh[s * D + i]; }
-    const double dlt = a - m;
-    const bool gt = dlt > 0.0;
-    const float e = ex2_approx(-fabsf((float)dlt) * 1.4426950408889634f);   // exp(-|a - m|)
-    S = gt ? fmaf(S, e, 1.0f) : S + e;
-    m = gt ? a : m;
+    for (int q = 0; q < CH; ++q) {
+      const int s = s0 + q < M ? s0 + q : M - 1;
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) { const double2 mh = sPmh[s * D + i]; const double xm = mh.x - xc[i]; acc += xm * xm * mh.y; }
+      a[q] = s0 + q < M ? acc : -INFINITY;
+    }
+    double mc = a[0];
+#pragma unroll
+    for (int q = 1; q < CH; ++q) mc = a[q] > mc ? a[q] : mc;
+    const float mcf = (float)mc;
+    float sc = 0.0f;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) sc += ex2_approx(((float)a[q] - mcf) * L2E);     // exp(a_q - mc), each <= 1
+    const bool gt = mc > m;
+    const float e = ex2_approx(-fabsf((float)(m - mc)) * L2E);                    // exp(-|m - mc|); 0 on the first chunk
+    S = gt ? fmaf(S, e, sc) : fmaf(sc, e, S);
+    m = gt ? mc : m;
   }
   amax = m;
   bool decided = false, acc = false;
@@ -166,7 +222,7 @@ __device__ __forceinline__ bool remote_candidate(const double *sPm, const double
     for (int s = 0; s < M; ++s) {
       double a = 0.0;
 #pragma unroll
-      for (int i = 0; i < D; ++i) { const double xm = sPm[s * D + i] - xc[i]; a += xm * xm * sPh[s * D + i]; }
+      for (int i = 0; i < D; ++i) { const double2 mh = sPmh[s * D + i]; const double xm = mh.x - xc[i]; a += xm * xm * mh.y; }
       const double gv = exp(a);
       qsum += gv; qmax = gv > qmax ? gv : qmax;
     }
@@ -175,15 +231,28 @@ __device__ __forceinline__ bool remote_candidate(const double *sPm, const double
   return acc;
 }
 
+#ifndef MCGPU_MINB
+#define MCGPU_MINB 6      // d = 2: cap registers at 80 (6 CTAs of 128 per SM); gpurun_out/tune.log sweep
+#endif
 template <int LIK, int D, int RNGK, bool MAIN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (D <= 2 ? MCGPU_MINB : 1))
 mh_steps_kernel(const StepParams p)
 {
   extern __shared__ double smem[];
-  // smem: [0, D*D) factor | [D*D, D*D+nsteps) 1/pwgt table | pool: mu, -1/(2 sig^2), sigma
-  double *sT = smem;
-  double *sW = smem + D * D;
-  double *sPm = sW + p.nsteps, *sPh = sPm + p.pool_m * D, *sPs = sPh + p.pool_m * D;
+  // smem: math tables | [D*D] factor | [nsteps] 1/pwgt table | pool: mu, -1/(2 sig^2), sigma
+  double *sT = smem + MCGPU_MATH_SMEM;
+  double *sW = sT + D * D;
+  double2 *sPmh = reinterpret_cast<double2*>(sW + ((p.nsteps + 1) & ~1));     // (mu, -1/(2 sig^2)) pairs, 16-byte aligned
+  double *sPs = reinterpret_cast<double*>(sPmh + p.pool_m * D);
+  MathTables T;
+#ifndef MCGPU_EXACT_TU
+  T.exp_tab = smem; T.log_tab = smem + MCGPU_EXP_TAB; T.trig_tab = T.log_tab + 2 * MCGPU_LOG_TAB;
+  for (int i = threadIdx.x; i < MCGPU_EXP_TAB; i += blockDim.x) smem[i] = MCGPU_EXP_TABLE[i];
+  for (int i = threadIdx.x; i < 2 * MCGPU_LOG_TAB; i += blockDim.x) smem[MCGPU_EXP_TAB + i] = MCGPU_LOG_TABLE[i];
+  for (int i = threadIdx.x; i < 2 * MCGPU_TRIG_TAB; i += blockDim.x) smem[MCGPU_EXP_TAB + 2 * MCGPU_LOG_TAB + i] = MCGPU_TRIG_TABLE[i];
+#else
+  T.exp_tab = T.log_tab = T.trig_tab = nullptr;
+#endif
 
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = j < p.C;
@@ -199,7 +268,7 @@ mh_steps_kernel(const StepParams p)
     if (RNGK == RNG_PHILOX && p.t0 + p.nsteps > p.sync)
       for (int i = threadIdx.x; i < p.pool_m * D; i += blockDim.x) {
         const double s2 = p.pool_cur[i * 2 + 1];
-        sPm[i] = p.pool_cur[i * 2]; sPh[i] = -0.5 / s2; sPs[i] = sqrt(s2);     // sigma = sqrt(sig^2), mcpar.cc:346
+        sPmh[i] = make_double2(p.pool_cur[i * 2], -0.5 / s2); sPs[i] = sqrt(s2);     // sigma = sqrt(sig^2), mcpar.cc:346
       }
   }
   __syncthreads();
@@ -266,7 +335,7 @@ mh_steps_kernel(const StepParams p)
           const uint32_t it = __shfl_sync(0xffffffffu, it_next, tgt) + (uint32_t)kk;
           const uint32_t tlo = __shfl_sync(0xffffffffu, glo, tgt), thi = __shfl_sync(0xffffffffu, ghi, tgt);
           int c; double am; double xc[D];
-          const bool acc = remote_candidate<D>(sPm, sPh, sPs, p.pool_m, tlo, thi, step, it, p.key0, p.key1, c, am, xc);
+          const bool acc = remote_candidate<D>(sPmh, sPs, p.pool_m, tlo, thi, step, it, p.key0, p.key1, c, am, xc, T);
           const unsigned accmask = __ballot_sync(0xffffffffu, acc);
           unsigned pat = 0;                                           // lanes r, r+n, r+2n, ... serve chain rank r
           for (int l = 0; l < 32; l += n) pat |= 1u << l;
@@ -293,12 +362,12 @@ mh_steps_kernel(const StepParams p)
           for (int s = 0; s < p.pool_m; ++s) {
             double a = 0.0;
 #pragma unroll
-            for (int i = 0; i < D; ++i) { const double xm = sPm[s * D + i] - x[i]; a += xm * xm * sPh[s * D + i]; }
+            for (int i = 0; i < D; ++i) { const double2 mh = sPmh[s * D + i]; const double xm = mh.x - x[i]; a += xm * xm * mh.y; }
             aold = a > aold ? a : aold;
           }
-          double qmax = exp(amax_acc);
+          double qmax = MC_EXP(amax_acc);
           qmax = qmax > MCGPU_FPEPS ? qmax : MCGPU_FPEPS;              // qimax starts at FPEPS, :357
-          cfac = exp(aold) / qmax;
+          cfac = MC_EXP(aold) / qmax;
         }
       }
     }
@@ -309,7 +378,7 @@ mh_steps_kernel(const StepParams p)
 #pragma unroll
         for (int q = 0; 2 * q < D; ++q) {
           const Words w = philox4x32_10(glo, ghi, step, (uint32_t)q, p.key0, p.key1);
-          normal_pair(w, z[2 * q], z[2 * q + 1]);
+          normal_pair_t(w, z[2 * q], z[2 * q + 1], T);
         }
       } else {
 #pragma unroll
@@ -324,7 +393,7 @@ mh_steps_kernel(const StepParams p)
       }
     }
 
-    const double lyt = Lik<LIK, D>::eval(xt, p);
+    const double lyt = Lik<LIK, D>::eval(xt, p, T);
     const bool a = accept_test(u_acc, lyt - ly, MAIN ? cfac : 1.0);   // mcpar.cc:67-69 / :167-169
     if (a) {
       ly = lyt;
@@ -346,7 +415,7 @@ mh_steps_kernel(const StepParams p)
       for (int i = 0; i < D; ++i) {
         if (adopt) {                                   // sigma -> sigma^2 round trip of :346,:447-448
           const double sd = sPs[cpick * D + i];
-          mu[i] = sPm[cpick * D + i];
+          mu[i] = sPmh[cpick * D + i].x;
           ps[i] = (sd * sd) * (pwgt - 1.0);
         }
         const double delta = x[i] - mu[i];
@@ -418,7 +487,13 @@ __global__ void init_loglik_kernel(const StepParams p)
   double x[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) x[i] = p.x[i * p.ld + j];
-  p.ly[j] = Lik<LIK, D>::eval(x, p);
+  MathTables T;
+#ifndef MCGPU_EXACT_TU
+  T.exp_tab = MCGPU_EXP_TABLE; T.log_tab = MCGPU_LOG_TABLE; T.trig_tab = MCGPU_TRIG_TABLE;   // global-memory tables
+#else
+  T.exp_tab = T.log_tab = T.trig_tab = nullptr;
+#endif
+  p.ly[j] = Lik<LIK, D>::eval(x, p, T);
 }
 
 #ifdef MCGPU_EXACT_TU

@@ -228,3 +228,108 @@ def test_normal_mode_matches_counter_oracle(lik, d, N, par, pool_m, pl):
     assert abs(s["accepted"] - int(o["counts"][0])) <= max(2, nsamp * N // 5000)
     assert o["remote"][nburn:].any(), "test must exercise the remote branch"
     e.close()
+
+
+# ---------------------------------------------------------------- sharding
+def test_two_sharded_engines_equal_one_engine():
+    """Chains sharded over two engines (host-driven exchange + summed tuning counters, the
+    protocol mcpar_b200/sharded.py runs over NCCL) reproduce the single-engine run bit for
+    bit: Philox is keyed on the global chain id, tuning is global, the pool is all-gathered."""
+    import torch
+    eng = _engine()
+    d, N, nburn, nsamp, M, pl = 2, 512, 130, 60, 16, 0.7
+    pin = tiled_pinit(N, d)
+    one = eng.Engine(d, N, mode="normal", pool_m=M, pl=pl, history_steps=nsamp)
+    one.run(nsamp, nburn, pin, "rosenbrock1")
+    ref_state, ref_hist, ref_factor = one.state(), one.history(), one.factor()
+    one.close()
+
+    half = N // 2
+    es = [eng.Engine(d, half, mode="normal", nchain_total=N, chain0=r * half, pool_m=M, pl=pl,
+                     history_steps=nsamp) for r in range(2)]
+    for r, e in enumerate(es):
+        e.set_likelihood("rosenbrock1"); e.set_covariance(None); e.set_state(pin[r * half:(r + 1) * half])
+    dev = torch.device("cuda", 0)
+    cnts = [torch.as_tensor(e.tuning_counters(), device=dev) for e in es]
+    left = nburn
+    while left > 0:                                              # burn-in with all-reduced counters
+        done = [e.burnin_some(left) for e in es]
+        assert done[0] == done[1]
+        left -= done[0][0]
+        if done[0][1]:
+            [e.synchronize() for e in es]
+            tot = cnts[0] + cnts[1]
+            cnts[0].copy_(tot); cnts[1].copy_(tot)
+            torch.cuda.synchronize()
+            [e.tune() for e in es]
+    [e.sample_begin(nsamp) for e in es]
+    t = 0
+    while t < nsamp:
+        n = min(10, nsamp - t)
+        [e.sample(n) for e in es]
+        t += n
+        if t % 10 == 0:                                          # "all-gather": copy each owner's slice to the peer
+            [e.synchronize() for e in es]
+            bufs = [e.exchange_begin() for e in es]
+            views = [torch.as_tensor(b[0], device=dev) for b in bufs]
+            for r in range(2):
+                off, own = bufs[r][1] // 8, bufs[r][2] // 8
+                views[1 - r][off:off + own].copy_(views[r][off:off + own])
+            torch.cuda.synchronize()
+            [e.exchange_end() for e in es]
+    [e.synchronize() for e in es]
+    st = [e.state() for e in es]
+    assert np.array_equal(np.concatenate([s["p"] for s in st]), ref_state["p"])
+    assert np.array_equal(np.concatenate([s["psum2"] for s in st]), ref_state["psum2"])
+    assert np.array_equal(np.concatenate([e.history() for e in es], axis=1), ref_hist)
+    assert np.array_equal(es[0].factor(), ref_factor) and np.array_equal(es[1].factor(), ref_factor)
+    [e.close() for e in es]
+
+
+# ---------------------------------------------------------------- statistics (normal mode)
+def test_posterior_moments_local_only_rosenbrock():
+    """PLOCAL = 1: analytic Rosenbrock moments from the device-side
+    moment accumulation over the stored history."""
+    eng = _engine()
+    N = 1 << 14
+    e = eng.Engine(2, N, mode="normal", pl=1.0, thin=20, history_steps=400)
+    e.run(8000, 500, tiled_pinit(N, 2), "rosenbrock1")
+    h = e.history(150)                                           # drop the first 3000 steps
+    r = h.reshape(-1, 3)
+    assert abs(r[:, 0].mean() - 1.0) < 0.01 and abs(r[:, 1].mean() - 1.5) < 0.03
+    assert abs(r[:, 0].var() - 0.5) < 0.02 and abs(r[:, 1].var() - 2.505) < 0.15
+    assert abs(np.cov(r[:, 0], r[:, 1])[0, 1] - 1.0) < 0.05
+    mean, cov = e.moments()                                      # device reduction agrees with the host one
+    hh = e.history().reshape(-1, 3)
+    assert np.allclose(mean, hh[:, :2].mean(0), rtol=1e-9) and np.allclose(cov, np.cov(hh[:, :2].T, bias=True), rtol=1e-7)
+    e.close()
+
+
+def test_ks_local_only_dualgaussian_marginal():
+    """PLOCAL = 1 from a start in the (0,0) mode: chains essentially stay there, so the x
+    marginal of the visited mode is N(0,1); KS at p > 0.01 on thinned, decorrelated draws."""
+    from scipy import stats
+    eng = _engine()
+    N = 1 << 13
+    e = eng.Engine(2, N, mode="normal", pl=1.0, thin=400, history_steps=3)
+    e.run(1200, 500, np.zeros((N, 2)), "dualgaussian", [5.0])
+    x = e.history()[2, :, 0]                                     # one draw per chain: independent across chains
+    x = x[np.abs(x) < 2.4]                                       # stay clear of the saddle towards (5,5)
+    tn = stats.truncnorm(-2.4, 2.4)
+    assert stats.kstest(x, tn.cdf).pvalue > 0.01
+    e.close()
+
+
+def test_remote_proposals_agree_with_counter_oracle_statistically():
+    """PLOCAL = 0.9 with a pool: two-sample KS of the GPU chains against the CPU oracle's
+    normal-mode semantics run with a different seed (distribution, not trajectory)."""
+    from scipy import stats
+    eng = _engine()
+    N, M = 2048, 16
+    pin = tiled_pinit(N, 2)
+    o = mh.run_counter("dualgaussian", 2, N, 400, 300, pin, par=[5.0], pool_m=M, seed=12345, thin=100)
+    e = eng.Engine(2, N, mode="normal", pool_m=M, thin=100, history_steps=4)
+    e.run(400, 300, pin, "dualgaussian", [5.0])
+    g = e.history()[3, :, :2]; c = o["rows"][3, :, :2]
+    assert stats.ks_2samp(g[:, 0], c[:, 0]).pvalue > 0.01 and stats.ks_2samp(g[:, 1], c[:, 1]).pvalue > 0.01
+    e.close()
