@@ -392,8 +392,10 @@ int mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out)
     if (cfg->chain0 % 32) return bail(MCGPU_EINVAL, "chain0 must be a multiple of 32");
     if (e->replay_local && e->sharded) return bail(MCGPU_EINVAL, "REPLAY_LOCAL hosts the whole rank");
     e->ld = (e->C + 31) / 32 * 32;
+    const bool never_remote = cfg->pl >= 1.0;              // the coin is < 1: rndlocal <= PLOCAL always (mcpar.cc:152)
     e->M = (cfg->pool_m > 0 && cfg->pool_m < e->N) ? cfg->pool_m : (int)std::min<long long>(e->N, 1 << 20);
-    if (cfg->pool_m <= 0 && e->N > (1 << 20)) return bail(MCGPU_EINVAL, "pool_m = 0 (all chains) is limited to 2^20 chains; choose a pool size");
+    if (never_remote && cfg->pool_m <= 0) e->M = 1;        // pool is never read: keep one slot
+    if (!never_remote && cfg->pool_m <= 0 && e->N > (1 << 20)) return bail(MCGPU_EINVAL, "pool_m = 0 (all chains) is limited to 2^20 chains; choose a pool size");
     e->stride = e->N / e->M;
     e->pool_in_smem = true;
     if ((size_t)e->M * d * 24 + (size_t)(d * d + cfg->sync) * 8 > 200 * 1024) return bail(MCGPU_EINVAL, "remote-mixture pool does not fit in shared memory: choose pool_m with pool_m*nparam <= 8192");
