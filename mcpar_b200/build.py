@@ -29,6 +29,8 @@ def _sources():
     out = [os.path.join(ROOT, "include", "mcgpu.h")]
     for f in os.listdir(CSRC):
         out.append(os.path.join(CSRC, f))
+    for f in os.listdir(os.path.join(HERE, "host")):
+        out.append(os.path.join(HERE, "host", f))
     return out
 
 
@@ -64,7 +66,30 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    build_host()
     return LIB
+
+
+HOST = os.path.join(HERE, "host")
+BIN = os.path.join(HERE, "bin")
+DRIVERS = ["mcpar-rosen1", "mcpar-dgauss", "mcpar-rosen2"]
+
+
+def build_host():
+    """libmcpar.so (C++ MCPar/MCout/VLFunc/mcutil mirror above the C ABI) + the driver mains."""
+    os.makedirs(BIN, exist_ok=True)
+    cxx = ["/usr/bin/g++", "-std=c++11", "-O2", "-fPIC", "-I", HOST, "-I", os.path.join(ROOT, "include")]
+    lib = os.path.join(HERE, "libmcpar.so")
+    srcs = [os.path.join(HOST, f) for f in ("likelihoods.cc", "mcout.cc", "mcutil.cc", "mcpar.cc")]
+    r = subprocess.run(cxx + ["-shared", "-o", lib] + srcs + ["-L", HERE, "-lmcgpu", "-Wl,-rpath,$ORIGIN"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host library build failed:\n" + r.stderr)
+    for d in DRIVERS:
+        r = subprocess.run(cxx + ["-o", os.path.join(BIN, d), os.path.join(HOST, d + ".cc"), "-L", HERE, "-lmcpar",
+                                  "-lmcgpu", "-Wl,-rpath,$ORIGIN/.."], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("driver build failed (%s):\n%s" % (d, r.stderr))
 
 
 if __name__ == "__main__":

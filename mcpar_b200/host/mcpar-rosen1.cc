@@ -1,0 +1,37 @@
+// mcpar-rosen1 -- 2-D Rosenbrock demo with the reference's command line and output
+// (src/mcpar-rosen1.cc): `mcpar-rosen1 [nsamp]` prints "nsamp = N" and then every sample
+// row; 4 chains per rank from the four fixed starting points.  `mpirun -np R` becomes
+// --ranks=R (all ranks live on the GPU); extra flags never disturb the positional form.
+#include <iostream>
+#include <stdlib.h>
+#include <string.h>
+#include "mcpar.hh"
+#include "rosenbrock.hh"
+#include "mcout.hh"
+
+int main(int argc, char *argv[])
+{
+  const int nparam = 2;
+  int nsamp = 100000, ranks = 1, npos = 0;
+  int pool = 0, thin = 1;
+  for (int i = 1; i < argc; ++i) {
+    if (!strncmp(argv[i], "--ranks=", 8)) ranks = atoi(argv[i] + 8);
+    else if (!strncmp(argv[i], "--pool=", 7)) pool = atoi(argv[i] + 7);
+    else if (!strncmp(argv[i], "--thin=", 7)) thin = atoi(argv[i] + 7);
+    else if (npos++ == 0) nsamp = atoi(argv[i]);
+  }
+  try {
+    Rosenbrock1 L(2);
+    MCout rslts(nparam, &std::cout, 0);
+    std::cout << "nsamp = " << nsamp << "\n";
+    MCPar mcpar(nparam, 4, ranks, 0);
+    mcpar.pool_m = pool; mcpar.thin = thin;
+    Real pinit[8] = {0.0, 0.0, 2.0, 2.0, 0.0, 1.5, 0.0, -2.0};
+    mcpar.run(nsamp, 500, pinit, L, rslts);
+    rslts.output();
+  } catch (const char *msg) {
+    std::cerr << msg << "\n";
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,43 @@
+// mcpar.hh -- the MH driver with the reference's interface (src/mcpar.hh:10-91), hosted on
+// the B200 engine through the C ABI (include/mcgpu.h).  One process owns all "ranks":
+// mpisiz is the number of rank-sized chain groups (nc chains each) and mpirank must be 0.
+#ifndef MCPAR_B200_MCPAR_HH_
+#define MCPAR_B200_MCPAR_HH_
+#include "vlfunc.hh"
+#include "mcout.hh"
+
+struct mcgpu_engine;
+
+class MCPar {
+public:
+  enum { OK, INVALID, ERROR };
+  const Real TGT_ARATE_MIN, TGT_ARATE_MAX, SCALE_DEC, SCALE_INC, PLOCAL;
+  const int SYNCSTEP;
+  static const Real FPEPS;
+
+  bool logging;                 // user switches, as in the reference (src/mcpar.hh:28-29)
+  int logstep;
+
+  // engine options beyond the reference's constructor (set before run())
+  int device;                   // CUDA ordinal
+  int pool_m;                   // remote-mixture pool size; 0 = every chain, as the reference
+  int thin;                     // keep every thin-th step
+  unsigned long long seed;      // Philox key; reference seed by default (mcpar.cc:271)
+
+  MCPar(int np, int nc = 1, int mpisiz = 1, int mpirank = 0, Real pl = 0.9, Real armin = 0.2,
+        Real armax = 0.5, Real dfac = 0.2, Real ifac = 1.5, int sync = 10);
+  ~MCPar();
+
+  int run(int nsamp, int nburn, const Real *pinit, VLFunc &L, MCout &outsamples, Real *incov = 0);
+
+  double last_device_ms() const { return mdevice_ms; }
+  double last_accept_rate() const { return maccept; }
+
+private:
+  int nparam, nchain, size, rank, tchains;
+  mcgpu_engine *eng;
+  double mdevice_ms, maccept;
+  MCPar(const MCPar &); MCPar &operator=(const MCPar &);
+};
+
+#endif

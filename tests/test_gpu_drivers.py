@@ -1,0 +1,88 @@
+"""GPU tests of the C++ host mirror (mcpar_b200/host: MCPar / MCout / VLFunc classes above
+the C ABI) through the driver mains: the reference's command-line, stdout, log-file and
+per-rank-file contract (src/mcpar-rosen1.cc, src/mcpar-dgauss.cc, src/mcpar.cc:23-28,
+:110-119; row order relied on by src/anly/mcpar-analysis.R:80-120)."""
+import os
+import subprocess
+import numpy as np
+import pytest
+
+from conftest import tiled_pinit
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "mcpar_b200", "bin")
+
+
+def _engine_rows(lik, par, d, ranks, nsamp, nburn, incov=None):
+    """Same run through the Python binding, re-ordered the way MCPar::run feeds MCout:
+    batches of outstep steps -> rank-major -> step-major -> chain."""
+    from mcpar_b200 import engine
+    N = 4 * ranks
+    e = engine.Engine(d, N, mode="normal", coin_group=4, pool_m=0, history_steps=nsamp)
+    e.run(nsamp, nburn, np.tile(tiled_pinit(4, d), (ranks, 1)), lik, par, incov)
+    h = e.history().reshape(nsamp, ranks, 4, d + 1)
+    e.close()
+    outstep = nsamp // 10 if nsamp > 50 else 5
+    out = []
+    for s0 in range(0, nsamp, outstep):
+        blk = h[s0:s0 + outstep]                         # [step][rank][chain]
+        out.append(blk.transpose(1, 0, 2, 3).reshape(-1, d + 1))
+    return np.concatenate(out)
+
+
+def test_mcpar_rosen1_contract(tmp_path):
+    nsamp, ranks = 60, 3
+    r = subprocess.run([os.path.join(BIN, "mcpar-rosen1"), str(nsamp), "--ranks=%d" % ranks], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "nsamp = %d" % nsamp                              # mcpar-rosen1.cc:35-36
+    rows = lines[1:]
+    assert len(rows) == nsamp * 4 * ranks                                 # nsamp x nc x mpisiz rows
+    assert all(l.endswith("  ") and len(l.split()) == 3 for l in rows)   # "v  v  v  "
+    got = np.array([[float(t) for t in l.split()] for l in rows])
+    exp = _engine_rows("rosenbrock1", None, 2, ranks, nsamp, 500)
+    assert np.allclose(got, exp, rtol=2e-5, atol=1e-6)                    # 6 significant digits in the text
+    log = open(tmp_path / "mcpar-log.000.txt").read().splitlines()        # mcpar.cc:56,:111-112,:116-118
+    assert log[0] == "Starting burn-in.  Samples = 500"
+    assert log[1] == "Starting main sample loop:  nsamp = 60" and log[2] == "Output after each 6 steps."
+    assert log[3] == "Beginning output at step 6" and log[4] == "Output finished"
+
+
+def test_mcpar_rosen1_default_positional_only(tmp_path):
+    r = subprocess.run([os.path.join(BIN, "mcpar-rosen1"), "12"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.splitlines()[0] == "nsamp = 12"
+    assert len(r.stdout.splitlines()) == 1 + 12 * 4
+
+
+def test_mcpar_dgauss_contract(tmp_path):
+    ranks = 2
+    r = subprocess.run([os.path.join(BIN, "mcpar-dgauss"), "--ranks=%d" % ranks], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert len(lines) == 8 * 4 * ranks + 2                                # run(8, 500): rows + 2 max-likelihood lines
+    assert lines[-2].startswith("max likelihood value: ")
+    exp = _engine_rows("dualgaussian", [5.0], 2, ranks, 8, 500)
+    got = np.array([[float(t) for t in l.split()] for l in lines[:-2]])
+    assert np.allclose(got, exp, rtol=2e-5, atol=1e-6)
+    best = exp[np.argmax(exp[:, 2])]
+    assert np.isclose(float(lines[-2].split(":")[1]), best[2], rtol=2e-5)
+    assert np.allclose([float(t) for t in lines[-1].split()], best[:2], rtol=2e-5, atol=1e-6)
+    for rk in range(ranks):                                               # mcpar-dgauss.RRR.txt, parameters only, tabs
+        f = open(tmp_path / ("mcpar-dgauss.%03d.txt" % rk)).read().splitlines()
+        assert len(f) == 8 * 4 and all(l.endswith("\t") and len(l.split()) == 2 for l in f)
+
+
+def test_mcpar_rosen2_d16(tmp_path):
+    r = subprocess.run([os.path.join(BIN, "mcpar-rosen2"), "20", "--ranks=2"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "nsamp = 20" and len(lines) == 1 + 20 * 8
+    got = np.array([[float(t) for t in l.split()] for l in lines[1:]])
+    assert got.shape[1] == 17
+    blk = (2.38 ** 2 / 16) * np.array([[0.5, 1.0], [1.0, 2.505]])
+    exp = _engine_rows("rosenbrock1", None, 16, 2, 20, 500, np.kron(np.eye(8), blk))
+    assert np.allclose(got, exp, rtol=2e-5, atol=1e-6)
