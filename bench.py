@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--chains", type=int, default=1 << 20, help="chains per GPU")
     ap.add_argument("--pool", type=int, default=16, help="remote-mixture pool size M")
     ap.add_argument("--pl", type=float, default=0.9)
+    ap.add_argument("--coin-group", type=int, default=0, help="0: one local/remote coin per step for the whole job; 1..32: per group of chains")
     ap.add_argument("--thin", type=int, default=10)
     ap.add_argument("--sync", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -201,7 +202,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)                 # engine kernels, NCCL ops and timing events share it
     e = engine.Engine(d, Cg, mode="normal", nchain_total=N, chain0=rank * Cg, pl=args.pl, sync=sync,
-                      seed=SEED, pool_m=args.pool, thin=thin, history_steps=kept, device=local)
+                      seed=SEED, pool_m=args.pool, thin=thin, coin_group=args.coin_group, history_steps=kept, device=local)
     e.set_stream(stream.cuda_stream)
     e.set_likelihood(W["lik"], W["par"]); e.set_covariance(incov_for(args.workload))
     pin = tiled_pinit(N, d)[rank * Cg:(rank + 1) * Cg]
@@ -273,7 +274,7 @@ def main():
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             e = engine.Engine(d, Cg, mode="normal", nchain_total=N, chain0=rank * Cg, pl=args.pl, sync=sync,
-                              seed=SEED, pool_m=args.pool, thin=thin, history_steps=kept_e, device=local)
+                              seed=SEED, pool_m=args.pool, thin=thin, coin_group=args.coin_group, history_steps=kept_e, device=local)
             e.set_stream(stream.cuda_stream)
             e.set_likelihood(W["lik"], W["par"]); e.set_covariance(incov_for(args.workload))
             t1 = time.perf_counter()
@@ -332,9 +333,11 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "%s: %s d=%d, %d chains/GPU x %d GPU, PLOCAL %.2f, SYNCSTEP %d, pool M=%d, thin %d, "
+                "config": {"workload": "%s: %s d=%d, %d chains/GPU x %d GPU, PLOCAL %.2f, SYNCSTEP %d, pool M=%d, %s, thin %d, "
                                        "seed %d; step = one %d-step exchange window" % (
-                                           W["name"], W["lik"], d, Cg, world, args.pl, sync, args.pool, thin, SEED, sync),
+                                           W["name"], W["lik"], d, Cg, world, args.pl, sync, args.pool,
+                                           "one local/remote coin per step" if args.coin_group == 0 else "coin per %d chains" % args.coin_group,
+                                           thin, SEED, sync),
                            "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
                            "parallelism": "chains sharded by global id, pool all-gather over NCCL each window" if world > 1 else "single GPU"},
                 "clocks": ck, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,

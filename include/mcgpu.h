@@ -76,7 +76,9 @@ typedef struct mcgpu_config {
   int32_t sync;             /* SYNCSTEP                                              */
   double  pl, armin, armax, dfac, ifac;
   uint64_t seed;            /* Philox key (reference seed 8675309, mcpar.cc:271)     */
-  int32_t coin_group;       /* NORMAL: chains sharing the local/remote coin (1..32, power of 2) */
+  int32_t coin_group;       /* NORMAL: chains sharing the local/remote coin: 0 = one coin per step for the
+                               whole job ("one coin per rank", mcpar.cc:106-109, the rank being the job);
+                               1..32 (power of 2) = one coin per group of consecutive chains */
   int32_t pool_m;           /* NORMAL: remote-mixture pool size; 0 = all chains      */
   int32_t thin;             /* keep every thin-th main step in the sample history    */
   int32_t trace;            /* VERIFY: steps of per-step accept/trial trace to keep (0 = none) */

@@ -146,11 +146,29 @@ void fill_step_params(mcgpu_engine *e, StepParams &p)
   p.nburn_total = e->nburn_total;
 }
 
-cudaError_t launch_steps_any(mcgpu_engine *e, bool main_phase, const StepParams &p)
+cudaError_t launch_steps_any(mcgpu_engine *e, int phase, const StepParams &p)
 {
   ++e->launches;
-  if (e->replay_local) return exact::launch_steps(e->lik, e->d, 1, main_phase, p, e->stream);
-  return fast::launch_steps(e->lik, e->d, 0, main_phase, p, e->stream);
+  if (e->replay_local) return exact::launch_steps(e->lik, e->d, 1, phase == PH_BURN ? PH_BURN : PH_LOCAL, p, e->stream);
+  return fast::launch_steps(e->lik, e->d, 0, phase, p, e->stream);
+}
+
+// Host copy of the device's Philox4x32-10 (mcgpu_device.cuh): with a job-wide coin the host
+// evaluates each step's local/remote draw itself -- words 2,3 of chain 0's accept block -- and
+// plans PH_LOCAL / PH_REMOTE launches without a device round trip.
+double host_coin(const mcgpu_engine *e, uint32_t step)
+{
+  uint32_t c0 = 0, c1 = 0, c2 = step, c3 = MCGPU_SLOT_ACCEPT;
+  uint32_t k0 = (uint32_t)e->cfg.seed, k1 = (uint32_t)(e->cfg.seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const unsigned long long bits = 0x3FF0000000000000ull | ((((unsigned long long)c2 << 32) | c3) >> 12);
+  double u; memcpy(&u, &bits, 8);
+  return u - 1.0;
 }
 
 int upload_streams(mcgpu_engine *e)
@@ -388,7 +406,7 @@ int mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out)
   TRY(dalloc(e, &e->overrun, 1));
   if (!e->verify) {
     if (cfg->mode != MCGPU_MODE_NORMAL && cfg->mode != MCGPU_MODE_REPLAY_LOCAL) return bail(MCGPU_EINVAL, "unknown mode");
-    if (cfg->coin_group < 1 || cfg->coin_group > 32 || (cfg->coin_group & (cfg->coin_group - 1))) return bail(MCGPU_EINVAL, "coin_group must be a power of two in 1..32");
+    if (cfg->coin_group < 0 || cfg->coin_group > 32 || (cfg->coin_group & (cfg->coin_group - 1))) return bail(MCGPU_EINVAL, "coin_group must be 0 (job-wide coin) or a power of two in 1..32");
     if (cfg->chain0 % 32) return bail(MCGPU_EINVAL, "chain0 must be a multiple of 32");
     if (e->replay_local && e->sharded) return bail(MCGPU_EINVAL, "REPLAY_LOCAL hosts the whole rank");
     e->ld = (e->C + 31) / 32 * 32;
@@ -568,7 +586,7 @@ static int burnin_some(mcgpu_engine *e, int nmax, int *ndone)
   const int n = (int)std::min<long long>(nmax, boundary - e->burn_done);
   StepParams p; fill_step_params(e, p);
   p.counts = e->counts; p.step0 = (uint32_t)e->burn_done; p.nsteps = n; p.t0 = 0;
-  CK(launch_steps_any(e, false, p));
+  CK(launch_steps_any(e, PH_BURN, p));
   e->burn_done += n; *ndone = n;
   if (e->burn_done == boundary) e->tune_pending = true;
   return 0;
@@ -671,10 +689,28 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
     } else {
       StepParams p; fill_step_params(e, p);
       p.counts = e->counts + 4;
-      p.step0 = (uint32_t)(e->nburn_total + e->t_main); p.nsteps = n; p.t0 = (int)e->t_main;
-      p.pool_cur = e->pool[e->pool_cur]; p.pool_next = e->pool[e->pool_cur ^ 1];
+      p.pool_cur = e->pool[e->pool_cur];
       p.hist = e->hist; p.hist_step0 = 0;
-      CK(launch_steps_any(e, true, p));
+      if (e->cfg.coin_group > 0 || e->replay_local) {       // per-group coins: one mixed launch per window
+        p.step0 = (uint32_t)(e->nburn_total + e->t_main); p.nsteps = n; p.t0 = (int)e->t_main;
+        p.pool_next = e->pool[e->pool_cur ^ 1];
+        CK(launch_steps_any(e, PH_MIXED, p));
+      } else {                                               // job-wide coin: runs of local / remote steps
+        int k = 0;
+        while (k < n) {
+          const long long t = e->t_main + k;
+          auto is_remote = [&](long long tt) {
+            return tt >= sync && !(host_coin(e, (uint32_t)(e->nburn_total + tt)) <= e->cfg.pl);   // mcpar.cc:142-152
+          };
+          const bool rem = is_remote(t);
+          int len = 1;
+          while (k + len < n && is_remote(t + len) == rem) ++len;
+          p.step0 = (uint32_t)(e->nburn_total + t); p.nsteps = len; p.t0 = (int)t;
+          p.pool_next = (k + len == n) ? e->pool[e->pool_cur ^ 1] : nullptr;    // publish at the end of the window
+          CK(launch_steps_any(e, rem ? PH_REMOTE : PH_LOCAL, p));
+          k += len;
+        }
+      }
     }
     e->t_main += n; left -= n;
     e->hist_kept = (e->t_main + e->cfg.thin - 1) / e->cfg.thin;

@@ -37,11 +37,11 @@ __device__ __forceinline__ Words philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return w;
 }
 
-// 53-bit uniform in [0,1) from two words
+// uniform in [0,1) from two words: the top 52 bits fill the mantissa of a double in [1,2),
+// then subtract 1 (two shifts, one LOP, one DADD; no integer->double conversion)
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo)
 {
-  const unsigned long long b = ((unsigned long long)hi << 32) | lo;
-  return (double)(b >> 11) * (1.0 / 9007199254740992.0);
+  return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12))) - 1.0;
 }
 
 // Box-Muller pair, MKL BOXMULLER2 convention: z0 = r sin(2 pi u2), z1 = r cos(2 pi u2)

@@ -90,11 +90,13 @@ MCGPU_HD double mc_exp(double x, const MathTables &T)
   return mc_make(mc_hi(res) + ((n >> 6) << 20), mc_lo(res));   // * 2^k, k in [-1022, 1023]
 }
 
-// log(x) for normal positive x; everything else goes to libm.
+// log(x) for normal positive x.  0 and subnormals give -inf (their logs, below -708, only
+// ever mark proposals that are rejected anyway), negative x gives NaN, +inf and NaN pass through.
 MCGPU_HD double mc_log(double x, const MathTables &T)
 {
   const int hi = mc_hi(x);
-  if (hi < 0x00100000 || hi >= 0x7ff00000) return log(x);   // <= 0, subnormal, inf, NaN
+  if (hi < 0x00100000 || hi >= 0x7ff00000)             // <= 0, subnormal, inf, NaN
+    return hi < 0 && x < 0.0 ? NAN : (hi >= 0x7ff00000 && hi > 0 ? x : -INFINITY);
   const int idx = (hi >> 13) & 127;
   const int big = idx >= 53;                           // m >= 1.4140625: use m/2, exponent + 1
   const int e = (hi >> 20) - 1023 + big;

@@ -10,7 +10,7 @@ static int step_block()
 }
 
 template <int LIK, int D>
-static cudaError_t launch_lik_d(int rngk, bool main_phase, const StepParams &p, size_t smem, cudaStream_t st)
+static cudaError_t launch_lik_d(int rngk, int phase, const StepParams &p, size_t smem, cudaStream_t st)
 {
   const int MCGPU_BLOCK = step_block();
   const unsigned grid = (unsigned)((p.C + MCGPU_BLOCK - 1) / MCGPU_BLOCK);
@@ -21,9 +21,13 @@ static cudaError_t launch_lik_d(int rngk, bool main_phase, const StepParams &p, 
     mh_steps_kernel<LIK, D, R, M><<<grid, MCGPU_BLOCK, smem, st>>>(p);                          \
   } while (0)
 #ifdef MCGPU_EXACT_TU
-  if (rngk == RNG_REPLAY) { if (main_phase) MCGPU_GO(RNG_REPLAY, true); else MCGPU_GO(RNG_REPLAY, false); }
+  if (rngk == RNG_REPLAY && phase == PH_BURN) MCGPU_GO(RNG_REPLAY, PH_BURN);
+  else if (rngk == RNG_REPLAY && phase == PH_LOCAL) MCGPU_GO(RNG_REPLAY, PH_LOCAL);
 #else
-  if (rngk == RNG_PHILOX) { if (main_phase) MCGPU_GO(RNG_PHILOX, true); else MCGPU_GO(RNG_PHILOX, false); }
+  if (rngk == RNG_PHILOX && phase == PH_BURN) MCGPU_GO(RNG_PHILOX, PH_BURN);
+  else if (rngk == RNG_PHILOX && phase == PH_MIXED) MCGPU_GO(RNG_PHILOX, PH_MIXED);
+  else if (rngk == RNG_PHILOX && phase == PH_LOCAL) MCGPU_GO(RNG_PHILOX, PH_LOCAL);
+  else if (rngk == RNG_PHILOX && phase == PH_REMOTE) MCGPU_GO(RNG_PHILOX, PH_REMOTE);
 #endif
   else return cudaErrorInvalidValue;
 #undef MCGPU_GO
@@ -31,13 +35,13 @@ static cudaError_t launch_lik_d(int rngk, bool main_phase, const StepParams &p, 
 }
 
 template <int LIK>
-static cudaError_t launch_lik(int d, int rngk, bool main_phase, const StepParams &p, size_t smem, cudaStream_t st)
+static cudaError_t launch_lik(int d, int rngk, int phase, const StepParams &p, size_t smem, cudaStream_t st)
 {
   switch (d) {
-    case 2:  return launch_lik_d<LIK, 2>(rngk, main_phase, p, smem, st);
-    case 4:  return launch_lik_d<LIK, 4>(rngk, main_phase, p, smem, st);
-    case 8:  return launch_lik_d<LIK, 8>(rngk, main_phase, p, smem, st);
-    case 16: return launch_lik_d<LIK, 16>(rngk, main_phase, p, smem, st);
+    case 2:  return launch_lik_d<LIK, 2>(rngk, phase, p, smem, st);
+    case 4:  return launch_lik_d<LIK, 4>(rngk, phase, p, smem, st);
+    case 8:  return launch_lik_d<LIK, 8>(rngk, phase, p, smem, st);
+    case 16: return launch_lik_d<LIK, 16>(rngk, phase, p, smem, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -51,17 +55,17 @@ bool steps_supported(int lik, int d)
 
 size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem)
 {
-  return sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)d * d + (size_t)((nsteps + 1) & ~1) + (pool_in_smem ? (size_t)pool_m * d * 3 : 0));
+  return sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)d * d + (size_t)((nsteps + 1) & ~1) + (pool_in_smem ? (size_t)((pool_m + 7) & ~7) * d * 3 : 0));
 }
 
-cudaError_t launch_steps(int lik, int d, int rngk, bool main_phase, const StepParams &p, cudaStream_t st)
+cudaError_t launch_steps(int lik, int d, int rngk, int phase, const StepParams &p, cudaStream_t st)
 {
   const size_t smem = steps_smem_bytes(d, p.nsteps, p.pool_m, p.pool_in_smem != 0);
   switch (lik) {
-    case MCGPU_ROSENBROCK1:  return launch_lik<MCGPU_ROSENBROCK1>(d, rngk, main_phase, p, smem, st);
-    case MCGPU_GAUSSMIX:     return launch_lik<MCGPU_GAUSSMIX>(d, rngk, main_phase, p, smem, st);
-    case MCGPU_GAUSSIAN:     return d == 2 ? launch_lik_d<MCGPU_GAUSSIAN, 2>(rngk, main_phase, p, smem, st) : cudaErrorInvalidValue;
-    case MCGPU_DUALGAUSSIAN: return d == 2 ? launch_lik_d<MCGPU_DUALGAUSSIAN, 2>(rngk, main_phase, p, smem, st) : cudaErrorInvalidValue;
+    case MCGPU_ROSENBROCK1:  return launch_lik<MCGPU_ROSENBROCK1>(d, rngk, phase, p, smem, st);
+    case MCGPU_GAUSSMIX:     return launch_lik<MCGPU_GAUSSMIX>(d, rngk, phase, p, smem, st);
+    case MCGPU_GAUSSIAN:     return d == 2 ? launch_lik_d<MCGPU_GAUSSIAN, 2>(rngk, phase, p, smem, st) : cudaErrorInvalidValue;
+    case MCGPU_DUALGAUSSIAN: return d == 2 ? launch_lik_d<MCGPU_DUALGAUSSIAN, 2>(rngk, phase, p, smem, st) : cudaErrorInvalidValue;
   }
   return cudaErrorInvalidValue;
 }

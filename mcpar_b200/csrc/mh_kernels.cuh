@@ -7,7 +7,7 @@
 // reference's C++ does (src/mcpar.cc, src/rosenbrock.cc), so states and polynomial
 // log-likelihoods are bit-identical to the CPU oracle on shared streams.
 //
-// Kernel 1  mh_steps_kernel<LIK,D,RNG,MAIN>   production path: one thread per chain,
+// Kernel 1  mh_steps_kernel<LIK,D,RNG,PHASE>  production path: one thread per chain,
 //           K steps per launch, state in registers; fuses proposal generation
 //           (genLocal mcpar.cc:302-312 / genRemote :315-451), likelihood
 //           (VLFunc, rosenbrock.cc), accept + update (:65-75,:165-175), running
@@ -139,7 +139,7 @@ __device__ __forceinline__ float ex2_approx(float x)
 // The accept test  u < exp(delta) * cfac  (mcpar.cc:67-69 / :167-169).  Only the
 // decision is needed, so it is settled by rigorous fp32 bounds on exp(delta) and
 // computed exactly (fp64 exp) only when u falls between the bounds (~1e-4 of cases).
-__device__ __forceinline__ bool accept_test(double u, double delta, double cfac)
+__device__ __forceinline__ bool accept_test(double u, double delta, double cfac, const MathTables &T)
 {
 #ifdef MCGPU_EXACT_TU
   return u < exp(delta) * cfac;
@@ -150,50 +150,55 @@ __device__ __forceinline__ bool accept_test(double u, double delta, double cfac)
   const double hi = (delta <= 80.0) ? e * cfac * (1.0 + 1.0e-4) : INFINITY;
   if (u < lo) return true;
   if (u >= hi) return false;
-  return u < exp(delta) * cfac;                       // also the NaN path: comparisons above are false
+  return u < mc_exp(delta, T) * cfac;                 // also the NaN path: comparisons above are false
 #endif
 }
 
-// One candidate iteration `it` of genRemote's rejection loop (mcpar.cc:333-443) for the
-// chain with counter (glo,ghi): pick a pool component, draw x' from it, and decide
-// u < max_s Q_s(x') / sum_s Q_s(x').  Pool arrays in shared memory: sPm = mu,
-// sPh = -1/(2 sigma^2), sPs = sigma.  The sum is bounded in fp32 (SFU exp2, online
-// rescaling); the exact fp64 sum is evaluated only if the bounds do not settle u.
+// exact rejection test pacpt = qimax / qisum (mcpar.cc:355-398) in fp64; out of line: it runs
+// for ~1e-4 of the candidates and must not bloat the hot loop's instruction footprint
 template <int D>
-__device__ __forceinline__ bool remote_candidate(const double2 *sPmh, const double *sPs, int M,
-                                                 uint32_t glo, uint32_t ghi, uint32_t step, uint32_t it,
-                                                 uint32_t k0, uint32_t k1, int &c, double &amax, double (&xc)[D],
-                                                 const MathTables &T)
+__device__ __noinline__ bool remote_exact(const double2 *sPmh, int M, const double (&xc)[D], double u, const MathTables &T)
 {
-  const uint32_t slot = MCGPU_SLOT_REMOTE | (it << 6);
-  const Words w = philox4x32_10(glo, ghi, step, slot, k0, k1);
-  c = (int)__umulhi(w.w0, (uint32_t)M);                // viRngUniform(0, tchains), mcpar.cc:337
-  const double u = u53(w.w2, w.w3);                    // vsRngUniform, mcpar.cc:401
-  double z[D + 1];
+  double qmax = MCGPU_FPEPS, qsum = MCGPU_FPEPS;
+  for (int s = 0; s < M; ++s) {
+    double a = 0.0;
 #pragma unroll
-  for (int q = 0; 2 * q < D; ++q) {
-    const Words wz = philox4x32_10(glo, ghi, step, slot | (uint32_t)(1 + q), k0, k1);
-    normal_pair_t(wz, z[2 * q], z[2 * q + 1], T);
+    for (int i = 0; i < D; ++i) { const double2 mh = sPmh[s * D + i]; const double xm = mh.x - xc[i]; a += xm * xm * mh.y; }
+    const double gv = mc_exp(a, T);
+    qsum += gv; qmax = gv > qmax ? gv : qmax;
   }
-#pragma unroll
-  for (int i = 0; i < D; ++i) xc[i] = sPmh[c * D + i].x + sPs[c * D + i] * z[i];   // DIAGONAL storage, :348-350
+  return u < qmax / qsum;
+}
 
-  // a_s = log Q_s(x') for the pool in chunks of 8: the 8 quadratic forms, their max and
-  // their fp32 exp-sum are independent instruction streams (ILP), chunks are merged by
-  // one rescale each.  fp32 enters only through S (a bound); m stays exact fp64.
+// c_stride_mask[n]: bits 0, n, 2n, ... below 32
+__constant__ unsigned c_stride_mask[33] = {0u,
+  0xffffffffu, 0x55555555u, 0x49249249u, 0x11111111u, 0x42108421u, 0x41041041u, 0x10204081u, 0x01010101u,
+  0x08040201u, 0x40100401u, 0x00400801u, 0x01001001u, 0x04002001u, 0x10004001u, 0x40008001u, 0x00010001u,
+  0x00020001u, 0x00040001u, 0x00080001u, 0x00100001u, 0x00200001u, 0x00400001u, 0x00800001u, 0x01000001u,
+  0x02000001u, 0x04000001u, 0x08000001u, 0x10000001u, 0x20000001u, 0x40000001u, 0x80000001u, 0x00000001u};
+
+// The rejection test of genRemote (mcpar.cc:355-406) for one candidate x' (xc):
+// decide  u < max_s Q_s(x') / sum_s Q_s(x')  over the pool.  Pool arrays in shared memory:
+// sPmh = (mu, -1/(2 sigma^2)) pairs, padded to a multiple of 8 slots whose Q is 0.  The sum is
+// bounded in fp32 (SFU exp2, chunks of 8 for ILP, one rescale per chunk); the max is exact
+// fp64; the exact fp64 sum is evaluated only if the bounds do not settle u.
+template <int D>
+__device__ __forceinline__ bool pool_test(const double2 *sPmh, int M, const double (&xc)[D], double u,
+                                          double &amax, const MathTables &T)
+{
   constexpr int CH = 8;
   constexpr float L2E = 1.4426950408889634f;
-  double m = -INFINITY;                                // running max of a_s
+  const int Mpad = (M + CH - 1) & ~(CH - 1);
+  double m = -INFINITY;                                // running max of a_s = log Q_s(x')
   float S = 0.0f;                                      // sum_s exp(a_s - m), fp32
-  for (int s0 = 0; s0 < M; s0 += CH) {
+  for (int s0 = 0; s0 < Mpad; s0 += CH) {
     double a[CH];
 #pragma unroll
     for (int q = 0; q < CH; ++q) {
-      const int s = s0 + q < M ? s0 + q : M - 1;
       double acc = 0.0;
 #pragma unroll
-      for (int i = 0; i < D; ++i) { const double2 mh = sPmh[s * D + i]; const double xm = mh.x - xc[i]; acc += xm * xm * mh.y; }
-      a[q] = s0 + q < M ? acc : -INFINITY;
+      for (int i = 0; i < D; ++i) { const double2 mh = sPmh[(s0 + q) * D + i]; const double xm = mh.x - xc[i]; acc += xm * xm * mh.y; }
+      a[q] = acc;
     }
     double mc = a[0];
 #pragma unroll
@@ -208,42 +213,47 @@ __device__ __forceinline__ bool remote_candidate(const double2 *sPmh, const doub
     m = gt ? mc : m;
   }
   amax = m;
-  bool decided = false, acc = false;
   if (m > -10.0) {                                     // then FPEPS/qmax < 2.3e-10 (mcpar.cc:357-358 offsets)
     const double eps = 1.0e-4 + 2.0e-5 * (double)M;
     const double Sd = (double)S;
-    const double r_lo = 1.0 / (Sd * (1.0 + eps) + 3.0e-10);
-    const double r_hi = 1.0 / (Sd * (1.0 - eps));
-    if (u < r_lo) { decided = true; acc = true; }
-    else if (u >= r_hi) { decided = true; acc = false; }
+    if (u * (Sd * (1.0 + eps) + 3.0e-10) < 1.0) return true;      // u < r_lo
+    if (u * (Sd * (1.0 - eps)) >= 1.0) return false;              // u >= r_hi
   }
-  if (!decided) {                                      // exact: pacpt = qimax / qisum, :355-398
-    double qmax = MCGPU_FPEPS, qsum = MCGPU_FPEPS;
-    for (int s = 0; s < M; ++s) {
-      double a = 0.0;
-#pragma unroll
-      for (int i = 0; i < D; ++i) { const double2 mh = sPmh[s * D + i]; const double xm = mh.x - xc[i]; a += xm * xm * mh.y; }
-      const double gv = exp(a);
-      qsum += gv; qmax = gv > qmax ? gv : qmax;
-    }
-    acc = u < qmax / qsum;
-  }
-  return acc;
+  return remote_exact<D>(sPmh, M, xc, u, T);            // rare: the fp32 bounds straddle u
 }
 
+#ifndef MCGPU_MINB_LOCAL
+#define MCGPU_MINB_LOCAL 10   // d = 2 local-only kernels: <= 48 registers, 40 warps per SM
+#endif
 #ifndef MCGPU_MINB
 #define MCGPU_MINB 6      // d = 2: cap registers at 80 (6 CTAs of 128 per SM); gpurun_out/tune.log sweep
 #endif
-template <int LIK, int D, int RNGK, bool MAIN>
-__global__ void __launch_bounds__(128, (D <= 2 ? MCGPU_MINB : 1))
+// PHASE selects what a launch may contain:
+//   PH_BURN    burn-in steps (local proposals, no moments, no history)            mcpar.cc:56-97
+//   PH_MIXED   main steps, one local/remote coin per group of <= 32 chains (a warp may hold
+//              both kinds of step)                                                  mcpar.cc:113-210
+//   PH_LOCAL   main steps known to be local for every chain (job-wide coin, or t < SYNCSTEP)
+//   PH_REMOTE  main steps known to be remote for every chain (job-wide coin)
+// With a job-wide coin (coin_group = 0: "one coin per rank per step", the rank being the whole
+// job) the host knows each step's kind in advance -- the coin is a counter-based draw -- and
+// launches lean PH_LOCAL kernels (no remote code, few registers, full occupancy) and dedicated
+// PH_REMOTE kernels instead of the mixed one.
+enum { PH_BURN = 0, PH_MIXED = 1, PH_LOCAL = 2, PH_REMOTE = 3 };
+
+template <int LIK, int D, int RNGK, int PHASE>
+__global__ void __launch_bounds__(128, (D <= 2 ? ((PHASE == PH_BURN || PHASE == PH_LOCAL) ? MCGPU_MINB_LOCAL : MCGPU_MINB) : 1))
 mh_steps_kernel(const StepParams p)
 {
+  constexpr bool MAIN = PHASE != PH_BURN;
+  constexpr bool CAN_REMOTE = RNGK == RNG_PHILOX && (PHASE == PH_MIXED || PHASE == PH_REMOTE);
   extern __shared__ double smem[];
+  __shared__ unsigned char s_rank[4][32];               // per warp: lanes of the chains still in the remote loop
   // smem: math tables | [D*D] factor | [nsteps] 1/pwgt table | pool: mu, -1/(2 sig^2), sigma
   double *sT = smem + MCGPU_MATH_SMEM;
   double *sW = sT + D * D;
   double2 *sPmh = reinterpret_cast<double2*>(sW + ((p.nsteps + 1) & ~1));     // (mu, -1/(2 sig^2)) pairs, 16-byte aligned
-  double *sPs = reinterpret_cast<double*>(sPmh + p.pool_m * D);
+  const int Mpad = (p.pool_m + 7) & ~7;
+  double *sPs = reinterpret_cast<double*>(sPmh + Mpad * D);
   MathTables T;
 #ifndef MCGPU_EXACT_TU
   T.exp_tab = smem; T.log_tab = smem + MCGPU_EXP_TAB; T.trig_tab = T.log_tab + 2 * MCGPU_LOG_TAB;
@@ -265,10 +275,12 @@ mh_steps_kernel(const StepParams p)
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) sT[i] = p.factor[i];
   if (MAIN) {
     for (int k = threadIdx.x; k < p.nsteps; k += blockDim.x) sW[k] = 1.0 / (double)(p.t0 + k + 1);
-    if (RNGK == RNG_PHILOX && p.t0 + p.nsteps > p.sync)
-      for (int i = threadIdx.x; i < p.pool_m * D; i += blockDim.x) {
-        const double s2 = p.pool_cur[i * 2 + 1];
-        sPmh[i] = make_double2(p.pool_cur[i * 2], -0.5 / s2); sPs[i] = sqrt(s2);     // sigma = sqrt(sig^2), mcpar.cc:346
+    if (CAN_REMOTE && p.t0 + p.nsteps > p.sync)
+      for (int i = threadIdx.x; i < Mpad * D; i += blockDim.x) {
+        if (i < p.pool_m * D) {
+          const double s2 = p.pool_cur[i * 2 + 1];
+          sPmh[i] = make_double2(p.pool_cur[i * 2], -0.5 / s2); sPs[i] = sqrt(s2);   // sigma = sqrt(sig^2), mcpar.cc:346
+        } else sPmh[i] = make_double2(1.0e300, -1.0);   // padding: (mu - x)^2 overflows, a = -inf, Q = 0
       }
   }
   __syncthreads();
@@ -282,17 +294,19 @@ mh_steps_kernel(const StepParams p)
     for (int i = 0; i < D; ++i) { mu[i] = p.mu[i * p.ld + jc]; ps[i] = p.ps[i * p.ld + jc]; }
   }
   unsigned int nacc = 0;
+  int tmod = MAIN ? p.t0 % p.thin : 0;                // t % thin and t / thin without per-step divisions
+  long long tkeep = MAIN ? (long long)(p.t0 / p.thin) - p.hist_step0 : 0;
 
   for (int k = 0; k < p.nsteps; ++k) {
     const uint32_t step = p.step0 + (uint32_t)k;
     const int t = p.t0 + k;
     double u_acc;
-    bool remote = false;
+    bool remote = PHASE == PH_REMOTE;
     long long zoff = 0;
     if (RNGK == RNG_PHILOX) {
       const Words wa = philox4x32_10(glo, ghi, step, MCGPU_SLOT_ACCEPT, p.key0, p.key1);
       u_acc = u53(wa.w0, wa.w1);
-      if (MAIN && t >= p.sync) {                       // one coin per group: the leader's spare words
+      if (PHASE == PH_MIXED && t >= p.sync) {          // one coin per group: the leader's spare words
         double coin = u53(wa.w2, wa.w3);
         coin = __shfl_sync(0xffffffffu, coin, leader);
         remote = !(coin <= p.pl);                      // mcpar.cc:152
@@ -316,34 +330,68 @@ mh_steps_kernel(const StepParams p)
     double cfac = 1.0;
     int cpick = 0;                                     // component the accepted remote draw came from
 
-    if constexpr (RNGK == RNG_PHILOX && MAIN) {
-      // ---- genRemote over the pool (mcpar.cc:315-451), warp-cooperative ----------------
-      // The reference's rejection loop tries candidate iterations it = 0,1,2,... until one
-      // is accepted.  Candidates are independent counter-based draws, so the warp evaluates
-      // 32 of them per round, spread over the chains still looping (finished chains' lanes
-      // help the stragglers), and each chain takes its FIRST accepted candidate in
-      // iteration order: the same outcome as the sequential loop, without divergence.
-      unsigned rm = __ballot_sync(0xffffffffu, remote && live);
-      if (rm) {
-        uint32_t it_next = 0;
-        bool pending = remote && live;
-        double amax_acc = 0.0;
-        while (rm) {
-          const int n = __popc(rm);
+    if constexpr (RNGK == RNG_PHILOX) {
+      // ---- proposal generation: genLocal (mcpar.cc:302-312) and genRemote (:315-451) ----
+      // One loop serves both so that the Philox + Box-Muller code exists once (instruction
+      // cache).  Round 0 is the local round: every lane draws its own normals and applies
+      // x' = x + T z.  Remote rounds follow while chains of this warp are still in the
+      // reference's rejection loop: that loop tries candidate iterations it = 0,1,2,... until
+      // one is accepted; candidates are independent counter-based draws, so the warp
+      // evaluates 32 of them per round, spread over the chains still looping (finished
+      // chains' lanes help the stragglers), and each chain takes its FIRST accepted candidate
+      // in iteration order -- the sequential loop's outcome, without lock-step divergence.
+      unsigned rm = CAN_REMOTE ? __ballot_sync(0xffffffffu, remote && live) : 0u;
+      bool local_round = PHASE == PH_REMOTE ? false : (CAN_REMOTE ? __any_sync(0xffffffffu, !remote) : true);
+      bool pending = CAN_REMOTE && remote && live;
+      uint32_t it_next = 0;
+      double amax_acc = 0.0;
+      while (local_round || rm) {
+        uint32_t tlo = glo, thi = ghi, slot = 0;
+        int n = 1, my_r = 0;
+        if (!local_round) {                             // schedule 32 candidates over the unfinished chains
+          n = __popc(rm);
           const int r = lane % n, kk = lane / n;
-          const int tgt = __fns(rm, 0, r + 1);                       // lane owning the r-th unfinished chain
+          my_r = __popc(rm & ((1u << lane) - 1u));      // rank of this lane's chain among the unfinished
+          if (pending) s_rank[threadIdx.x >> 5][my_r] = (unsigned char)lane;
+          __syncwarp();
+          const int tgt = s_rank[threadIdx.x >> 5][r];  // lane owning the r-th unfinished chain
+          __syncwarp();
           const uint32_t it = __shfl_sync(0xffffffffu, it_next, tgt) + (uint32_t)kk;
-          const uint32_t tlo = __shfl_sync(0xffffffffu, glo, tgt), thi = __shfl_sync(0xffffffffu, ghi, tgt);
-          int c; double am; double xc[D];
-          const bool acc = remote_candidate<D>(sPmh, sPs, p.pool_m, tlo, thi, step, it, p.key0, p.key1, c, am, xc, T);
+          tlo = __shfl_sync(0xffffffffu, glo, tgt); thi = __shfl_sync(0xffffffffu, ghi, tgt);
+          slot = MCGPU_SLOT_REMOTE | (it << 6);
+        }
+        double z[D + 1];
+#pragma unroll
+        for (int q = 0; 2 * q < D; ++q) {               // local: slots 0.. ; remote: slots base+1..
+          const Words w = philox4x32_10(tlo, thi, step, slot + (local_round ? 0u : 1u) + (uint32_t)q, p.key0, p.key1);
+          normal_pair_t(w, z[2 * q], z[2 * q + 1], T);
+        }
+        if (local_round) {
+          if (!remote) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              double acc = x[i];
+#pragma unroll
+              for (int q = 0; q <= i; ++q) acc += sT[i * D + q] * z[q];
+              xt[i] = acc;
+            }
+          }
+          local_round = false;
+          continue;
+        }
+        if constexpr (CAN_REMOTE) {
+          const Words w0 = philox4x32_10(tlo, thi, step, slot, p.key0, p.key1);
+          const int c = (int)__umulhi(w0.w0, (uint32_t)p.pool_m);      // viRngUniform(0, tchains), mcpar.cc:337
+          const double u = u53(w0.w2, w0.w3);                          // vsRngUniform, mcpar.cc:401
+          double xc[D], am;
+#pragma unroll
+          for (int i = 0; i < D; ++i) xc[i] = sPmh[c * D + i].x + sPs[c * D + i] * z[i];   // DIAGONAL storage, :348-350
+          const bool acc = pool_test<D>(sPmh, p.pool_m, xc, u, am, T);
           const unsigned accmask = __ballot_sync(0xffffffffu, acc);
-          unsigned pat = 0;                                           // lanes r, r+n, r+2n, ... serve chain rank r
-          for (int l = 0; l < 32; l += n) pat |= 1u << l;
           int src = lane;
           bool fin = false;
           if (pending) {
-            const int my_r = __popc(rm & ((1u << lane) - 1u));
-            const unsigned cm = pat << my_r;
+            const unsigned cm = c_stride_mask[n] << my_r;             // lanes my_r, my_r+n, ... served this chain
             const unsigned hit = accmask & cm;
             if (hit) { src = __ffs(hit) - 1; fin = true; }           // lowest lane = lowest iteration index
             else it_next += (uint32_t)__popc(cm);
@@ -356,6 +404,8 @@ mh_steps_kernel(const StepParams p)
           if (it_next >= (1u << 24) - 64u) pending = false;          // slot space exhausted (never in practice)
           rm = __ballot_sync(0xffffffffu, pending);
         }
+      }
+      if constexpr (CAN_REMOTE) {
         if (remote) {
           // cfac = max_i Q_i(x_old) / max_i Q_i(x'), mcpar.cc:412-439
           double aold = -INFINITY;
@@ -370,20 +420,11 @@ mh_steps_kernel(const StepParams p)
           cfac = MC_EXP(aold) / qmax;
         }
       }
-    }
-    if (!remote) {
-      // genLocal: x' = x + T z, T row-major lower (mcpar.cc:302-312)
+    } else {
+      // replayed streams: genLocal with the supplied normals
       double z[D + 1];
-      if (RNGK == RNG_PHILOX) {
 #pragma unroll
-        for (int q = 0; 2 * q < D; ++q) {
-          const Words w = philox4x32_10(glo, ghi, step, (uint32_t)q, p.key0, p.key1);
-          normal_pair_t(w, z[2 * q], z[2 * q + 1], T);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < D; ++i) z[i] = (zoff + D <= p.nz) ? p.Z[zoff + i] : 0.0;
-      }
+      for (int i = 0; i < D; ++i) z[i] = (zoff + D <= p.nz) ? p.Z[zoff + i] : 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         double acc = x[i];
@@ -394,7 +435,7 @@ mh_steps_kernel(const StepParams p)
     }
 
     const double lyt = Lik<LIK, D>::eval(xt, p, T);
-    const bool a = accept_test(u_acc, lyt - ly, MAIN ? cfac : 1.0);   // mcpar.cc:67-69 / :167-169
+    const bool a = accept_test(u_acc, lyt - ly, MAIN ? cfac : 1.0, T);   // mcpar.cc:67-69 / :167-169
     if (a) {
       ly = lyt;
 #pragma unroll
@@ -403,14 +444,15 @@ mh_steps_kernel(const StepParams p)
     nacc += a ? 1u : 0u;
 
     if (MAIN) {
-      if (p.hist && live && (t % p.thin) == 0) {       // MCout::add, mcout.cc:129-145
-        double *row = p.hist + (((long long)(t / p.thin) - p.hist_step0) * p.C + j) * (D + 1);
+      if (p.hist && live && tmod == 0) {               // MCout::add, mcout.cc:129-145
+        double *row = p.hist + (tkeep * p.C + j) * (D + 1);
 #pragma unroll
         for (int i = 0; i < D; ++i) row[i] = x[i];
         row[D] = ly;
       }
+      if (++tmod == p.thin) { tmod = 0; ++tkeep; }
       const double pwgt = (double)(t + 1), winv = sW[k];
-      const bool adopt = remote && a;                  // mcpar.cc:190-197
+      const bool adopt = CAN_REMOTE && remote && a;    // mcpar.cc:190-197
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         if (adopt) {                                   // sigma -> sigma^2 round trip of :346,:447-448

@@ -2,10 +2,11 @@
 #pragma once
 #include "mcgpu_device.cuh"
 namespace mcgpu {
+enum { PH_BURN = 0, PH_MIXED = 1, PH_LOCAL = 2, PH_REMOTE = 3 };   // kernel phases, see mh_kernels.cuh
 namespace fast {
 bool steps_supported(int lik, int d);
 size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem);
-cudaError_t launch_steps(int lik, int d, int rngk, bool main_phase, const StepParams &p, cudaStream_t st);
+cudaError_t launch_steps(int lik, int d, int rngk, int phase, const StepParams &p, cudaStream_t st);
 cudaError_t launch_init_loglik(int lik, int d, const StepParams &p, cudaStream_t st);
 cudaError_t launch_tune(unsigned long long *counts, unsigned long long *cum, double *factor, int dd,
                         double armin, double armax, double dfac, double ifac, cudaStream_t st);
@@ -13,7 +14,7 @@ cudaError_t launch_tune(unsigned long long *counts, unsigned long long *cum, dou
 namespace exact {
 bool steps_supported(int lik, int d);
 size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem);
-cudaError_t launch_steps(int lik, int d, int rngk, bool main_phase, const StepParams &p, cudaStream_t st);
+cudaError_t launch_steps(int lik, int d, int rngk, int phase, const StepParams &p, cudaStream_t st);
 cudaError_t launch_init_loglik(int lik, int d, const StepParams &p, cudaStream_t st);
 cudaError_t launch_tune(unsigned long long *counts, unsigned long long *cum, double *factor, int dd,
                         double armin, double armax, double dfac, double ifac, cudaStream_t st);

@@ -37,8 +37,11 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 double orc_u53(uint32_t hi, uint32_t lo)
 {
+  /* top 52 bits -> mantissa of a double in [1,2), minus 1: uniform on [0,1) with 52 bits */
   uint64_t b = ((uint64_t)hi << 32) | lo;
-  return (double)(b >> 11) * (1.0 / 9007199254740992.0);
+  uint64_t m = 0x3FF0000000000000ull | (b >> 12);
+  double x; memcpy(&x, &m, 8);
+  return x - 1.0;
 }
 
 /* ------------------------------------------------------------------ */
@@ -500,7 +503,7 @@ int orc_run_counter(const orc_config *cfg, const double *pinit, const double *in
                     unsigned char *tr_accept, long long *remote_iters)
 {
   const int N = cfg->nchain, d = cfg->nparam;
-  const int G = cfg->coin_group > 0 ? cfg->coin_group : 32;
+  const int G = cfg->coin_group > 0 ? cfg->coin_group : N;   /* 0: one coin per step for the whole job */
   const int M = (cfg->pool_m > 0 && cfg->pool_m < N) ? cfg->pool_m : N;
   const int stride = N / M;
   const int thin = cfg->thin > 0 ? cfg->thin : 1;

@@ -36,7 +36,7 @@ typedef struct orc_config {
   int trace_musig;
   /* counter (Philox) mode only */
   uint64_t seed;
-  int coin_group;        /* chains sharing one local/remote coin (power of two <= 32) */
+  int coin_group;        /* chains sharing one local/remote coin (power of two <= 32); 0 = whole job */
   int pool_m;            /* remote-mixture pool size, 0 => all chains    */
   int thin;              /* keep every thin-th main step in rows         */
 } orc_config;

@@ -202,20 +202,23 @@ def test_production_kernel_replay_local(lik, d, C, par, incov):
 
 
 # ---------------------------------------------------------------- normal mode vs counter oracle
-@pytest.mark.parametrize("lik,d,N,par,pool_m,pl", [
-    ("rosenbrock1", 2, 256, None, 0, 0.9),
-    ("rosenbrock1", 2, 512, None, 16, 0.7),
-    ("dualgaussian", 2, 256, [5.0], 8, 0.8),
-    ("rosenbrock1", 4, 128, None, 8, 0.8),
+@pytest.mark.parametrize("lik,d,N,par,pool_m,pl,cg", [
+    ("rosenbrock1", 2, 256, None, 0, 0.9, 32),
+    ("rosenbrock1", 2, 512, None, 16, 0.7, 32),
+    ("dualgaussian", 2, 256, [5.0], 8, 0.8, 32),
+    ("rosenbrock1", 4, 128, None, 8, 0.8, 32),
+    ("dualgaussian", 2, 256, [5.0], 8, 0.8, 4),       # rank-sized coin groups (mixed warps)
+    ("dualgaussian", 2, 512, [5.0], 16, 0.7, 0),      # job-wide coin: host-planned local / remote launches
+    ("rosenbrock1", 2, 200, None, 10, 0.6, 0),        # ragged: chains not a multiple of 32, pool not of 8
 ])
-def test_normal_mode_matches_counter_oracle(lik, d, N, par, pool_m, pl):
+def test_normal_mode_matches_counter_oracle(lik, d, N, par, pool_m, pl, cg):
     """Same Philox draws on both sides: identical accept sequences; values agree to
     rounding (host libm vs CUDA libm differ in the last ulp of log/sin/cos/exp)."""
     eng = _engine()
     nburn, nsamp = 120, 60
     pin = tiled_pinit(N, d)
-    o = mh.run_counter(lik, d, N, nsamp, nburn, pin, par=par, pool_m=pool_m, pl=pl, trace=True)
-    e = eng.Engine(d, N, mode="normal", pool_m=pool_m, pl=pl, history_steps=nsamp)
+    o = mh.run_counter(lik, d, N, nsamp, nburn, pin, par=par, pool_m=pool_m, pl=pl, coin_group=cg, trace=True)
+    e = eng.Engine(d, N, mode="normal", pool_m=pool_m, pl=pl, coin_group=cg, history_steps=nsamp)
     e.run(nsamp, nburn, pin, lik, par)
     st = e.state()
     h = e.history()
@@ -236,16 +239,25 @@ def test_two_sharded_engines_equal_one_engine():
     protocol mcpar_b200/sharded.py runs over NCCL) reproduce the single-engine run bit for
     bit: Philox is keyed on the global chain id, tuning is global, the pool is all-gathered."""
     import torch
+    _two_vs_one(32)
+
+
+def test_two_sharded_engines_equal_one_engine_jobwide_coin():
+    _two_vs_one(0)
+
+
+def _two_vs_one(cg):
+    import torch
     eng = _engine()
     d, N, nburn, nsamp, M, pl = 2, 512, 130, 60, 16, 0.7
     pin = tiled_pinit(N, d)
-    one = eng.Engine(d, N, mode="normal", pool_m=M, pl=pl, history_steps=nsamp)
+    one = eng.Engine(d, N, mode="normal", pool_m=M, pl=pl, coin_group=cg, history_steps=nsamp)
     one.run(nsamp, nburn, pin, "rosenbrock1")
     ref_state, ref_hist, ref_factor = one.state(), one.history(), one.factor()
     one.close()
 
     half = N // 2
-    es = [eng.Engine(d, half, mode="normal", nchain_total=N, chain0=r * half, pool_m=M, pl=pl,
+    es = [eng.Engine(d, half, mode="normal", nchain_total=N, chain0=r * half, pool_m=M, pl=pl, coin_group=cg,
                      history_steps=nsamp) for r in range(2)]
     for r, e in enumerate(es):
         e.set_likelihood("rosenbrock1"); e.set_covariance(None); e.set_state(pin[r * half:(r + 1) * half])
