@@ -46,6 +46,12 @@ struct mcgpu_engine {
   int *overrun = nullptr;
   double *Zd = nullptr, *Ud = nullptr; int *Id = nullptr; long long nz = 0, nu = 0, ni = 0;
 
+  // wide kernels (d >= 8, job-wide coin): AoS state, column-major factor, prepared pool, transposed GaussMix
+  bool wide = false;
+  double *factor_cm = nullptr; int *diag_d = nullptr;
+  double *pprep = nullptr; int mpad = 0;
+  double *gm_t = nullptr; int kpad = 0;
+
   // VERIFY extras
   int Cr = 0, Rl = 0, R = 0, rank0 = 0;
   double *ptrial = nullptr, *sig = nullptr, *mutrial = nullptr, *sigtrial = nullptr, *musig = nullptr;
@@ -149,6 +155,18 @@ void fill_step_params(mcgpu_engine *e, StepParams &p)
 cudaError_t launch_steps_any(mcgpu_engine *e, int phase, const StepParams &p)
 {
   ++e->launches;
+  if (e->wide) {
+    WideParams w; memset(&w, 0, sizeof w);
+    w.x = p.x; w.ly = p.ly; w.mu = p.mu; w.ps = p.ps; w.C = p.C; w.chain0 = p.chain0;
+    w.factor_cm = e->factor_cm; w.factor_rm = e->factor; w.diagonal = e->diag_d; w.counts = p.counts;
+    w.key0 = p.key0; w.key1 = p.key1; w.step0 = p.step0; w.nsteps = p.nsteps; w.t0 = p.t0;
+    w.pm = e->pprep; w.ph = e->pprep + (size_t)e->d * e->mpad; w.psd = e->pprep + (size_t)2 * e->d * e->mpad;
+    w.pool_m = e->M; w.mpad = e->mpad; w.pool_next = p.pool_next; w.pool_stride = p.pool_stride;
+    w.hist = p.hist; w.thin = p.thin; w.hist_step0 = p.hist_step0;
+    w.gm_mu = e->gm_t; w.gm_is2 = e->gm_t ? e->gm_t + (size_t)e->d * e->kpad : nullptr;
+    w.gm_lw = e->gm_t ? e->gm_t + (size_t)2 * e->d * e->kpad : nullptr; w.kpad = e->kpad;
+    return fast::launch_wide(e->lik, e->d, phase, w, e->stream);
+  }
   if (e->replay_local) return exact::launch_steps(e->lik, e->d, 1, phase == PH_BURN ? PH_BURN : PH_LOCAL, p, e->stream);
   return fast::launch_steps(e->lik, e->d, 0, phase, p, e->stream);
 }
@@ -416,7 +434,6 @@ int mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out)
     if (!never_remote && cfg->pool_m <= 0 && e->N > (1 << 20)) return bail(MCGPU_EINVAL, "pool_m = 0 (all chains) is limited to 2^20 chains; choose a pool size");
     e->stride = e->N / e->M;
     e->pool_in_smem = true;
-    if ((size_t)e->M * d * 24 + (size_t)(d * d + cfg->sync) * 8 > 200 * 1024) return bail(MCGPU_EINVAL, "remote-mixture pool does not fit in shared memory: choose pool_m with pool_m*nparam <= 8192");
     TRY(dalloc(e, &e->x, (size_t)d * e->ld)); TRY(dalloc(e, &e->ly, (size_t)e->ld));
     TRY(dalloc(e, &e->mu, (size_t)d * e->ld)); TRY(dalloc(e, &e->ps, (size_t)d * e->ld));
     TRY(dalloc(e, &e->factor, (size_t)d * d)); TRY(dalloc(e, &e->counts, 6));
@@ -467,7 +484,7 @@ int mcgpu_destroy(mcgpu_engine *e)
   void *ptrs[] = {e->x, e->ly, e->mu, e->ps, e->factor, e->counts, e->pool[0], e->pool[1], e->hist, e->overrun,
                   e->Zd, e->Ud, e->Id, e->ptrial, e->sig, e->mutrial, e->sigtrial, e->musig, e->snap[0], e->snap[1],
                   e->soff, e->cursors, e->irate_d, e->rstats, e->tr_accept, e->tr_remote, e->tr_trial_ly,
-                  e->tr_trial_p, e->tr_cfac, e->tr_iters, e->lik_dev};
+                  e->tr_trial_p, e->tr_cfac, e->tr_iters, e->lik_dev, e->factor_cm, e->diag_d, e->pprep, e->gm_t};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) { if (e->pin[i]) cudaFreeHost(e->pin[i]); if (e->pin_ev[i]) cudaEventDestroy(e->pin_ev[i]); }
   if (e->side) cudaStreamSynchronize(e->side);
@@ -497,7 +514,12 @@ int mcgpu_set_likelihood(mcgpu_engine *e, int lik, const double *par, int npar)
   if (rc) { e->err = err; return rc; }
   if (!e->verify) {
     if (lik == MCGPU_ROSENBROCK2) return fail(e, MCGPU_EINVAL, "Rosenbrock2 couples neighbouring chains of a batch (rosenbrock.cc:32-33); available in VERIFY mode and mcgpu_loglik only");
-    if (!fast::steps_supported(lik, e->d)) return fail(e, MCGPU_EINVAL, "no step kernel instantiated for this (likelihood, nparam)");
+    const bool can_wide = e->cfg.mode == MCGPU_MODE_NORMAL && e->cfg.coin_group == 0 && fast::wide_supported(lik, e->d);
+    if (!can_wide && !fast::steps_supported(lik, e->d)) return fail(e, MCGPU_EINVAL, "no step kernel instantiated for this (likelihood, nparam)");
+    if (e->have_state && can_wide != e->wide) return fail(e, MCGPU_ESTATE, "likelihood change would change the state layout: create a new engine");
+    e->wide = can_wide;
+    if (!e->wide && e->cfg.pl < 1.0 && (size_t)e->M * e->d * 24 + (size_t)(e->d * e->d + e->cfg.sync) * 8 > 200 * 1024)
+      return fail(e, MCGPU_EINVAL, "remote-mixture pool does not fit in shared memory: choose pool_m with pool_m*nparam <= 8192");
   }
   if (e->lik_dev) { cudaFree(e->lik_dev); e->lik_dev = nullptr; }
   if (!dev.empty()) {
@@ -506,6 +528,27 @@ int mcgpu_set_likelihood(mcgpu_engine *e, int lik, const double *par, int npar)
     CK(cudaStreamSynchronize(e->stream));
   }
   e->lik = lik; e->lik_k = K;
+  if (e->wide) {
+    const int d = e->d, L = d / 2;
+    if (!e->factor_cm) { CK(cudaMalloc((void**)&e->factor_cm, (size_t)d * d * 8)); CK(cudaMalloc((void**)&e->diag_d, sizeof(int))); }
+    e->mpad = (e->M + L - 1) / L * L;
+    if (!e->pprep) CK(cudaMalloc((void**)&e->pprep, (size_t)3 * d * e->mpad * 8));
+    if (e->gm_t) { cudaFree(e->gm_t); e->gm_t = nullptr; }
+    if (lik == MCGPU_GAUSSMIX) {                        // [d][Kpad] mu, [d][Kpad] 1/s2, [Kpad] log w; padding has weight 0
+      e->kpad = (K + L - 1) / L * L;
+      std::vector<double> t((size_t)2 * d * e->kpad + e->kpad, 0.0);
+      for (int k = 0; k < e->kpad; ++k) {
+        for (int i = 0; i < d; ++i) {
+          t[(size_t)i * e->kpad + k] = k < K ? dev[(size_t)k * d + i] : 0.0;
+          t[(size_t)d * e->kpad + (size_t)i * e->kpad + k] = k < K ? dev[(size_t)K * d + (size_t)k * d + i] : 0.0;
+        }
+        t[(size_t)2 * d * e->kpad + k] = k < K ? dev[(size_t)2 * K * d + k] : -INFINITY;
+      }
+      CK(cudaMalloc((void**)&e->gm_t, t.size() * 8));
+      CK(cudaMemcpyAsync(e->gm_t, t.data(), t.size() * 8, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+    }
+  }
   return MCGPU_OK;
 }
 
@@ -540,6 +583,11 @@ int mcgpu_set_state(mcgpu_engine *e, const double *pinit)
       ++e->launches;
       CK(exact::launch_loglik_aos(L, e->x + (size_t)r * e->Cr * d, e->ly + (size_t)r * e->Cr, e->Cr, e->stream));
     }
+  } else if (e->wide) {
+    CK(cudaMemcpyAsync(e->x, pinit, (size_t)e->C * d * 8, cudaMemcpyHostToDevice, e->stream));
+    LikSpec L; L.lik = e->lik; L.d = d; L.k = e->lik_k; memcpy(L.lp, e->lp, sizeof L.lp); L.dev = e->lik_dev;
+    ++e->launches;
+    CK(exact::launch_loglik_aos(L, e->x, e->ly, (int)e->C, e->stream));   // L(nchain, pvals, lylast), mcpar.cc:53
   } else {
     double *tmp = nullptr;
     CK(cudaMallocAsync((void**)&tmp, (size_t)e->C * d * 8, e->stream));
@@ -572,6 +620,7 @@ static int ready_to_step(mcgpu_engine *e)
 {
   if (!e->have_state) return fail(e, MCGPU_ESTATE, "set_state first");
   if (!e->have_factor) { int rc = mcgpu_set_covariance(e, nullptr); if (rc) return rc; }
+  if (e->wide) { ++e->launches; CK(fast::launch_factor_prep(e->factor, e->factor_cm, e->d, e->diag_d, e->stream)); }
   if (e->verify || e->replay_local) { int rc = upload_streams(e); if (rc) return rc; }
   return 0;
 }
@@ -600,6 +649,7 @@ int mcgpu_tune(mcgpu_engine *e)
   ++e->launches;
   CK(fast::launch_tune(e->counts, e->counts + 2, e->factor, e->d * e->d, e->cfg.armin, e->cfg.armax, e->cfg.dfac, e->cfg.ifac, e->stream));
   e->irate += 50; e->tune_pending = false;
+  if (e->wide) { ++e->launches; CK(fast::launch_factor_prep(e->factor, e->factor_cm, e->d, e->diag_d, e->stream)); }
   return MCGPU_OK;
 }
 
@@ -696,6 +746,11 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
         p.pool_next = e->pool[e->pool_cur ^ 1];
         CK(launch_steps_any(e, PH_MIXED, p));
       } else {                                               // job-wide coin: runs of local / remote steps
+        if (e->wide && e->t_main >= sync) {                  // (mu, sig^2) pool -> (mu, -1/2sig^2, sig), slot-fastest
+          ++e->launches;
+          CK(fast::launch_pool_prep(e->pool[e->pool_cur], e->M, e->mpad, e->d, e->pprep, e->pprep + (size_t)e->d * e->mpad,
+                                    e->pprep + (size_t)2 * e->d * e->mpad, e->stream));
+        }
         int k = 0;
         while (k < n) {
           const long long t = e->t_main + k;
@@ -812,6 +867,16 @@ int mcgpu_get_state(mcgpu_engine *e, double *pvals, double *lylast, double *mu, 
     if (mu) CK(cudaMemcpyAsync(mu, e->mu, nb, cudaMemcpyDeviceToHost, e->stream));
     if (sig) CK(cudaMemcpyAsync(sig, e->sig, nb, cudaMemcpyDeviceToHost, e->stream));
     if (psum2) CK(cudaMemcpyAsync(psum2, e->ps, nb, cudaMemcpyDeviceToHost, e->stream));
+  } else if (e->wide) {
+    if (pvals) CK(cudaMemcpyAsync(pvals, e->x, nb, cudaMemcpyDeviceToHost, e->stream));
+    if (mu) CK(cudaMemcpyAsync(mu, e->mu, nb, cudaMemcpyDeviceToHost, e->stream));
+    if (psum2) CK(cudaMemcpyAsync(psum2, e->ps, nb, cudaMemcpyDeviceToHost, e->stream));
+    if (sig) {
+      CK(cudaMemcpyAsync(sig, e->ps, nb, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      const double winv = e->t_main > 0 ? 1.0 / (double)e->t_main : 0.0;      // sig = psum2 * winv (mcpar.cc:202)
+      for (size_t i = 0; i < (size_t)e->C * d; ++i) sig[i] *= winv;
+    }
   } else {
     double *tmp = nullptr;
     CK(cudaMallocAsync((void**)&tmp, nb, e->stream));

@@ -81,6 +81,25 @@ struct StepParams {
   double lp[8]; const double *lik_dev; int lik_k;
 };
 
+// One launch worth of arguments for the wide (d >= 8, D/2 lanes per chain) kernels.
+struct WideParams {
+  // chain state, chain-major (AoS): x[chain*D + i], ly[chain], mu, ps like x
+  double *x, *ly, *mu, *ps;
+  long long C, chain0;
+  const double *factor_cm;        // [D*D] COLUMN-major lower factor (factor_cm[q*D + i] = T[i][q])
+  const double *factor_rm;        // [D*D] row-major copy (the tuned matrix lives here; diagonal read)
+  const int *diagonal;            // device flag: factor has no off-diagonal entries
+  unsigned long long *counts;
+  uint32_t key0, key1, step0;
+  int nsteps, t0;
+  // remote pool, prepared: pm / ph / psd [D][Mpad] (mu, -1/(2 sig^2), sigma), slot fastest
+  const double *pm, *ph, *psd; int pool_m, mpad;
+  double *pool_next; long long pool_stride;      // publication target [M][D][2]
+  double *hist; int thin; long long hist_step0;
+  // likelihood: GaussMix parameters [D][Kpad] mu, [D][Kpad] 1/s2, [Kpad] log w (component fastest)
+  const double *gm_mu, *gm_is2, *gm_lw; int kpad;
+};
+
 // runtime-dispatched likelihood description (verification mode, batched evaluation)
 struct LikSpec { int lik, d, k; double lp[8]; const double *dev; };
 

@@ -2,6 +2,60 @@
 #define MCGPU_NS fast
 #include <stdlib.h>
 #include "mh_kernels.cuh"
+#include "mh_wide.cuh"
 namespace mcgpu { namespace fast {
 #include "mh_dispatch.inl"
+
+// ---- wide (d >= 8, D/2 lanes per chain) kernels ------------------------------------------
+bool wide_supported(int lik, int d)
+{
+  return (lik == MCGPU_ROSENBROCK1 || lik == MCGPU_GAUSSMIX) && (d == 8 || d == 16 || d == 32 || d == 64);
+}
+
+template <int LIK, int D>
+static cudaError_t launch_wide_d(int phase, const WideParams &p, cudaStream_t st)
+{
+  constexpr int L = D / 2;
+  const int block = 128, cpb = block / L;
+  const unsigned grid = (unsigned)((p.C + cpb - 1) / cpb);
+  const size_t smem = sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)cpb * 2 * D);
+  switch (phase) {
+    case PH_BURN:   mh_wide_kernel<LIK, D, PH_BURN><<<grid, block, smem, st>>>(p); break;
+    case PH_LOCAL:  mh_wide_kernel<LIK, D, PH_LOCAL><<<grid, block, smem, st>>>(p); break;
+    case PH_REMOTE: mh_wide_kernel<LIK, D, PH_REMOTE><<<grid, block, smem, st>>>(p); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+template <int LIK>
+static cudaError_t launch_wide_lik(int d, int phase, const WideParams &p, cudaStream_t st)
+{
+  switch (d) {
+    case 8:  return launch_wide_d<LIK, 8>(phase, p, st);
+    case 16: return launch_wide_d<LIK, 16>(phase, p, st);
+    case 32: return launch_wide_d<LIK, 32>(phase, p, st);
+    case 64: return launch_wide_d<LIK, 64>(phase, p, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_wide(int lik, int d, int phase, const WideParams &p, cudaStream_t st)
+{
+  if (lik == MCGPU_ROSENBROCK1) return launch_wide_lik<MCGPU_ROSENBROCK1>(d, phase, p, st);
+  if (lik == MCGPU_GAUSSMIX) return launch_wide_lik<MCGPU_GAUSSMIX>(d, phase, p, st);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double *pm, double *ph, double *psd, cudaStream_t st)
+{
+  pool_prep_kernel<<<(D * mpad + 127) / 128, 128, 0, st>>>(pool, M, mpad, D, pm, ph, psd);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_factor_prep(const double *rm, double *cm, int D, int *diag, cudaStream_t st)
+{
+  factor_prep_kernel<<<1, 256, 0, st>>>(rm, cm, D, diag);
+  return cudaGetLastError();
+}
 }}

@@ -127,6 +127,30 @@ template <int D> struct Lik<MCGPU_GAUSSMIX, D> {
 // Kernel 1: production path
 // ----------------------------------------------------------------------------
 
+// Philox block -> normal pair.  Inlined at d <= 4 (two or fewer pairs per step); at larger d
+// the out-of-line copy keeps the d/2 draws of a step from being scheduled all at once, which
+// would hold every Philox state live and push the kernel past 255 registers.
+__device__ __forceinline__ void draw_pair_inl(uint32_t glo, uint32_t ghi, uint32_t step, uint32_t slot, uint32_t k0, uint32_t k1,
+                                              double &za, double &zb, const MathTables &T)
+{
+  const Words w = philox4x32_10(glo, ghi, step, slot, k0, k1);
+  normal_pair_t(w, za, zb, T);
+}
+__device__ __noinline__ void draw_pair_call(uint32_t glo, uint32_t ghi, uint32_t step, uint32_t slot, uint32_t k0, uint32_t k1,
+                                            double &za, double &zb, const MathTables &T)
+{
+  draw_pair_inl(glo, ghi, step, slot, k0, k1, za, zb, T);
+}
+
+// proposal factor entry from shared memory.  At d > 4 the read is volatile: the d(d+1)/2
+// entries are loop-invariant and would otherwise be hoisted into registers for the whole step loop.
+template <int D>
+__device__ __forceinline__ double factor_at(const double *sT, int idx)
+{
+  if (D <= 4) return sT[idx];
+  return *reinterpret_cast<const volatile double *>(sT + idx);
+}
+
 // exp2 on the SFU (fp32): used only to BOUND quantities whose exact value is not
 // needed -- decisions fall back to fp64 whenever a bound does not settle them.
 __device__ __forceinline__ float ex2_approx(float x)
@@ -360,21 +384,34 @@ mh_steps_kernel(const StepParams p)
           tlo = __shfl_sync(0xffffffffu, glo, tgt); thi = __shfl_sync(0xffffffffu, ghi, tgt);
           slot = MCGPU_SLOT_REMOTE | (it << 6);
         }
-        double z[D + 1];
+        // normals are consumed as they are produced (no z[D] array: registers at d = 16):
+        // local  x'_i = x_i + sum_{q<=i} T[i][q] z_q, accumulated column by column, which adds
+        //        the terms of every row in the same q = 0,1,.. order as the row-wise loop;
+        // remote x'_i = mu_c,i + sigma_c,i z_i needs the component first -> z kept in xz[]
+        double xz[D];
+        if (local_round) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) xz[i] = x[i];
+        }
 #pragma unroll
         for (int q = 0; 2 * q < D; ++q) {               // local: slots 0.. ; remote: slots base+1..
-          const Words w = philox4x32_10(tlo, thi, step, slot + (local_round ? 0u : 1u) + (uint32_t)q, p.key0, p.key1);
-          normal_pair_t(w, z[2 * q], z[2 * q + 1], T);
+          double za, zb;
+          if (D <= 4) draw_pair_inl(tlo, thi, step, slot + (local_round ? 0u : 1u) + (uint32_t)q, p.key0, p.key1, za, zb, T);
+          else draw_pair_call(tlo, thi, step, slot + (local_round ? 0u : 1u) + (uint32_t)q, p.key0, p.key1, za, zb, T);
+          if (local_round) {
+#pragma unroll
+            for (int i = 2 * q; i < D; ++i) xz[i] += factor_at<D>(sT, i * D + 2 * q) * za;
+#pragma unroll
+            for (int i = 2 * q + 1; i < D; ++i) xz[i] += factor_at<D>(sT, i * D + 2 * q + 1) * zb;
+          } else {
+            xz[2 * q] = za;
+            if (2 * q + 1 < D) xz[2 * q + 1] = zb;
+          }
         }
         if (local_round) {
           if (!remote) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-              double acc = x[i];
-#pragma unroll
-              for (int q = 0; q <= i; ++q) acc += sT[i * D + q] * z[q];
-              xt[i] = acc;
-            }
+            for (int i = 0; i < D; ++i) xt[i] = xz[i];
           }
           local_round = false;
           continue;
@@ -385,7 +422,7 @@ mh_steps_kernel(const StepParams p)
           const double u = u53(w0.w2, w0.w3);                          // vsRngUniform, mcpar.cc:401
           double xc[D], am;
 #pragma unroll
-          for (int i = 0; i < D; ++i) xc[i] = sPmh[c * D + i].x + sPs[c * D + i] * z[i];   // DIAGONAL storage, :348-350
+          for (int i = 0; i < D; ++i) xc[i] = sPmh[c * D + i].x + sPs[c * D + i] * xz[i];   // DIAGONAL storage, :348-350
           const bool acc = pool_test<D>(sPmh, p.pool_m, xc, u, am, T);
           const unsigned accmask = __ballot_sync(0xffffffffu, acc);
           int src = lane;

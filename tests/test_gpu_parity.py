@@ -210,6 +210,10 @@ def test_production_kernel_replay_local(lik, d, C, par, incov):
     ("dualgaussian", 2, 256, [5.0], 8, 0.8, 4),       # rank-sized coin groups (mixed warps)
     ("dualgaussian", 2, 512, [5.0], 16, 0.7, 0),      # job-wide coin: host-planned local / remote launches
     ("rosenbrock1", 2, 200, None, 10, 0.6, 0),        # ragged: chains not a multiple of 32, pool not of 8
+    ("rosenbrock1", 16, 72, "rosen16", 8, 0.7, 0),    # wide kernel: 8 lanes per chain, full lower factor
+    ("rosenbrock1", 8, 40, None, 5, 0.7, 0),          # wide kernel: 4 lanes per chain, diagonal factor
+    ("gaussmix", 64, 24, "gmix64", 6, 0.7, 0),        # wide kernel: one chain per warp, K = 64 mixture
+    ("gaussmix", 16, 48, "gmix16", 8, 0.8, 0),
 ])
 def test_normal_mode_matches_counter_oracle(lik, d, N, par, pool_m, pl, cg):
     """Same Philox draws on both sides: identical accept sequences; values agree to
@@ -217,9 +221,19 @@ def test_normal_mode_matches_counter_oracle(lik, d, N, par, pool_m, pl, cg):
     eng = _engine()
     nburn, nsamp = 120, 60
     pin = tiled_pinit(N, d)
-    o = mh.run_counter(lik, d, N, nsamp, nburn, pin, par=par, pool_m=pool_m, pl=pl, coin_group=cg, trace=True)
+    incov = None
+    if par == "rosen16":
+        par, incov = None, np.kron(np.eye(8), (2.38 ** 2 / 16) * np.array([[0.5, 1.0], [1.0, 2.505]]))
+    elif isinstance(par, str):                       # K-component mixture in d dimensions, chains start on the means
+        K = {"gmix64": 64, "gmix16": 5}[par]
+        rng = np.random.default_rng(8)
+        gmu = rng.uniform(-5, 5, (K, d)); gs2 = rng.uniform(0.5, 2.0, (K, d))
+        par = mh.gaussmix_params(K, d, gmu, gs2, np.ones(K))
+        pin = gmu[np.arange(N) % K].copy()
+        incov = np.eye(d) * (2.38 ** 2 / d)
+    o = mh.run_counter(lik, d, N, nsamp, nburn, pin, incov=incov, par=par, pool_m=pool_m, pl=pl, coin_group=cg, trace=True)
     e = eng.Engine(d, N, mode="normal", pool_m=pool_m, pl=pl, coin_group=cg, history_steps=nsamp)
-    e.run(nsamp, nburn, pin, lik, par)
+    e.run(nsamp, nburn, pin, lik, par, incov)
     st = e.state()
     h = e.history()
     # accept pattern of the main phase from the history: a row changed iff accepted
