@@ -35,11 +35,26 @@ WORKLOADS = {
     "dgauss":  dict(lik="dualgaussian", par=[5.0], d=2, F_hw=280.0, F_alg=46.0, name="mcpar-dgauss"),
     "rosen2d": dict(lik="rosenbrock1", par=None, d=2, F_hw=167.0, F_alg=38.0, name="mcpar-rosen1 shape, 2-D Rosenbrock"),
     "rosen16": dict(lik="rosenbrock1", par=None, d=16, F_hw=1350.0, F_alg=516.0, name="mcpar-rosen2 (d=16)"),
+    # GaussMix d=64, K=64, exchange every sweep (SYNCSTEP 1), diagonal incov
+    "gmix64":  dict(lik="gaussmix", par="gmix64", d=64, F_hw=22600.0, F_alg=17500.0, name="sum-of-Gaussians mixture d=64 K=64",
+                    sync=1, thin=100),
 }
+
+
+def gmix64_params(seed=SEED):
+    """mu_ki = 10 (u - 0.5), sig2_ki = 0.5 + 1.5 u', w_k = 1 (numpy Philox stream of the seed)."""
+    import numpy as np
+    rng = np.random.Generator(np.random.Philox(seed))
+    K, d = 64, 64
+    mu = 10.0 * (rng.random((K, d)) - 0.5)
+    s2 = 0.5 + 1.5 * rng.random((K, d))
+    return K, d, mu, s2, np.ones(K)
 
 
 def incov_for(wl):
     import numpy as np
+    if wl == "gmix64":              # C4: diagonal (2.38^2/64) I
+        return np.eye(64) * (2.38 ** 2 / 64)
     if wl == "rosen16":             # SURVEY.md 8(d) C3: analytic target covariance, Roberts-Rosenthal scale
         blk = (2.38 ** 2 / 16) * np.array([[0.5, 1.0], [1.0, 2.505]])
         return np.kron(np.eye(8), blk)
@@ -106,9 +121,28 @@ def cpu_reference_run(wl, nranks, nchain, nburn, nsamp, pl=0.9, bits=64):
     return nranks * nchain * (nburn + nsamp) / o["seconds"]
 
 
+def cpu_baseline_port(wl):
+    """Workloads the reference cannot run (GaussMix is not one of its likelihoods): the
+    oracle's plain-C restatement of the same normal-mode algorithm, one thread."""
+    import numpy as np
+    from oracle import mh
+    K, d, gmu, gs2, gw = gmix64_params()
+    N, nburn, nsamp = 128, 100, 100
+    par = np.concatenate([[float(K)], gmu.ravel(), gs2.ravel(), gw])
+    t0 = time.time()
+    mh.run_counter("gaussmix", d, N, nsamp, nburn, gmu[np.arange(N) % K], incov=incov_for(wl), par=par,
+                   seed=SEED, coin_group=0, pool_m=16, sync=1, thin=100, want_rows=False)
+    sec = time.time() - t0
+    return {"value": N * (nburn + nsamp) / sec, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle/mh_oracle.c (orc_run_counter), %d chains x %d steps, pool M=16, one thread" % (N, nburn + nsamp),
+            "seconds": round(sec, 1)}
+
+
 def cpu_baseline(wl):
     """Bounded sample of the same workload on all host cores: the reference's own launch
     shape (one rank per core, 4 chains per rank as in mcpar-dgauss.cc:31)."""
+    if WORKLOADS[wl]["lik"] == "gaussmix":
+        return cpu_baseline_port(wl)
     cores = os.cpu_count() or 1
     R = min(cores, 64)              # remote proposals cost O(N^2) in the reference: bound the rank count
     t0 = time.time()
@@ -191,7 +225,15 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    W = WORKLOADS[args.workload]
+    W = dict(WORKLOADS[args.workload])
+    if W["par"] == "gmix64":
+        K_, d_, gmu, gs2, gw = gmix64_params()
+        W["par"] = np.concatenate([[float(K_)], gmu.ravel(), gs2.ravel(), gw])
+        W["pinit"] = lambda N_: gmu[np.arange(N_) % K_]            # chain g starts at mu_{g mod K}
+    if "sync" in W and args.sync == 10:
+        args.sync = W["sync"]
+    if "thin" in W and args.thin == 10:
+        args.thin = W["thin"]
     d, Cg, sync, thin = W["d"], args.chains, args.sync, args.thin
     N = Cg * world
     K, Wu = args.steps, args.warmup
@@ -205,7 +247,7 @@ def main():
                       seed=SEED, pool_m=args.pool, thin=thin, coin_group=args.coin_group, history_steps=kept, device=local)
     e.set_stream(stream.cuda_stream)
     e.set_likelihood(W["lik"], W["par"]); e.set_covariance(incov_for(args.workload))
-    pin = tiled_pinit(N, d)[rank * Cg:(rank + 1) * Cg]
+    pin = np.ascontiguousarray((W["pinit"](N) if "pinit" in W else tiled_pinit(N, d))[rank * Cg:(rank + 1) * Cg])
     e.set_state(pin)
 
     # ---- sharded runs: pool all-gather + tuning all-reduce over NCCL (mcpar_b200/sharded.py)
