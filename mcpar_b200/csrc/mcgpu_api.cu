@@ -172,11 +172,13 @@ cudaError_t launch_steps_any(mcgpu_engine *e, int phase, const StepParams &p)
 }
 
 // Host copy of the device's Philox4x32-10 (mcgpu_device.cuh): with a job-wide coin the host
-// evaluates each step's local/remote draw itself -- words 2,3 of chain 0's accept block -- and
-// plans PH_LOCAL / PH_REMOTE launches without a device round trip.
+// evaluates each step's local/remote draw itself and plans PH_LOCAL / PH_REMOTE launches
+// without a device round trip.
 double host_coin(const mcgpu_engine *e, uint32_t step)
 {
-  uint32_t c0 = 0, c1 = 0, c2 = step, c3 = MCGPU_SLOT_ACCEPT;
+  // the coin is word 2*NP+1 of chain 0's local stream (mcgpu_device.cuh "draws")
+  const int np = (e->d + 1) / 2, idx = 2 * np + 1;
+  uint32_t c0 = 0, c1 = 0, c2 = step, c3 = (uint32_t)(idx / 4);
   uint32_t k0 = (uint32_t)e->cfg.seed, k1 = (uint32_t)(e->cfg.seed >> 32);
   for (int r = 0; r < 10; ++r) {
     const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
@@ -184,9 +186,8 @@ double host_coin(const mcgpu_engine *e, uint32_t step)
     c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  const unsigned long long bits = 0x3FF0000000000000ull | ((((unsigned long long)c2 << 32) | c3) >> 12);
-  double u; memcpy(&u, &bits, 8);
-  return u - 1.0;
+  const uint32_t w[4] = {c0, c1, c2, c3};
+  return (double)w[idx % 4] * (1.0 / 4294967296.0);
 }
 
 int upload_streams(mcgpu_engine *e)

@@ -9,7 +9,6 @@
 #include <stdint.h>
 
 #define MCGPU_FPEPS 1.0e-14          // src/mcpar.cc:15
-#define MCGPU_SLOT_ACCEPT 0x10000000u
 #define MCGPU_SLOT_REMOTE 0x40000000u
 #define MCGPU_MAX_D_REG 16           // thread-per-chain kernels keep the state in registers up to this d
 #define MCGPU_MAX_D 64
@@ -37,20 +36,27 @@ __device__ __forceinline__ Words philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return w;
 }
 
-// uniform in [0,1) from two words: the top 52 bits fill the mantissa of a double in [1,2),
-// then subtract 1 (two shifts, one LOP, one DADD; no integer->double conversion)
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo)
-{
-  return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12))) - 1.0;
-}
+// ---- draws ------------------------------------------------------------------------------
+// Every draw is ONE 32-bit Philox word (the reference's MKL streams deliver float32, i.e.
+// 24-bit, variates).  Words are addressed as a stream: word idx of (chain, step, base) is
+// word idx%4 of the Philox block at slot base + idx/4.
+//   local step   (base 0):            pair q -> words (2q, 2q+1); accept uniform -> word 2*NP;
+//                                      local/remote coin (of the group leader) -> word 2*NP+1
+//   remote candidate it (base REMOTE | it<<6): word 0 -> component pick, word 1 -> rejection
+//                                      uniform, pair q -> words (2+2q, 3+2q)
+// with NP = ceil(d/2) normal pairs.  At d = 2 a local step is one Philox call, and so is a
+// remote candidate.
+__device__ __forceinline__ double u32_half(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }           // [0,1)
+__device__ __forceinline__ double u32_mid(uint32_t w)  { return ((double)w + 0.5) * (1.0 / 4294967296.0); }   // (0,1)
+__device__ __forceinline__ double u32_pos(uint32_t w)  { return ((double)w + 1.0) * (1.0 / 4294967296.0); }   // (0,1]
+__device__ __forceinline__ uint32_t word_of(const Words &w, int k) { return k == 0 ? w.w0 : k == 1 ? w.w1 : k == 2 ? w.w2 : w.w3; }
 
 // Box-Muller pair, MKL BOXMULLER2 convention: z0 = r sin(2 pi u2), z1 = r cos(2 pi u2)
-__device__ __forceinline__ void normal_pair(const Words &w, double &z0, double &z1)
+__device__ __forceinline__ void normal_pair(uint32_t wa, uint32_t wb, double &z0, double &z1)
 {
-  const double u1 = u53(w.w0, w.w1), u2 = u53(w.w2, w.w3);
-  const double r = sqrt(-2.0 * log(1.0 - u1));
+  const double r = sqrt(fmax(-2.0 * log(u32_pos(wa)), 0.0));
   double s, c;
-  sincospi(2.0 * u2, &s, &c);
+  sincospi(2.0 * u32_half(wb), &s, &c);
   z0 = r * s; z1 = r * c;
 }
 

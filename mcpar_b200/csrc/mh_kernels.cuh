@@ -49,15 +49,14 @@ enum { RNG_PHILOX = 0, RNG_REPLAY = 1 };
 #endif
 
 // Box-Muller pair, MKL BOXMULLER2 convention: z0 = r sin(2 pi u2), z1 = r cos(2 pi u2)
-__device__ __forceinline__ void normal_pair_t(const Words &w, double &z0, double &z1, const MathTables &T)
+__device__ __forceinline__ void normal_pair_t(uint32_t wa, uint32_t wb, double &z0, double &z1, const MathTables &T)
 {
 #ifdef MCGPU_EXACT_TU
-  normal_pair(w, z0, z1);
+  normal_pair(wa, wb, z0, z1);
 #else
-  const double u1 = u53(w.w0, w.w1), u2 = u53(w.w2, w.w3);
-  const double r = sqrt(fmax(-2.0 * mc_log(1.0 - u1, T), 0.0));
+  const double r = sqrt(fmax(-2.0 * mc_log(u32_pos(wa), T), 0.0));
   double s, c;
-  mc_sincos2pi(u2, s, c, T);
+  mc_sincos2pi(u32_half(wb), s, c, T);
   z0 = r * s; z1 = r * c;
 #endif
 }
@@ -127,19 +126,17 @@ template <int D> struct Lik<MCGPU_GAUSSMIX, D> {
 // Kernel 1: production path
 // ----------------------------------------------------------------------------
 
-// Philox block -> normal pair.  Inlined at d <= 4 (two or fewer pairs per step); at larger d
-// the out-of-line copy keeps the d/2 draws of a step from being scheduled all at once, which
-// would hold every Philox state live and push the kernel past 255 registers.
-__device__ __forceinline__ void draw_pair_inl(uint32_t glo, uint32_t ghi, uint32_t step, uint32_t slot, uint32_t k0, uint32_t k1,
-                                              double &za, double &zb, const MathTables &T)
+// Out-of-line Philox call for d > 4: keeps the step's several blocks from being scheduled all
+// at once (every Philox state live -> past 255 registers).
+__device__ __noinline__ Words philox_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
-  const Words w = philox4x32_10(glo, ghi, step, slot, k0, k1);
-  normal_pair_t(w, za, zb, T);
+  return philox4x32_10(c0, c1, c2, c3, k0, k1);
 }
-__device__ __noinline__ void draw_pair_call(uint32_t glo, uint32_t ghi, uint32_t step, uint32_t slot, uint32_t k0, uint32_t k1,
-                                            double &za, double &zb, const MathTables &T)
+template <int D>
+__device__ __forceinline__ Words philox_d(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
-  draw_pair_inl(glo, ghi, step, slot, k0, k1, za, zb, T);
+  if (D <= 4) return philox4x32_10(c0, c1, c2, c3, k0, k1);
+  return philox_call(c0, c1, c2, c3, k0, k1);
 }
 
 // proposal factor entry from shared memory.  At d > 4 the read is volatile: the d(d+1)/2
@@ -327,13 +324,15 @@ mh_steps_kernel(const StepParams p)
     double u_acc;
     bool remote = PHASE == PH_REMOTE;
     long long zoff = 0;
+    constexpr int NP = (D + 1) / 2;                   // normal pairs per proposal
+    constexpr int ABLK = (2 * NP) / 4, AW = (2 * NP) % 4;   // accept uniform: word 2*NP of the local stream
+    Words wacc;
     if (RNGK == RNG_PHILOX) {
-      const Words wa = philox4x32_10(glo, ghi, step, MCGPU_SLOT_ACCEPT, p.key0, p.key1);
-      u_acc = u53(wa.w0, wa.w1);
-      if (PHASE == PH_MIXED && t >= p.sync) {          // one coin per group: the leader's spare words
-        double coin = u53(wa.w2, wa.w3);
-        coin = __shfl_sync(0xffffffffu, coin, leader);
-        remote = !(coin <= p.pl);                      // mcpar.cc:152
+      wacc = philox4x32_10(glo, ghi, step, (uint32_t)ABLK, p.key0, p.key1);
+      u_acc = u32_mid(word_of(wacc, AW));
+      if (PHASE == PH_MIXED && t >= p.sync) {          // one coin per group: the leader's word 2*NP+1
+        const uint32_t cw = __shfl_sync(0xffffffffu, word_of(wacc, AW + 1), leader);
+        remote = !(u32_half(cw) <= p.pl);              // mcpar.cc:152
       }
     } else {
       // reference stream offsets for an all-local run of ONE rank hosting the C chains
@@ -393,11 +392,21 @@ mh_steps_kernel(const StepParams p)
 #pragma unroll
           for (int i = 0; i < D; ++i) xz[i] = x[i];
         }
+        // word stream: local pair q = words (2q, 2q+1); remote pair q = words (2+2q, 3+2q)
+        // behind the pick / rejection-uniform words of block 0
+        const int woff = local_round ? 0 : 1;           // in units of pairs
+        Words blk;
+        if (!local_round) blk = philox_d<D>(tlo, thi, step, slot, p.key0, p.key1);
+        else if (ABLK == 0) blk = wacc;                 // d = 2: the accept block also carries pair 0
+        const Words blk0 = blk;
 #pragma unroll
-        for (int q = 0; 2 * q < D; ++q) {               // local: slots 0.. ; remote: slots base+1..
+        for (int q = 0; q < NP; ++q) {
+          const int qq = q + woff;                      // pair position in the stream
+          if ((qq & 1) == 0 && !(qq == 0 && ABLK == 0 && local_round))
+            blk = philox_d<D>(tlo, thi, step, slot + (uint32_t)(qq >> 1), p.key0, p.key1);
+          const uint32_t wa = (qq & 1) ? blk.w2 : blk.w0, wb = (qq & 1) ? blk.w3 : blk.w1;
           double za, zb;
-          if (D <= 4) draw_pair_inl(tlo, thi, step, slot + (local_round ? 0u : 1u) + (uint32_t)q, p.key0, p.key1, za, zb, T);
-          else draw_pair_call(tlo, thi, step, slot + (local_round ? 0u : 1u) + (uint32_t)q, p.key0, p.key1, za, zb, T);
+          normal_pair_t(wa, wb, za, zb, T);
           if (local_round) {
 #pragma unroll
             for (int i = 2 * q; i < D; ++i) xz[i] += factor_at<D>(sT, i * D + 2 * q) * za;
@@ -417,9 +426,8 @@ mh_steps_kernel(const StepParams p)
           continue;
         }
         if constexpr (CAN_REMOTE) {
-          const Words w0 = philox4x32_10(tlo, thi, step, slot, p.key0, p.key1);
-          const int c = (int)__umulhi(w0.w0, (uint32_t)p.pool_m);      // viRngUniform(0, tchains), mcpar.cc:337
-          const double u = u53(w0.w2, w0.w3);                          // vsRngUniform, mcpar.cc:401
+          const int c = (int)__umulhi(blk0.w0, (uint32_t)p.pool_m);    // viRngUniform(0, tchains), mcpar.cc:337
+          const double u = u32_mid(blk0.w1);                           // vsRngUniform, mcpar.cc:401
           double xc[D], am;
 #pragma unroll
           for (int i = 0; i < D; ++i) xc[i] = sPmh[c * D + i].x + sPs[c * D + i] * xz[i];   // DIAGONAL storage, :348-350

@@ -147,15 +147,19 @@ mh_wide_kernel(const WideParams p)
   for (int k = 0; k < p.nsteps; ++k) {
     const uint32_t step = p.step0 + (uint32_t)k;
     const int t = p.t0 + k;
-    const Words wa = philox4x32_10(glo, ghi, step, MCGPU_SLOT_ACCEPT, p.key0, p.key1);
-    const double u_acc = u53(wa.w0, wa.w1);
+    constexpr int ABLK = (2 * L) / 4, AW = (2 * L) % 4;     // accept uniform: word 2*NP (NP = L pairs) of the local stream
+    const Words wacc = philox4x32_10(glo, ghi, step, (uint32_t)ABLK, p.key0, p.key1);
+    const double u_acc = u32_mid(word_of(wacc, AW));
     double xt0, xt1, cfac = 1.0;
     int cpick = 0;
 
     if (PHASE != PH_REMOTE) {
-      // genLocal: lane r's Box-Muller pair is normals (2r, 2r+1) = Philox slot r
+      // genLocal: lane r's Box-Muller pair = words (2r, 2r+1) of the local stream
       double za, zb;
-      draw_pair_inl(glo, ghi, step, (uint32_t)r, p.key0, p.key1, za, zb, T);
+      {
+        const Words b = philox4x32_10(glo, ghi, step, (uint32_t)(r >> 1), p.key0, p.key1);
+        normal_pair_t((r & 1) ? b.w2 : b.w0, (r & 1) ? b.w3 : b.w1, za, zb, T);
+      }
       if (diag) {
         xt0 = x0 + tdiag0 * za; xt1 = x1 + tdiag1 * zb;
       } else {
@@ -180,9 +184,13 @@ mh_wide_kernel(const WideParams p)
         const uint32_t slot = MCGPU_SLOT_REMOTE | (it << 6);
         const Words w0 = philox4x32_10(glo, ghi, step, slot, p.key0, p.key1);      // same block in every lane of the chain
         const int c = (int)__umulhi(w0.w0, (uint32_t)p.pool_m);                     // viRngUniform, mcpar.cc:337
-        const double u = u53(w0.w2, w0.w3);                                         // vsRngUniform, mcpar.cc:401
+        const double u = u32_mid(w0.w1);                                            // vsRngUniform, mcpar.cc:401
         double za, zb;
-        draw_pair_inl(glo, ghi, step, slot + 1u + (uint32_t)r, p.key0, p.key1, za, zb, T);
+        {                                                // lane r's pair = words (2+2r, 3+2r) of the candidate's stream
+          const int qq = r + 1;
+          const Words b = philox4x32_10(glo, ghi, step, slot + (uint32_t)(qq >> 1), p.key0, p.key1);
+          normal_pair_t((qq & 1) ? b.w2 : b.w0, (qq & 1) ? b.w3 : b.w1, za, zb, T);
+        }
         const double c0 = __ldg(p.pm + (size_t)i0 * p.mpad + c) + __ldg(p.psd + (size_t)i0 * p.mpad + c) * za;
         const double c1 = __ldg(p.pm + (size_t)(i0 + 1) * p.mpad + c) + __ldg(p.psd + (size_t)(i0 + 1) * p.mpad + c) * zb;
         sx[i0] = c0; sx[i0 + 1] = c1;

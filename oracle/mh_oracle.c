@@ -471,28 +471,30 @@ done:
 /* ------------------------------------------------------------------ */
 /* COUNTER engine: same algorithm, draws addressed by (chain, step, slot) */
 /* ------------------------------------------------------------------ */
-/* Philox counter = (g_lo, g_hi, step, slot); key = seed.  Slots:
- *   p (0..)               local-proposal normal pair p   -> words (0,1)=u1, (2,3)=u2
- *   0x10000000            accept uniform = words (0,1);   words (2,3) of the coin
- *                         group LEADER's block = the group's local/remote coin
- *   0x40000000|it<<6|0    remote iteration it: word 0 -> component pick, words (2,3) -> uniform
- *   0x40000000|it<<6|1+p  remote iteration it: normal pair p
- * Box-Muller (MKL BOXMULLER2 convention): z0 = r sin(2 pi u2), z1 = r cos(2 pi u2),
- * r = sqrt(-2 ln(1-u1)).                                                        */
-#define SLOT_ACCEPT 0x10000000u
+/* Philox counter = (g_lo, g_hi, step, slot); key = seed.  Every draw is ONE 32-bit word;
+ * words are addressed as a stream: word idx of (chain, step, base) is word idx%4 of the block
+ * at slot base + idx/4.
+ *   local step (base 0):   pair q -> words (2q, 2q+1); accept uniform -> word 2*NP;
+ *                          local/remote coin (of the coin group's leader chain) -> word 2*NP+1
+ *   remote candidate it (base 0x40000000 | it<<6): word 0 -> component pick, word 1 ->
+ *                          rejection uniform, pair q -> words (2+2q, 3+2q)
+ * NP = ceil(d/2).  Box-Muller (MKL BOXMULLER2 convention): z0 = r sin(2 pi u2),
+ * z1 = r cos(2 pi u2), r = sqrt(-2 ln v), v = (wa+1) 2^-32, u2 = wb 2^-32.             */
 #define SLOT_REMOTE 0x40000000u
+#define W32 (1.0 / 4294967296.0)
 
-static void draw(const orc_config *cfg, uint64_t g, uint32_t step, uint32_t slot, uint32_t w[4])
+static uint32_t draw_word(const orc_config *cfg, uint64_t g, uint32_t step, uint32_t base, int idx)
 {
-  uint32_t ctr[4] = {(uint32_t)g, (uint32_t)(g >> 32), step, slot};
-  uint32_t key[2] = {(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)};
+  uint32_t ctr[4] = {(uint32_t)g, (uint32_t)(g >> 32), step, base + (uint32_t)(idx / 4)};
+  uint32_t key[2] = {(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)}, w[4];
   orc_philox4x32_10(ctr, key, w);
+  return w[idx % 4];
 }
 
-static void normal_pair(const uint32_t w[4], double *z0, double *z1)
+static void normal_pair(uint32_t wa, uint32_t wb, double *z0, double *z1)
 {
-  double u1 = orc_u53(w[0], w[1]), u2 = orc_u53(w[2], w[3]);
-  double r = sqrt(-2.0 * log(1.0 - u1));
+  double v = ((double)wa + 1.0) * W32, u2 = (double)wb * W32;
+  double r = sqrt(fmax(-2.0 * log(v), 0.0));
   double a = 6.283185307179586476925 * u2;
   *z0 = r * sin(a); *z1 = r * cos(a);
 }
@@ -518,7 +520,8 @@ int orc_run_counter(const orc_config *cfg, const double *pinit, const double *in
   if (rc) goto done;
   long long nacc = 0, ntry = 0; int irate = 50;
   long long riters = 0;
-  uint32_t step = 0, w[4];
+  uint32_t step = 0;
+  const int NP = (d + 1) / 2;
 
   for (int isamp = 0; isamp < cfg->nburn + cfg->nsamp; ++isamp, ++step) {
     const int burn = isamp < cfg->nburn;
@@ -532,21 +535,19 @@ int orc_run_counter(const orc_config *cfg, const double *pinit, const double *in
       double *xg = x + (size_t)g*d;
       int remotep = 0; double cfac = 1.0;
       if (!burn && t >= cfg->sync) {                   /* mcpar.cc:142-159, one coin per group */
-        draw(cfg, (uint64_t)(g / G) * G, step, SLOT_ACCEPT, w);
-        remotep = !(orc_u53(w[2], w[3]) <= cfg->pl);
+        remotep = !((double)draw_word(cfg, (uint64_t)(g / G) * G, step, 0, 2*NP + 1) * W32 <= cfg->pl);
       }
       if (!remotep) {                                  /* genLocal with the scaled factor */
-        for (int p = 0; 2*p < d; ++p) { draw(cfg, g, step, (uint32_t)p, w); normal_pair(w, &z[2*p], &z[2*p+1]); }
+        for (int p = 0; p < NP; ++p) normal_pair(draw_word(cfg, g, step, 0, 2*p), draw_word(cfg, g, step, 0, 2*p + 1), &z[2*p], &z[2*p+1]);
         for (int i = 0; i < d; ++i) { double acc = xg[i]; for (int q = 0; q <= i; ++q) acc += T0[i*d+q] * z[q]; xt[i] = acc; }
       } else {                                         /* genRemote, per-chain rejection loop over the pool */
         double qmax = 0, qsum = 0; int c = 0;
         for (uint32_t it = 0;; ++it) {
           ++riters;
-          draw(cfg, g, step, SLOT_REMOTE | (it << 6), w);
-          c = (int)(((uint64_t)w[0] * (uint64_t)M) >> 32);
-          double u = orc_u53(w[2], w[3]);
-          uint32_t wz[4];
-          for (int p = 0; 2*p < d; ++p) { draw(cfg, g, step, SLOT_REMOTE | (it << 6) | (uint32_t)(1+p), wz); normal_pair(wz, &z[2*p], &z[2*p+1]); }
+          const uint32_t base = SLOT_REMOTE | (it << 6);
+          c = (int)(((uint64_t)draw_word(cfg, g, step, base, 0) * (uint64_t)M) >> 32);
+          double u = ((double)draw_word(cfg, g, step, base, 1) + 0.5) * W32;
+          for (int p = 0; p < NP; ++p) normal_pair(draw_word(cfg, g, step, base, 2 + 2*p), draw_word(cfg, g, step, base, 3 + 2*p), &z[2*p], &z[2*p+1]);
           for (int i = 0; i < d; ++i) {
             mut[i] = pool[((size_t)c*d+i)*2]; sigt[i] = sqrt(pool[((size_t)c*d+i)*2+1]);
             xt[i] = mut[i] + sigt[i]*z[i];
@@ -563,8 +564,7 @@ int orc_run_counter(const orc_config *cfg, const double *pinit, const double *in
       }
       double lyt;
       orc_loglik(cfg->lik, d, par, 1, xt, &lyt);
-      draw(cfg, g, step, SLOT_ACCEPT, w);
-      double u = orc_u53(w[0], w[1]);
+      double u = ((double)draw_word(cfg, g, step, 0, 2*NP) + 0.5) * W32;
       double pac = exp(lyt - ly[g]); if (!burn) pac *= cfac;
       int a = u < pac;
       ++ntry; nacc += a;
