@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -752,19 +753,31 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
           CK(fast::launch_pool_prep(e->pool[e->pool_cur], e->M, e->mpad, e->d, e->pprep, e->pprep + (size_t)e->d * e->mpad,
                                     e->pprep + (size_t)2 * e->d * e->mpad, e->stream));
         }
-        int k = 0;
-        while (k < n) {
-          const long long t = e->t_main + k;
-          auto is_remote = [&](long long tt) {
-            return tt >= sync && !(host_coin(e, (uint32_t)(e->nburn_total + tt)) <= e->cfg.pl);   // mcpar.cc:142-152
-          };
-          const bool rem = is_remote(t);
-          int len = 1;
-          while (k + len < n && is_remote(t + len) == rem) ++len;
-          p.step0 = (uint32_t)(e->nburn_total + t); p.nsteps = len; p.t0 = (int)t;
-          p.pool_next = (k + len == n) ? e->pool[e->pool_cur ^ 1] : nullptr;    // publish at the end of the window
-          CK(launch_steps_any(e, rem ? PH_REMOTE : PH_LOCAL, p));
-          k += len;
+        auto is_remote = [&](long long tt) {
+          return tt >= sync && !(host_coin(e, (uint32_t)(e->nburn_total + tt)) <= e->cfg.pl);   // mcpar.cc:142-152
+        };
+        static const int plan = getenv("MCGPU_PLAN") ? atoi(getenv("MCGPU_PLAN")) : 1;
+        uint32_t mask = 0;
+        for (int k = 0; k < n && k < 32; ++k) if (is_remote(e->t_main + k)) mask |= 1u << k;
+        if (plan && !e->wide && n <= 32) {
+          // one launch per window: the lean local kernel when no step of the window is remote,
+          // otherwise the two-path kernel with the host-drawn plan (uniform branches)
+          p.step0 = (uint32_t)(e->nburn_total + e->t_main); p.nsteps = n; p.t0 = (int)e->t_main;
+          p.pool_next = e->pool[e->pool_cur ^ 1];
+          p.plan_mask = mask; p.plan_valid = 1;
+          CK(launch_steps_any(e, mask ? PH_MIXED : PH_LOCAL, p));
+        } else {
+          int k = 0;
+          while (k < n) {
+            const long long t = e->t_main + k;
+            const bool rem = is_remote(t);
+            int len = 1;
+            while (k + len < n && is_remote(t + len) == rem) ++len;
+            p.step0 = (uint32_t)(e->nburn_total + t); p.nsteps = len; p.t0 = (int)t;
+            p.pool_next = (k + len == n) ? e->pool[e->pool_cur ^ 1] : nullptr;    // publish at the end of the window
+            CK(launch_steps_any(e, rem ? PH_REMOTE : PH_LOCAL, p));
+            k += len;
+          }
         }
       }
     }

@@ -75,6 +75,7 @@ struct StepParams {
   int nburn_total;                 // replay offsets: burn-in length of the run
   int sync, coin_group;
   double pl;
+  uint32_t plan_mask; int plan_valid;   // PH_MIXED with a job-wide coin: bit k = step k of this launch is remote
   // remote-proposal pool: [pool_m][d][2] (mu, sigma^2); slot s is global chain s*pool_stride
   const double *pool_cur; double *pool_next;
   int pool_m; long long pool_stride;

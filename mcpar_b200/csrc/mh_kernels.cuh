@@ -330,9 +330,12 @@ mh_steps_kernel(const StepParams p)
     if (RNGK == RNG_PHILOX) {
       wacc = philox4x32_10(glo, ghi, step, (uint32_t)ABLK, p.key0, p.key1);
       u_acc = u32_mid(word_of(wacc, AW));
-      if (PHASE == PH_MIXED && t >= p.sync) {          // one coin per group: the leader's word 2*NP+1
-        const uint32_t cw = __shfl_sync(0xffffffffu, word_of(wacc, AW + 1), leader);
-        remote = !(u32_half(cw) <= p.pl);              // mcpar.cc:152
+      if (PHASE == PH_MIXED) {
+        if (p.plan_valid) remote = (p.plan_mask >> k) & 1u;   // job-wide coin, drawn by the host (launch-uniform)
+        else if (t >= p.sync) {                        // one coin per group: the leader's word 2*NP+1
+          const uint32_t cw = __shfl_sync(0xffffffffu, word_of(wacc, AW + 1), leader);
+          remote = !(u32_half(cw) <= p.pl);            // mcpar.cc:152
+        }
       }
     } else {
       // reference stream offsets for an all-local run of ONE rank hosting the C chains
