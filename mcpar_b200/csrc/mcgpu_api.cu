@@ -161,10 +161,10 @@ cudaError_t launch_steps_any(mcgpu_engine *e, int phase, const StepParams &p)
     w.x = p.x; w.ly = p.ly; w.mu = p.mu; w.ps = p.ps; w.C = p.C; w.chain0 = p.chain0;
     w.factor_cm = e->factor_cm; w.factor_rm = e->factor; w.diagonal = e->diag_d; w.counts = p.counts;
     w.key0 = p.key0; w.key1 = p.key1; w.step0 = p.step0; w.nsteps = p.nsteps; w.t0 = p.t0;
-    w.pm = e->pprep; w.ph = e->pprep + (size_t)e->d * e->mpad; w.psd = e->pprep + (size_t)2 * e->d * e->mpad;
+    w.pmh = reinterpret_cast<const double2*>(e->pprep); w.psd = e->pprep + (size_t)2 * e->d * e->mpad;
     w.pool_m = e->M; w.mpad = e->mpad; w.pool_next = p.pool_next; w.pool_stride = p.pool_stride;
     w.hist = p.hist; w.thin = p.thin; w.hist_step0 = p.hist_step0;
-    w.gm_mu = e->gm_t; w.gm_is2 = e->gm_t ? e->gm_t + (size_t)e->d * e->kpad : nullptr;
+    w.gm2 = reinterpret_cast<const double2*>(e->gm_t);
     w.gm_lw = e->gm_t ? e->gm_t + (size_t)2 * e->d * e->kpad : nullptr; w.kpad = e->kpad;
     return fast::launch_wide(e->lik, e->d, phase, w, e->stream);
   }
@@ -536,13 +536,13 @@ int mcgpu_set_likelihood(mcgpu_engine *e, int lik, const double *par, int npar)
     e->mpad = (e->M + L - 1) / L * L;
     if (!e->pprep) CK(cudaMalloc((void**)&e->pprep, (size_t)3 * d * e->mpad * 8));
     if (e->gm_t) { cudaFree(e->gm_t); e->gm_t = nullptr; }
-    if (lik == MCGPU_GAUSSMIX) {                        // [d][Kpad] mu, [d][Kpad] 1/s2, [Kpad] log w; padding has weight 0
-      e->kpad = (K + L - 1) / L * L;
+    if (lik == MCGPU_GAUSSMIX) {                        // [d][Kpad] (mu, 1/s2) pairs, then [Kpad] log w; padding has weight 0
+      e->kpad = (K + 2 * L - 1) / (2 * L) * (2 * L);
       std::vector<double> t((size_t)2 * d * e->kpad + e->kpad, 0.0);
       for (int k = 0; k < e->kpad; ++k) {
         for (int i = 0; i < d; ++i) {
-          t[(size_t)i * e->kpad + k] = k < K ? dev[(size_t)k * d + i] : 0.0;
-          t[(size_t)d * e->kpad + (size_t)i * e->kpad + k] = k < K ? dev[(size_t)K * d + (size_t)k * d + i] : 0.0;
+          t[((size_t)i * e->kpad + k) * 2] = k < K ? dev[(size_t)k * d + i] : 0.0;
+          t[((size_t)i * e->kpad + k) * 2 + 1] = k < K ? dev[(size_t)K * d + (size_t)k * d + i] : 0.0;
         }
         t[(size_t)2 * d * e->kpad + k] = k < K ? dev[(size_t)2 * K * d + k] : -INFINITY;
       }
@@ -750,7 +750,7 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
       } else {                                               // job-wide coin: runs of local / remote steps
         if (e->wide && e->t_main >= sync) {                  // (mu, sig^2) pool -> (mu, -1/2sig^2, sig), slot-fastest
           ++e->launches;
-          CK(fast::launch_pool_prep(e->pool[e->pool_cur], e->M, e->mpad, e->d, e->pprep, e->pprep + (size_t)e->d * e->mpad,
+          CK(fast::launch_pool_prep(e->pool[e->pool_cur], e->M, e->mpad, e->d, reinterpret_cast<double2*>(e->pprep),
                                     e->pprep + (size_t)2 * e->d * e->mpad, e->stream));
         }
         auto is_remote = [&](long long tt) {

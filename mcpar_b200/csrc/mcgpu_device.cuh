@@ -99,12 +99,12 @@ struct WideParams {
   unsigned long long *counts;
   uint32_t key0, key1, step0;
   int nsteps, t0;
-  // remote pool, prepared: pm / ph / psd [D][Mpad] (mu, -1/(2 sig^2), sigma), slot fastest
-  const double *pm, *ph, *psd; int pool_m, mpad;
+  // remote pool, prepared, slot fastest: pmh [D][Mpad] = (mu, -1/(2 sig^2)) pairs, psd [D][Mpad] = sigma
+  const double2 *pmh; const double *psd; int pool_m, mpad;
   double *pool_next; long long pool_stride;      // publication target [M][D][2]
   double *hist; int thin; long long hist_step0;
-  // likelihood: GaussMix parameters [D][Kpad] mu, [D][Kpad] 1/s2, [Kpad] log w (component fastest)
-  const double *gm_mu, *gm_is2, *gm_lw; int kpad;
+  // likelihood: GaussMix parameters, component fastest: gm2 [D][Kpad] = (mu, 1/s2) pairs, gm_lw [Kpad] = log w
+  const double2 *gm2; const double *gm_lw; int kpad;
 };
 
 // runtime-dispatched likelihood description (verification mode, batched evaluation)

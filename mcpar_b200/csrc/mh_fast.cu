@@ -12,17 +12,23 @@ bool wide_supported(int lik, int d)
   return (lik == MCGPU_ROSENBROCK1 || lik == MCGPU_GAUSSMIX) && (d == 8 || d == 16 || d == 32 || d == 64);
 }
 
+// chains per lane group: register-level reuse of the streamed GaussMix / pool parameters
+#ifndef MCGPU_WIDE_NCH64
+#define MCGPU_WIDE_NCH64 4
+#endif
+template <int D> struct WideNch { static constexpr int value = D >= 64 ? MCGPU_WIDE_NCH64 : (D >= 32 ? 2 : 1); };
+
 template <int LIK, int D>
 static cudaError_t launch_wide_d(int phase, const WideParams &p, cudaStream_t st)
 {
-  constexpr int L = D / 2;
-  const int block = 128, cpb = block / L;
+  constexpr int L = D / 2, NCH = WideNch<D>::value;
+  const int block = 128, gpb = block / L, cpb = gpb * NCH;
   const unsigned grid = (unsigned)((p.C + cpb - 1) / cpb);
-  const size_t smem = sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)cpb * 2 * D);
+  const size_t smem = sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)gpb * 2 * D * NCH);
   switch (phase) {
-    case PH_BURN:   mh_wide_kernel<LIK, D, PH_BURN><<<grid, block, smem, st>>>(p); break;
-    case PH_LOCAL:  mh_wide_kernel<LIK, D, PH_LOCAL><<<grid, block, smem, st>>>(p); break;
-    case PH_REMOTE: mh_wide_kernel<LIK, D, PH_REMOTE><<<grid, block, smem, st>>>(p); break;
+    case PH_BURN:   mh_wide_kernel<LIK, D, NCH, PH_BURN><<<grid, block, smem, st>>>(p); break;
+    case PH_LOCAL:  mh_wide_kernel<LIK, D, NCH, PH_LOCAL><<<grid, block, smem, st>>>(p); break;
+    case PH_REMOTE: mh_wide_kernel<LIK, D, NCH, PH_REMOTE><<<grid, block, smem, st>>>(p); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -47,9 +53,9 @@ cudaError_t launch_wide(int lik, int d, int phase, const WideParams &p, cudaStre
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double *pm, double *ph, double *psd, cudaStream_t st)
+cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd, cudaStream_t st)
 {
-  pool_prep_kernel<<<(D * mpad + 127) / 128, 128, 0, st>>>(pool, M, mpad, D, pm, ph, psd);
+  pool_prep_kernel<<<(D * mpad + 127) / 128, 128, 0, st>>>(pool, M, mpad, D, pmh, psd);
   return cudaGetLastError();
 }
 
