@@ -376,7 +376,7 @@ def main():
                 "hbm": {"achieved": per_gpu * bytes_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": per_gpu * bytes_step / 1e9 / hbm_peak, "bytes_per_chain_step": bytes_step,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
-        cpu = None if args.no_cpu else cpu_baseline(args.workload)
+        cpu = None if (args.no_cpu or world > 1) else cpu_baseline(args.workload)   # rank 0 at N = 1 only
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",

@@ -386,3 +386,125 @@ def test_remote_proposals_match_reference_distribution():
     ref_stat, gpu_stat = np.array(ref_stat), np.array(gpu_stat)
     for j in range(3):
         assert stats.ks_2samp(ref_stat[:, j], gpu_stat[:, j]).pvalue > 0.01, (j, ref_stat[:, j].mean(), gpu_stat[:, j].mean())
+
+
+# ---------------------------------------------------------------- edge cases
+def test_far_start_is_stuck_as_in_the_reference():
+    """DualGaussian has no log-sum-exp guard (rosenbrock.cc:75): far from both modes logL = -inf,
+    exp(-inf - -inf) = NaN, `acpt < NaN` is false, so such a chain rejects until a proposal lands
+    where logL is finite.  Verification mode and the production kernel must both follow that."""
+    eng = _engine()
+    d, C, R, nburn, nsamp = 2, 4, 1, 60, 40
+    pin = np.array([[60.0, 60.0], [0.0, 0.0], [-45.0, 50.0], [2.0, 2.0]])
+    Z, U, I = make_streams(R, C, d, nburn + nsamp, 21)
+    o = mh.run_replay("dualgaussian", d, C, R, nsamp, nburn, pin, Z, U, I, par=[5.0], trace=True)
+    # chain 0 cannot move during burn-in (local proposals only); a remote proposal may free it later
+    assert np.isinf(o["trace"]["pre_ly"][0, 0, 0]) and not o["accept"][0, :nburn, 0].any()
+    e = eng.Engine(d, C, mode="verify", chains_per_rank=C, trace=nburn + nsamp, history_steps=nsamp)
+    e.set_likelihood("dualgaussian", [5.0]); e.set_state(pin); e.set_streams(0, Z[0], U[0], I[0])
+    e.burnin(nburn); e.sample_begin(nsamp); e.sample(nsamp); e.synchronize()
+    tr = e.trace(0, nburn + nsamp)
+    assert np.array_equal(tr["accept"].astype(bool), o["accept"][0])
+    assert np.array_equal(e.state()["p"], o["p"][0])
+    e.close()
+    oc = mh.run_counter("dualgaussian", d, 64, 30, 60, np.tile(pin, (16, 1)), par=[5.0], pool_m=8, coin_group=0)
+    e = eng.Engine(d, 64, mode="normal", pool_m=8, coin_group=0, history_steps=30)
+    e.run(30, 60, np.tile(pin, (16, 1)), "dualgaussian", [5.0])
+    st = e.state()
+    assert np.allclose(st["p"], oc["p"], rtol=1e-7, atol=1e-9)
+    assert np.array_equal(np.isinf(st["ly"]), np.isinf(oc["ly"]))
+    e.close()
+
+
+@pytest.mark.parametrize("nburn,nsamp", [(0, 0), (0, 7), (37, 0), (51, 3), (52, 1)])
+def test_degenerate_lengths(nburn, nsamp):
+    """Empty phases and runs that end exactly on / next to a tuning boundary (isamp = 51)."""
+    eng = _engine()
+    d, C, R = 2, 4, 2
+    pin = tiled_pinit(C, d)
+    Z, U, I = make_streams(R, C, d, nburn + nsamp + 1, 31)
+    o = mh.run_replay("rosenbrock1", d, C, R, nsamp, nburn, pin, Z, U, I, trace=True)
+    e = eng.Engine(d, R * C, mode="verify", chains_per_rank=C, history_steps=max(nsamp, 1))
+    e.set_likelihood("rosenbrock1"); e.set_state(np.tile(pin, (R, 1)))
+    for r in range(R):
+        e.set_streams(r, Z[r], U[r], I[r])
+    e.burnin(nburn); e.sample_begin(nsamp); e.sample(nsamp); e.synchronize()
+    st = e.state()
+    assert np.array_equal(st["p"].reshape(R, C, d), o["p"]) and np.array_equal(st["ly"].reshape(R, C), o["ly"])
+    for r in range(R):
+        assert np.array_equal(e.factor(r), o["cov"][r])
+    assert e.stats()["history_rows"] == nsamp * R * C
+    e.close()
+    en = eng.Engine(d, 96, mode="normal", coin_group=0, pool_m=8, history_steps=max(nsamp, 1))
+    en.run(nsamp, nburn, tiled_pinit(96, d), "rosenbrock1")
+    oc = mh.run_counter("rosenbrock1", d, 96, nsamp, nburn, tiled_pinit(96, d), pool_m=8, coin_group=0)
+    assert np.allclose(en.state()["p"], oc["p"], rtol=1e-9, atol=1e-12) and np.array_equal(en.factor(), oc["cov"])
+    en.close()
+
+
+def test_single_chain_and_large_rank():
+    """C = 1 (one thread per CTA) and C = 1024 (the verify kernel's maximum CTA)."""
+    eng = _engine()
+    for C, nburn, nsamp in [(1, 120, 40), (1024, 60, 12)]:
+        pin = tiled_pinit(C, 2)
+        Z, U, I = make_streams(1, C, 2, nburn + nsamp, 41, mult=12)
+        o = mh.run_replay("rosenbrock1", 2, C, 1, nsamp, nburn, pin, Z, U, I, pl=0.5, trace=True)
+        e = eng.Engine(2, C, mode="verify", chains_per_rank=C, pl=0.5, trace=nburn + nsamp, history_steps=nsamp)
+        e.set_likelihood("rosenbrock1"); e.set_state(pin); e.set_streams(0, Z[0], U[0], I[0])
+        e.burnin(nburn); e.sample_begin(nsamp); e.sample(nsamp); e.synchronize()
+        tr = e.trace(0, nburn + nsamp)
+        assert np.array_equal(tr["accept"].astype(bool), o["accept"][0])
+        assert np.array_equal(tr["cursors"], o["used"][0][:3])
+        assert np.array_equal(e.state()["p"], o["p"][0]) and np.array_equal(e.musig(0), o["musig"][0])
+        e.close()
+
+
+def test_qriguess_matches_oracle():
+    """mcutil::qriguess on the device (Sobol points in a box, rank skip-ahead, mcutil.cc:16-31)."""
+    eng = _engine()
+    plo, phi = [0.0, -1.0, 2.0, 10.0, -3.0], [1.0, 1.0, 4.0, 11.0, 3.0]
+    for rank, npset in [(0, 1000), (3, 257), (1, 1)]:
+        assert np.array_equal(eng.qriguess(rank, npset, 5, plo, phi), mh.qriguess(rank, npset, 5, plo, phi))
+    with pytest.raises(eng.McgpuError):
+        eng.qriguess(0, 4, 17, [0] * 17, [1] * 17)
+
+
+def test_host_sink_receives_the_history():
+    """mcgpu_history_attach_host: rows drained on the side stream during sampling equal a read-back."""
+    eng = _engine()
+    N, nsamp, thin = 4096, 120, 4
+    e = eng.Engine(2, N, mode="normal", coin_group=0, pool_m=8, thin=thin, history_steps=nsamp // thin)
+    e.set_likelihood("dualgaussian", [5.0]); e.set_covariance(None); e.set_state(tiled_pinit(N, 2))
+    e.burnin(60)
+    sink = np.full((nsamp // thin, N, 3), np.nan)
+    e.attach_host_sink(sink)
+    e.sample_begin(nsamp)
+    for _ in range(nsamp // 10):
+        e.sample(10)
+    e.synchronize()
+    assert np.array_equal(sink, e.history())
+    e.attach_host_sink(None)
+    e.close()
+
+
+def test_api_misuse_is_reported():
+    eng = _engine()
+    e = eng.Engine(2, 64, mode="normal", history_steps=40)
+    with pytest.raises(eng.McgpuError, match="ESTATE"):
+        e.set_state(np.zeros((64, 2)))                 # likelihood first
+    e.set_likelihood("rosenbrock1")
+    with pytest.raises(eng.McgpuError, match="ESTATE"):
+        e.burnin(10)                                   # state first
+    e.set_state(np.zeros((64, 2)))
+    with pytest.raises(eng.McgpuError, match="ESTATE"):
+        e.sample(5)                                    # sample_begin first
+    e.sample_begin(40)
+    with pytest.raises(eng.McgpuError, match="EINVAL"):
+        e.sample(41)
+    with pytest.raises(eng.McgpuError, match="EINVAL"):
+        e.set_likelihood("rosenbrock2")                # couples neighbouring chains: verify mode only
+    e.close()
+    with pytest.raises(eng.McgpuError, match="EINVAL"):
+        eng.Engine(3, 64, mode="normal").set_likelihood("rosenbrock1")    # odd n (rosenbrock.hh:13-16)
+    with pytest.raises(eng.McgpuError, match="EINVAL"):
+        eng.Engine(2, 64, mode="normal", coin_group=3)
