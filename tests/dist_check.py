@@ -1,0 +1,57 @@
+"""Multi-process NCCL check (run under torchrun on >= 2 GPUs; tests/test_gpu_dist.py launches it):
+chains sharded one engine per rank, pool all-gathered in place and tuning counters all-reduced by
+mcpar_b200/sharded.py over NCCL, must reproduce the single-engine run bit for bit."""
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import tiled_pinit                        # noqa: E402
+from mcpar_b200 import engine                           # noqa: E402
+from mcpar_b200.sharded import DistGroup, Shard, ShardedRunner, check_even_pool   # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for lik, par, d, Cg, M, cg in [("dualgaussian", [5.0], 2, 4096, 16, 0), ("rosenbrock1", None, 2, 2048, 8, 32),
+                                   ("rosenbrock1", None, 16, 512, 8, 0)]:
+        N, nburn, nsamp, sync, pl = Cg * world, 130, 60, 10, 0.7
+        check_even_pool(Shard(rank, world, Cg), M)
+        pin = tiled_pinit(N, d)
+        stream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(stream)
+        e = engine.Engine(d, Cg, mode="normal", nchain_total=N, chain0=rank * Cg, pool_m=M, pl=pl, sync=sync,
+                          coin_group=cg, history_steps=nsamp, device=local)
+        e.set_stream(stream.cuda_stream)
+        e.set_likelihood(lik, par); e.set_covariance(None); e.set_state(pin[rank * Cg:(rank + 1) * Cg])
+        r = ShardedRunner(e, DistGroup(dist), lambda ptr: torch.as_tensor(ptr, device=dev))
+        r.burnin(nburn)
+        r.sample(nsamp, sync)
+        e.synchronize(); torch.cuda.synchronize()
+        mine = e.state()["p"]; hist = e.history(); fac = e.factor()
+        e.close()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (mine, hist, fac))
+        if rank == 0:
+            one = engine.Engine(d, N, mode="normal", pool_m=M, pl=pl, sync=sync, coin_group=cg, history_steps=nsamp, device=local)
+            one.run(nsamp, nburn, pin, lik, par)
+            same = (np.array_equal(np.concatenate([g[0] for g in gathered]), one.state()["p"])
+                    and np.array_equal(np.concatenate([g[1] for g in gathered], axis=1), one.history())
+                    and all(np.array_equal(g[2], one.factor()) for g in gathered))
+            print("dist_check", lik, "d=%d" % d, "world=%d" % world, "OK" if same else "MISMATCH", flush=True)
+            ok = ok and same
+            one.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
