@@ -22,6 +22,11 @@
 namespace mcgpu {
 namespace MCGPU_NS {
 
+#ifndef MCGPU_WIDE_UNROLL
+#define MCGPU_WIDE_UNROLL 4
+#endif
+constexpr int kWideUnroll = MCGPU_WIDE_UNROLL;   // inner-loop unroll of the streamed-parameter loops
+
 template <int L>
 __device__ __forceinline__ double group_sum(double v)
 {
@@ -83,7 +88,7 @@ __device__ __forceinline__ void wide_loglik(const double (&x0)[NCH], const doubl
       double q0[NCH], q1[NCH];
 #pragma unroll
       for (int c = 0; c < NCH; ++c) { q0[c] = 0.0; q1[c] = 0.0; }
-#pragma unroll 4
+#pragma unroll kWideUnroll
       for (int i = 0; i < D; ++i) {
         const double2 a = __ldg(g), b = __ldg(g + L);
         g += p.kpad;
@@ -177,7 +182,7 @@ __device__ __noinline__ double wide_pool_exact_sum(const double *sx, int c, int 
 #define MCGPU_WIDE_MINB 3       // d >= 32: <= 170 registers, 12 warps per SM (gpurun_out/tune_wide.log)
 #endif
 template <int LIK, int D, int NCH, int PHASE>
-__global__ void __launch_bounds__(128, (NCH > 1 ? MCGPU_WIDE_MINB : 4))
+__global__ void __launch_bounds__(128, (D >= 32 ? MCGPU_WIDE_MINB : 4))
 mh_wide_kernel(const WideParams p)
 {
   constexpr int L = D / 2;                      // lanes per group
