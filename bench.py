@@ -207,6 +207,8 @@ def main():
     ap.add_argument("--coin-group", type=int, default=0, help="0: one local/remote coin per step for the whole job; 1..32: per group of chains")
     ap.add_argument("--thin", type=int, default=10)
     ap.add_argument("--sync", type=int, default=10)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: in-kernel peer-to-peer stores over NVLink (default) or an NCCL all-gather call per window")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -258,7 +260,21 @@ def main():
     # ---- sharded runs: pool all-gather + tuning all-reduce over NCCL (mcpar_b200/sharded.py)
     from mcpar_b200.sharded import ShardedRunner, DistGroup
     as_tensor = lambda ptr: torch.as_tensor(ptr, device=dev)
-    runner = [ShardedRunner(e, DistGroup(dist), as_tensor) if world > 1 else None]
+
+    def gather_bytes(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+
+    def make_runner(eng):
+        if world == 1:
+            return None
+        r = ShardedRunner(eng, DistGroup(dist), as_tensor)
+        if args.exchange == "p2p":
+            r.enable_p2p(rank, world, gather_bytes)
+        return r
+
+    runner = [make_runner(e)]
 
     def burn(n):
         if world == 1:
@@ -301,7 +317,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     st = e.stats()
-    launches = st["kernel_launches"] - l0 + (K if world > 1 else 0)      # + NCCL all-gathers
+    launches = st["kernel_launches"] - l0 + (K if world > 1 and args.exchange == "nccl" else 0)   # + NCCL all-gathers
     value = N * sync * K / (ms * 1e-3)
     acc_rate = st["accepted"] / max(1, st["tried"])
     mean, cov = e.moments()
@@ -311,6 +327,8 @@ def main():
     if not args.no_e2e:
         nb_e, ns_e = 500, 1000
         kept_e = (ns_e + thin - 1) // thin
+        if world > 1:
+            dist.barrier()
         e.close(); del flush; torch.cuda.empty_cache()
         host_rows = torch.empty((kept_e, Cg, d + 1), dtype=torch.float64).pin_memory().numpy()
         host_pin = torch.from_numpy(np.ascontiguousarray(pin)).pin_memory().numpy()
@@ -327,7 +345,7 @@ def main():
             t1 = time.perf_counter()
             e.set_state(host_pin)                                       # H2D inside the timed region
             e.attach_host_sink(host_rows)                               # D2H drains on a side stream per window
-            runner[0] = ShardedRunner(e, DistGroup(dist), as_tensor) if world > 1 else None
+            runner[0] = make_runner(e)
             burn(nb_e)
             e.sample_begin(ns_e)
             for _ in range(ns_e // sync):
@@ -336,6 +354,8 @@ def main():
             e.synchronize()                                              # compute + drain finished
             torch.cuda.synchronize()
             t2 = time.perf_counter()
+            if world > 1:
+                dist.barrier()                                           # peers may still map this engine's exchange region
             e.close()
             tt = torch.tensor([t2 - t1], dtype=torch.float64, device=dev)
             if world > 1:
@@ -386,7 +406,10 @@ def main():
                                            "one local/remote coin per step" if args.coin_group == 0 else "coin per %d chains" % args.coin_group,
                                            thin, SEED, sync),
                            "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
-                           "parallelism": "chains sharded by global id, pool all-gather over NCCL each window" if world > 1 else "single GPU"},
+                           "parallelism": ("single GPU" if world == 1 else
+                                           "chains sharded by global id; pool exchanged inside the window kernel by peer-to-peer stores over NVLink"
+                                           if args.exchange == "p2p" else
+                                           "chains sharded by global id; pool all-gather over NCCL each window")},
                 "clocks": ck, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "accept_rate": acc_rate, "posterior_mean": [float(x) for x in mean],
                 "posterior_var": [float(cov[i, i]) for i in range(d)]}

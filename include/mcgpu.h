@@ -39,7 +39,8 @@ enum {
   MCGPU_ECUDA = -3,         /* CUDA runtime error (see mcgpu_last_error)   */
   MCGPU_ESTATE = -4,        /* call out of order                           */
   MCGPU_ENOMEM = -5,
-  MCGPU_ESTREAM = -6        /* a replay stream ran dry                     */
+  MCGPU_ESTREAM = -6,       /* a replay stream ran dry                     */
+  MCGPU_EPEER = -7          /* a peer GPU did not publish within the bound */
 };
 
 /* likelihood functors; replaces the VLFunc subclasses of src/rosenbrock.hh */
@@ -140,6 +141,24 @@ int  mcgpu_exchange_begin(mcgpu_engine *e, void **dev_buffer, size_t *total_byte
                           size_t *own_offset, size_t *own_bytes);
 int  mcgpu_exchange_end(mcgpu_engine *e);
 
+/* Peer-to-peer exchange between sharded engines (replaces MPI_Allgather(MPI_IN_PLACE),
+ * src/mcpar.cc:127-140, without a collective call): after attaching, the window
+ * kernels store the published (mu, sigma^2) slots directly into every peer GPU's
+ * next pool buffer over NVLink and signal an arrival counter there; the next
+ * window's kernel waits for the arrivals on the device.  mcgpu_sample may then
+ * cross multiples of `sync` and the exchange_begin/end calls are not used.  All
+ * engines must make the same sequence of sample calls.  Engines host equal
+ * contiguous blocks (chain0 = rank*nchain).  Attach before the first
+ * mcgpu_sample_begin.  mcgpu_synchronize returns MCGPU_EPEER if a window waited
+ * longer than ~10 s for a peer.
+ *  - one process per GPU: export a handle (cudaIpcMemHandle_t, MCGPU_P2P_HANDLE_BYTES),
+ *    all-gather the handles in rank order by any host means, attach;
+ *  - one process, several engines (same or different devices): attach_local. */
+#define MCGPU_P2P_HANDLE_BYTES 64
+int  mcgpu_p2p_export(mcgpu_engine *e, void *handle, size_t nbytes);
+int  mcgpu_p2p_attach(mcgpu_engine *e, int world, int rank, const void *handles);
+int  mcgpu_p2p_attach_local(mcgpu_engine *const *engines, int world);
+
 /* Burn-in tuning across sharded engines: device address of this engine's
  * {accepted, tried} int64 pair for the current tuning window (sum it across
  * engines between mcgpu_burnin calls that end on a tuning boundary). */
@@ -149,6 +168,9 @@ int  mcgpu_tuning_counters(mcgpu_engine *e, void **dev_counts);
  * one: all-reduce (sum) the tuning counters across engines, then mcgpu_tune. */
 int  mcgpu_burnin_some(mcgpu_engine *e, int nmax, int *ndone, int *tune_pending);
 int  mcgpu_tune(mcgpu_engine *e);
+/* The same for `world` sharded engines living in ONE process (one per GPU): burn all of
+ * them in, summing the counters across engines on the host at each tuning boundary. */
+int  mcgpu_burnin_group(mcgpu_engine *const *engines, int world, int nburn);
 
 int  mcgpu_synchronize(mcgpu_engine *e);
 

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -42,7 +43,11 @@ struct mcgpu_engine {
   double *x = nullptr, *ly = nullptr, *mu = nullptr, *ps = nullptr;
   double *factor = nullptr;
   unsigned long long *counts = nullptr;   // [0,1] window, [2,3] cumulative, [4,5] main-phase stats
-  double *pool[2] = {nullptr, nullptr}; int pool_cur = 0; int M = 0; long long stride = 1; bool pool_in_smem = true;
+  // exchange region (one allocation, IPC-exportable): 3 pool buffers [M][d][2] + the arrival counter
+  char *xchg = nullptr; size_t pool_bytes = 0, xchg_bytes = 0;
+  double *pool[3] = {nullptr, nullptr, nullptr}; int M = 0; long long stride = 1; bool pool_in_smem = true;
+  long long npub = 0;                      // publications completed since create: the pool read now is pool[npub % nbuf]
+  bool p2p = false; int p2p_world = 0; char **peers_d = nullptr; std::vector<void*> peer_opened; int *xflag_d = nullptr;
   double *hist = nullptr; long long hist_cap = 0, hist_kept = 0;
   int *overrun = nullptr;
   double *Zd = nullptr, *Ud = nullptr; int *Id = nullptr; long long nz = 0, nu = 0, ni = 0;
@@ -138,6 +143,27 @@ int cholesky_lower(int d, double *a)
   return 0;
 }
 
+// Pool buffers rotate with the publication count.  Two suffice when the exchange is stream-ordered (one
+// engine, or a caller-driven all-gather).  The peer-to-peer exchange needs three: a GPU that has all of
+// publication P may write publication P+1 into its peers while their last CTAs of the window that
+// produced P still read pool P-1 -- so P+1 must not alias P-1.  (Every main-phase launch waits for the
+// arrivals of the pool it is entitled to read, so no GPU is ever more than one publication ahead.)
+int pool_nbuf(const mcgpu_engine *e) { return e->p2p ? 3 : 2; }
+double *pool_cur(const mcgpu_engine *e) { return e->pool[e->npub % pool_nbuf(e)]; }
+double *pool_next(const mcgpu_engine *e) { return e->pool[(e->npub + 1) % pool_nbuf(e)]; }
+int arrivals_per_slot(const mcgpu_engine *e) { return e->wide ? e->d / 2 : 1; }   // the wide kernel's lanes arrive one by one
+
+// peer-to-peer exchange: where this launch publishes and what it waits for
+void fill_p2p(const mcgpu_engine *e, StepParams &p)
+{
+  if (!e->p2p) return;
+  p.peers = e->peers_d; p.npeers = e->p2p_world;
+  p.next_off = (long long)(((e->npub + 1) % 3) * e->pool_bytes); p.arr_off = (long long)(3 * e->pool_bytes);
+  p.arrivals = reinterpret_cast<const unsigned long long*>(e->xchg + 3 * e->pool_bytes);
+  p.wait_target = (unsigned long long)e->M * arrivals_per_slot(e) * (unsigned long long)e->npub;
+  p.xflag = e->xflag_d;
+}
+
 void fill_step_params(mcgpu_engine *e, StepParams &p)
 {
   memset(&p, 0, sizeof p);
@@ -163,6 +189,8 @@ cudaError_t launch_steps_any(mcgpu_engine *e, int phase, const StepParams &p)
     w.key0 = p.key0; w.key1 = p.key1; w.step0 = p.step0; w.nsteps = p.nsteps; w.t0 = p.t0;
     w.pmh = reinterpret_cast<const double2*>(e->pprep); w.psd = e->pprep + (size_t)2 * e->d * e->mpad;
     w.pool_m = e->M; w.mpad = e->mpad; w.pool_next = p.pool_next; w.pool_stride = p.pool_stride;
+    w.peers = p.peers; w.npeers = p.npeers; w.next_off = p.next_off; w.arr_off = p.arr_off;
+    w.arrivals = p.arrivals; w.wait_target = 0; w.xflag = p.xflag;   // the wide path waits in pool_prep
     w.hist = p.hist; w.thin = p.thin; w.hist_step0 = p.hist_step0;
     w.gm2 = reinterpret_cast<const double2*>(e->gm_t);
     w.gm_lw = e->gm_t ? e->gm_t + (size_t)2 * e->d * e->kpad : nullptr; w.kpad = e->kpad;
@@ -439,7 +467,11 @@ int mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out)
     TRY(dalloc(e, &e->x, (size_t)d * e->ld)); TRY(dalloc(e, &e->ly, (size_t)e->ld));
     TRY(dalloc(e, &e->mu, (size_t)d * e->ld)); TRY(dalloc(e, &e->ps, (size_t)d * e->ld));
     TRY(dalloc(e, &e->factor, (size_t)d * d)); TRY(dalloc(e, &e->counts, 6));
-    TRY(dalloc(e, &e->pool[0], (size_t)e->M * d * 2)); TRY(dalloc(e, &e->pool[1], (size_t)e->M * d * 2));
+    e->pool_bytes = ((size_t)e->M * d * 16 + 255) / 256 * 256;
+    e->xchg_bytes = 3 * e->pool_bytes + 256;
+    TRY(dalloc(e, &e->xchg, e->xchg_bytes));
+    for (int b = 0; b < 3; ++b) e->pool[b] = reinterpret_cast<double*>(e->xchg + (size_t)b * e->pool_bytes);
+    TRY(dalloc(e, &e->xflag_d, 1));
     e->hist_cap = cfg->history_steps;
     if (e->hist_cap > 0) TRY(dalloc(e, &e->hist, (size_t)e->hist_cap * e->C * (d + 1), false));
     e->host_streams.resize(1);
@@ -482,12 +514,25 @@ int mcgpu_destroy(mcgpu_engine *e)
   if (!e) return MCGPU_OK;
   cudaSetDevice(e->dev);
   if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+  if (e->stream && e->stream != e->own_stream) cudaStreamSynchronize(e->stream);
+  if (e->p2p && e->xchg) {
+    // peers may still be storing their last publication into this region: wait (bounded, 10 s) until every
+    // arrival this engine is owed has landed before the region is freed.  (Peers that imported the region
+    // must also have stopped using it: callers put a barrier between their last synchronize and destroy.)
+    const unsigned long long want = (unsigned long long)e->M * arrivals_per_slot(e) * (unsigned long long)e->npub;
+    for (int i = 0; i < 10000; ++i) {
+      unsigned long long got = 0;
+      if (cudaMemcpy(&got, e->xchg + 3 * e->pool_bytes, sizeof got, cudaMemcpyDeviceToHost) != cudaSuccess || got >= want) break;
+      struct timespec ts = {0, 1000000}; nanosleep(&ts, nullptr);
+    }
+  }
   timers_resolve(e);
-  void *ptrs[] = {e->x, e->ly, e->mu, e->ps, e->factor, e->counts, e->pool[0], e->pool[1], e->hist, e->overrun,
+  void *ptrs[] = {e->x, e->ly, e->mu, e->ps, e->factor, e->counts, e->xchg, e->xflag_d, e->peers_d, e->hist, e->overrun,
                   e->Zd, e->Ud, e->Id, e->ptrial, e->sig, e->mutrial, e->sigtrial, e->musig, e->snap[0], e->snap[1],
                   e->soff, e->cursors, e->irate_d, e->rstats, e->tr_accept, e->tr_remote, e->tr_trial_ly,
                   e->tr_trial_p, e->tr_cfac, e->tr_iters, e->lik_dev, e->factor_cm, e->diag_d, e->pprep, e->gm_t};
   for (void *p : ptrs) if (p) cudaFree(p);
+  for (void *q : e->peer_opened) cudaIpcCloseMemHandle(q);
   for (int i = 0; i < 2; ++i) { if (e->pin[i]) cudaFreeHost(e->pin[i]); if (e->pin_ev[i]) cudaEventDestroy(e->pin_ev[i]); }
   if (e->side) cudaStreamSynchronize(e->side);
   if (e->sink && e->sink_registered) cudaHostUnregister(e->sink);
@@ -741,17 +786,20 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
     } else {
       StepParams p; fill_step_params(e, p);
       p.counts = e->counts + 4;
-      p.pool_cur = e->pool[e->pool_cur];
+      p.pool_cur = pool_cur(e);
+      fill_p2p(e, p);
       p.hist = e->hist; p.hist_step0 = 0;
+      // publish (mu, sigma^2) into the next pool only from the launch that ends the window
+      double *const publish = ((e->t_main + n) % sync == 0) ? pool_next(e) : nullptr;
       if (e->cfg.coin_group > 0 || e->replay_local) {       // per-group coins: one mixed launch per window
         p.step0 = (uint32_t)(e->nburn_total + e->t_main); p.nsteps = n; p.t0 = (int)e->t_main;
-        p.pool_next = e->pool[e->pool_cur ^ 1];
+        p.pool_next = publish;
         CK(launch_steps_any(e, PH_MIXED, p));
       } else {                                               // job-wide coin: runs of local / remote steps
-        if (e->wide && e->t_main >= sync) {                  // (mu, sig^2) pool -> (mu, -1/2sig^2, sig), slot-fastest
-          ++e->launches;
-          CK(fast::launch_pool_prep(e->pool[e->pool_cur], e->M, e->mpad, e->d, reinterpret_cast<double2*>(e->pprep),
-                                    e->pprep + (size_t)2 * e->d * e->mpad, e->stream));
+        if (e->wide && (e->t_main >= sync || p.wait_target)) {   // (mu, sig^2) pool -> (mu, -1/2sig^2, sig), slot-fastest
+          ++e->launches;                                          // (with a peer-to-peer exchange it also waits for the arrivals)
+          CK(fast::launch_pool_prep(pool_cur(e), e->M, e->mpad, e->d, reinterpret_cast<double2*>(e->pprep),
+                                    e->pprep + (size_t)2 * e->d * e->mpad, p.arrivals, p.wait_target, p.xflag, e->stream));
         }
         auto is_remote = [&](long long tt) {
           return tt >= sync && !(host_coin(e, (uint32_t)(e->nburn_total + tt)) <= e->cfg.pl);   // mcpar.cc:142-152
@@ -763,7 +811,7 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
           // one launch per window: the lean local kernel when no step of the window is remote,
           // otherwise the two-path kernel with the host-drawn plan (uniform branches)
           p.step0 = (uint32_t)(e->nburn_total + e->t_main); p.nsteps = n; p.t0 = (int)e->t_main;
-          p.pool_next = e->pool[e->pool_cur ^ 1];
+          p.pool_next = publish;
           p.plan_mask = mask; p.plan_valid = 1;
           CK(launch_steps_any(e, mask ? PH_MIXED : PH_LOCAL, p));
         } else {
@@ -774,7 +822,7 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
             int len = 1;
             while (k + len < n && is_remote(t + len) == rem) ++len;
             p.step0 = (uint32_t)(e->nburn_total + t); p.nsteps = len; p.t0 = (int)t;
-            p.pool_next = (k + len == n) ? e->pool[e->pool_cur ^ 1] : nullptr;    // publish at the end of the window
+            p.pool_next = (k + len == n) ? publish : nullptr;
             CK(launch_steps_any(e, rem ? PH_REMOTE : PH_LOCAL, p));
             k += len;
           }
@@ -792,9 +840,9 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
       e->sink_sent = e->hist_kept;
     }
     if (e->t_main % sync == 0) {
-      if (e->sharded) e->exchange_pending = true;          // caller all-gathers the published slices
+      if (e->sharded && !e->p2p) e->exchange_pending = true;   // caller all-gathers the published slices
       else if (e->verify) e->snap_cur ^= 1;
-      else e->pool_cur ^= 1;
+      else ++e->npub;                                      // one engine, or the kernels exchanged over NVLink themselves
     }
   }
   timer_end(e);
@@ -815,7 +863,7 @@ int mcgpu_exchange_begin(mcgpu_engine *e, void **dev_buffer, size_t *total_bytes
     // own pool slots: s with chain0 <= s*stride < chain0 + C
     const long long s0 = (e->cfg.chain0 + e->stride - 1) / e->stride;
     const long long s1 = std::min<long long>(e->M, (e->cfg.chain0 + e->C + e->stride - 1) / e->stride);
-    *dev_buffer = e->pool[e->pool_cur ^ 1];
+    *dev_buffer = pool_next(e);
     if (total_bytes) *total_bytes = (size_t)e->M * d * 16;
     if (own_offset) *own_offset = (size_t)s0 * d * 16;
     if (own_bytes) *own_bytes = (size_t)std::max<long long>(0, s1 - s0) * d * 16;
@@ -827,8 +875,127 @@ int mcgpu_exchange_end(mcgpu_engine *e)
 {
   if (!e) return MCGPU_EINVAL;
   if (!e->exchange_pending) return MCGPU_OK;
-  if (e->verify) e->snap_cur ^= 1; else e->pool_cur ^= 1;
+  if (e->verify) e->snap_cur ^= 1; else ++e->npub;
   e->exchange_pending = false;
+  return MCGPU_OK;
+}
+
+// ---- peer-to-peer exchange --------------------------------------------------------------------
+// The window kernels of sharded engines store their published (mu, sigma^2) slots straight into
+// every GPU's next pool buffer over NVLink and bump that GPU's arrival counter; the next window's
+// kernel waits on its own counter.  No host round trip, no separate collective launch: this
+// replaces MPI_Allgather(MPI_IN_PLACE) of src/mcpar.cc:127-140 inside the step kernel.
+static int p2p_check(mcgpu_engine *e, int world, int rank)
+{
+  if (e->verify || e->replay_local) return fail(e, MCGPU_ESTATE, "peer-to-peer exchange exists in NORMAL mode only");
+  if (e->npub != 0 || e->sampling || e->p2p) return fail(e, MCGPU_ESTATE, "attach peers once, before the first mcgpu_sample_begin");
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(e, MCGPU_EINVAL, "bad world/rank");
+  if (e->C * world != e->N || e->cfg.chain0 != rank * e->C) return fail(e, MCGPU_EINVAL, "peers must host equal contiguous blocks of chains: chain0 = rank * nchain");
+  return MCGPU_OK;
+}
+
+static int p2p_finish(mcgpu_engine *e, int world, const std::vector<char*> &bases)
+{
+  CK(cudaMalloc((void**)&e->peers_d, sizeof(char*) * world));
+  CK(cudaMemcpyAsync(e->peers_d, bases.data(), sizeof(char*) * world, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->p2p = true; e->p2p_world = world;
+  return MCGPU_OK;
+}
+
+int mcgpu_p2p_export(mcgpu_engine *e, void *handle, size_t nbytes)
+{
+  if (!e || !handle) return MCGPU_EINVAL;
+  if (nbytes < sizeof(cudaIpcMemHandle_t) || sizeof(cudaIpcMemHandle_t) > MCGPU_P2P_HANDLE_BYTES) return fail(e, MCGPU_EINVAL, "handle buffer too small");
+  if (!e->xchg) return fail(e, MCGPU_ESTATE, "no exchange region (VERIFY engine)");
+  DeviceGuard g(e->dev);
+  CK(cudaStreamSynchronize(e->stream));                    // the region is zeroed before anybody maps it
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, e->xchg));
+  memset(handle, 0, nbytes); memcpy(handle, &h, sizeof h);
+  return MCGPU_OK;
+}
+
+int mcgpu_p2p_attach(mcgpu_engine *e, int world, int rank, const void *handles)
+{
+  if (!e || !handles) return MCGPU_EINVAL;
+  int rc = p2p_check(e, world, rank); if (rc) return rc;
+  DeviceGuard g(e->dev);
+  std::vector<char*> bases(world, nullptr);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { bases[r] = e->xchg; continue; }
+    cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles + (size_t)r * MCGPU_P2P_HANDLE_BYTES, sizeof h);
+    void *q = nullptr;
+    CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    e->peer_opened.push_back(q); bases[r] = (char*)q;
+  }
+  return p2p_finish(e, world, bases);
+}
+
+int mcgpu_p2p_attach_local(mcgpu_engine *const *engines, int world)
+{
+  if (!engines || world < 1) return MCGPU_EINVAL;
+  for (int r = 0; r < world; ++r) {
+    if (!engines[r]) return MCGPU_EINVAL;
+    int rc = p2p_check(engines[r], world, r); if (rc) return rc;
+    if (engines[r]->M != engines[0]->M || engines[r]->d != engines[0]->d) return fail(engines[r], MCGPU_EINVAL, "peers differ in shape");
+  }
+  for (int r = 0; r < world; ++r) {
+    mcgpu_engine *e = engines[r];
+    DeviceGuard g(e->dev);
+    std::vector<char*> bases(world, nullptr);
+    for (int q = 0; q < world; ++q) {
+      bases[q] = engines[q]->xchg;
+      if (engines[q]->dev == e->dev) continue;
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, e->dev, engines[q]->dev));
+      if (!can) return fail(e, MCGPU_ECUDA, "devices cannot access each other's memory");
+      cudaError_t s = cudaDeviceEnablePeerAccess(engines[q]->dev, 0);
+      if (s != cudaSuccess && s != cudaErrorPeerAccessAlreadyEnabled) CK(s);
+      cudaGetLastError();
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    int rc = p2p_finish(e, world, bases); if (rc) return rc;
+  }
+  return MCGPU_OK;
+}
+
+// Burn-in of several sharded engines of one process: the window's {accepted, tried} counters are
+// summed over the engines before every tuning decision (what sharded.py does with an all-reduce).
+int mcgpu_burnin_group(mcgpu_engine *const *engines, int world, int nburn)
+{
+  if (!engines || world < 1 || nburn < 0) return MCGPU_EINVAL;
+  for (int r = 0; r < world; ++r) {
+    if (!engines[r]) return MCGPU_EINVAL;
+    if (engines[r]->verify) return fail(engines[r], MCGPU_EINVAL, "VERIFY mode tunes inside the kernel: use mcgpu_burnin");
+  }
+  int left = nburn;
+  while (left > 0) {
+    int done = 0, pending = 0;
+    for (int r = 0; r < world; ++r) {
+      int dr = 0, pr = 0;
+      int rc = mcgpu_burnin_some(engines[r], left, &dr, &pr); if (rc) return rc;
+      if (r > 0 && (dr != done || pr != pending)) return fail(engines[r], MCGPU_ESTATE, "engines of a group are out of step");
+      done = dr; pending = pr;
+    }
+    left -= done;
+    if (!pending) continue;
+    unsigned long long sum[2] = {0, 0};
+    for (int r = 0; r < world; ++r) {
+      mcgpu_engine *e = engines[r]; DeviceGuard g(e->dev);
+      unsigned long long c[2];
+      CK(cudaMemcpyAsync(c, e->counts, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      sum[0] += c[0]; sum[1] += c[1];
+    }
+    for (int r = 0; r < world; ++r) {
+      mcgpu_engine *e = engines[r]; DeviceGuard g(e->dev);
+      CK(cudaMemcpyAsync(e->counts, sum, sizeof sum, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaStreamSynchronize(e->stream));              // `sum` is pageable stack memory
+      int rc = mcgpu_tune(e); if (rc) return rc;
+    }
+  }
+  for (int r = 0; r < world; ++r) engines[r]->nburn_total = (int)engines[r]->burn_done;
   return MCGPU_OK;
 }
 
@@ -845,6 +1012,11 @@ int mcgpu_synchronize(mcgpu_engine *e)
   DeviceGuard g(e->dev);
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaStreamSynchronize(e->side));
+  if (e->p2p) {                                            // did a window give up waiting for a peer's publication?
+    int flag = 0;
+    CK(cudaMemcpy(&flag, e->xflag_d, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) return fail(e, MCGPU_EPEER, "peer-to-peer exchange timed out: a peer did not publish its pool slots");
+  }
   return MCGPU_OK;
 }
 
@@ -931,7 +1103,7 @@ int mcgpu_get_musig(mcgpu_engine *e, int local_rank, double *musig)
     const size_t nm = (size_t)2 * e->N * e->d;
     CK(cudaMemcpyAsync(musig, e->musig + (size_t)local_rank * nm, nm * 8, cudaMemcpyDeviceToHost, e->stream));
   } else {
-    CK(cudaMemcpyAsync(musig, e->pool[e->pool_cur], (size_t)e->M * e->d * 16, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(musig, pool_cur(e), (size_t)e->M * e->d * 16, cudaMemcpyDeviceToHost, e->stream));
   }
   CK(cudaStreamSynchronize(e->stream));
   return MCGPU_OK;
@@ -1089,7 +1261,7 @@ int mcgpu_device_ptr(mcgpu_engine *e, int which, void **ptr, size_t *bytes)
     case 2: *ptr = e->mu; nb = st; break;
     case 3: *ptr = e->ps; nb = st; break;
     case 4: *ptr = e->hist; nb = (size_t)e->hist_cap * e->C * (e->d + 1) * 8; break;
-    case 5: *ptr = e->verify ? e->snap[e->snap_cur] : e->pool[e->pool_cur]; nb = e->verify ? (size_t)2 * e->N * e->d * 8 : (size_t)e->M * e->d * 16; break;
+    case 5: *ptr = e->verify ? e->snap[e->snap_cur] : pool_cur(e); nb = e->verify ? (size_t)2 * e->N * e->d * 8 : (size_t)e->M * e->d * 16; break;
     default: return fail(e, MCGPU_EINVAL, "unknown buffer id");
   }
   if (bytes) *bytes = nb;

@@ -78,6 +78,11 @@ struct StepParams {
   uint32_t plan_mask; int plan_valid;   // PH_MIXED with a job-wide coin: bit k = step k of this launch is remote
   // remote-proposal pool: [pool_m][d][2] (mu, sigma^2); slot s is global chain s*pool_stride
   const double *pool_cur; double *pool_next;
+  // peer-to-peer exchange (chains sharded over GPUs, one process each): publication stores go
+  // straight into every peer's next pool buffer over NVLink, then bump the peer's arrival counter
+  char *const *peers; int npeers; long long next_off, arr_off;
+  // consumer side: wait until `arrivals` (this GPU's counter) reaches wait_target before reading the pool
+  const unsigned long long *arrivals; unsigned long long wait_target; int *xflag;
   int pool_m; long long pool_stride;
   int pool_in_smem;
   // sample history: rows (p..., logL), kept step major, then hosted chain
@@ -102,6 +107,11 @@ struct WideParams {
   // remote pool, prepared, slot fastest: pmh [D][Mpad] = (mu, -1/(2 sig^2)) pairs, psd [D][Mpad] = sigma
   const double2 *pmh; const double *psd; int pool_m, mpad;
   double *pool_next; long long pool_stride;      // publication target [M][D][2]
+  // peer-to-peer exchange (chains sharded over GPUs, one process each): publication stores go
+  // straight into every peer's next pool buffer over NVLink, then bump the peer's arrival counter
+  char *const *peers; int npeers; long long next_off, arr_off;
+  // consumer side: wait until `arrivals` (this GPU's counter) reaches wait_target before reading the pool
+  const unsigned long long *arrivals; unsigned long long wait_target; int *xflag;
   double *hist; int thin; long long hist_step0;
   // likelihood: GaussMix parameters, component fastest: gm2 [D][Kpad] = (mu, 1/s2) pairs, gm_lw [Kpad] = log w
   const double2 *gm2; const double *gm_lw; int kpad;
@@ -132,5 +142,32 @@ struct VerifyParams {
   int *overrun;
   unsigned long long *rstats;        // {remote rank-steps, rejection iterations, accepted(main), tried(main)}
 };
+
+// ---- peer-to-peer exchange helpers ---------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// one thread per CTA waits (bounded: 10 s, then the engine reports MCGPU_EPEER) until all pool slots of
+// the exchange have arrived in this GPU's memory; callers follow with __syncthreads()
+__device__ __forceinline__ void wait_arrivals(const unsigned long long *arrivals, unsigned long long target, int *xflag)
+{
+  if (threadIdx.x == 0 && target) {
+    if (ld_acquire_sys(arrivals) >= target) return;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(arrivals) < target) {
+      if (global_ns() - t0 > 10000000000ull) { atomicExch(xflag, 1); break; }
+      __nanosleep(100);
+    }
+  }
+}
 
 }  // namespace mcgpu

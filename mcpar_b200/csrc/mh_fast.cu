@@ -53,9 +53,10 @@ cudaError_t launch_wide(int lik, int d, int phase, const WideParams &p, cudaStre
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd, cudaStream_t st)
+cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd,
+                             const unsigned long long *arrivals, unsigned long long wait_target, int *xflag, cudaStream_t st)
 {
-  pool_prep_kernel<<<(D * mpad + 127) / 128, 128, 0, st>>>(pool, M, mpad, D, pmh, psd);
+  pool_prep_kernel<<<(D * mpad + 127) / 128, 128, 0, st>>>(pool, M, mpad, D, pmh, psd, arrivals, wait_target, xflag);
   return cudaGetLastError();
 }
 

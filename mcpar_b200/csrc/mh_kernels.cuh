@@ -295,6 +295,10 @@ mh_steps_kernel(const StepParams p)
 
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) sT[i] = p.factor[i];
   if (MAIN) {
+    // peer-to-peer exchange: every main-phase launch (also a purely local one) waits until the pool it is
+    // entitled to read has arrived from all GPUs -- that also keeps any GPU from running more than one
+    // publication ahead of its peers (three pool buffers, mcgpu_api.cu)
+    if (p.wait_target) { wait_arrivals(p.arrivals, p.wait_target, p.xflag); __syncthreads(); }
     for (int k = threadIdx.x; k < p.nsteps; k += blockDim.x) sW[k] = 1.0 / (double)(p.t0 + k + 1);
     if (CAN_REMOTE && p.t0 + p.nsteps > p.sync)
       for (int i = threadIdx.x; i < Mpad * D; i += blockDim.x) {
@@ -527,10 +531,21 @@ mh_steps_kernel(const StepParams p)
       if (p.pool_next && gg % p.pool_stride == 0 && gg / p.pool_stride < p.pool_m) {
         const long long s = gg / p.pool_stride;
         const double winv = 1.0 / (double)(p.t0 + p.nsteps);
+        if (p.npeers > 0) {                            // sharded: store into every GPU's next pool over NVLink
+          for (int r = 0; r < p.npeers; ++r) {
+            double *dst = reinterpret_cast<double *>(p.peers[r] + p.next_off);
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-          p.pool_next[(s * D + i) * 2] = mu[i];
-          p.pool_next[(s * D + i) * 2 + 1] = ps[i] * winv;
+            for (int i = 0; i < D; ++i) { dst[(s * D + i) * 2] = mu[i]; dst[(s * D + i) * 2 + 1] = ps[i] * winv; }
+          }
+          __threadfence_system();
+          for (int r = 0; r < p.npeers; ++r)
+            atomicAdd_system(reinterpret_cast<unsigned long long *>(p.peers[r] + p.arr_off), 1ull);
+        } else {
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            p.pool_next[(s * D + i) * 2] = mu[i];
+            p.pool_next[(s * D + i) * 2 + 1] = ps[i] * winv;
+          }
         }
       }
     }

@@ -6,7 +6,8 @@ enum { PH_BURN = 0, PH_MIXED = 1, PH_LOCAL = 2, PH_REMOTE = 3 };   // kernel pha
 namespace fast {
 bool wide_supported(int lik, int d);
 cudaError_t launch_wide(int lik, int d, int phase, const WideParams &p, cudaStream_t st);
-cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd, cudaStream_t st);
+cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd,
+                             const unsigned long long *arrivals, unsigned long long wait_target, int *xflag, cudaStream_t st);
 cudaError_t launch_factor_prep(const double *rm, double *cm, int D, int *diag, cudaStream_t st);
 bool steps_supported(int lik, int d);
 size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem);

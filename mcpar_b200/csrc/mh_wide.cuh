@@ -383,8 +383,19 @@ mh_wide_kernel(const WideParams p)
         if (p.pool_next && gg % p.pool_stride == 0 && gg / p.pool_stride < p.pool_m) {
           const long long s = gg / p.pool_stride;
           const double wi = 1.0 / (double)(p.t0 + p.nsteps);
-          p.pool_next[(s * D + i0) * 2] = mu0[c];     p.pool_next[(s * D + i0) * 2 + 1] = ps0[c] * wi;
-          p.pool_next[(s * D + i0 + 1) * 2] = mu1[c]; p.pool_next[(s * D + i0 + 1) * 2 + 1] = ps1[c] * wi;
+          if (p.npeers > 0) {                          // sharded: store into every GPU's next pool over NVLink
+            for (int q = 0; q < p.npeers; ++q) {
+              double *dst = reinterpret_cast<double *>(p.peers[q] + p.next_off);
+              dst[(s * D + i0) * 2] = mu0[c];     dst[(s * D + i0) * 2 + 1] = ps0[c] * wi;
+              dst[(s * D + i0 + 1) * 2] = mu1[c]; dst[(s * D + i0 + 1) * 2 + 1] = ps1[c] * wi;
+            }
+            __threadfence_system();                    // each lane's stores are visible before its arrival
+            for (int q = 0; q < p.npeers; ++q)
+              atomicAdd_system(reinterpret_cast<unsigned long long *>(p.peers[q] + p.arr_off), 1ull);
+          } else {
+            p.pool_next[(s * D + i0) * 2] = mu0[c];     p.pool_next[(s * D + i0) * 2 + 1] = ps0[c] * wi;
+            p.pool_next[(s * D + i0 + 1) * 2] = mu1[c]; p.pool_next[(s * D + i0 + 1) * 2 + 1] = ps1[c] * wi;
+          }
         }
       }
       if (r == 0) { wacc += nacc[c]; ++nlive; }
@@ -400,8 +411,10 @@ mh_wide_kernel(const WideParams p)
 }
 
 // pool [M][D][2] (mu, sigma^2) -> pmh [D][Mpad] (mu, -1/(2 sigma^2)), psd [D][Mpad] sigma; padding slots get Q = 0
-static __global__ void pool_prep_kernel(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd)
+static __global__ void pool_prep_kernel(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd,
+                                        const unsigned long long *arrivals, unsigned long long wait_target, int *xflag)
 {
+  if (wait_target) { wait_arrivals(arrivals, wait_target, xflag); __syncthreads(); }   // peer-to-peer exchange: all slots in?
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= D * mpad) return;
   const int i = idx / mpad, s = idx % mpad;

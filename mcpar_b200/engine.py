@@ -14,13 +14,16 @@ LIB_PATH = os.path.join(HERE, "libmcgpu.so")
 
 LIK = {"rosenbrock1": 0, "rosenbrock2": 1, "gaussian": 2, "dualgaussian": 3, "gaussmix": 4}
 MODE = {"normal": 0, "verify": 1, "replay_local": 2}
-ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ECUDA", -4: "ESTATE", -5: "ENOMEM", -6: "ESTREAM"}
+ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ECUDA", -4: "ESTATE", -5: "ENOMEM", -6: "ESTREAM",
+          -7: "EPEER"}
+P2P_HANDLE_BYTES = 64
 
 EXPORTS = [
     "mcgpu_version", "mcgpu_device_count", "mcgpu_last_error", "mcgpu_create", "mcgpu_destroy",
     "mcgpu_set_stream", "mcgpu_set_likelihood", "mcgpu_set_covariance", "mcgpu_set_state",
     "mcgpu_set_streams", "mcgpu_burnin", "mcgpu_sample_begin", "mcgpu_sample",
-    "mcgpu_exchange_begin", "mcgpu_exchange_end", "mcgpu_tuning_counters", "mcgpu_burnin_some",
+    "mcgpu_exchange_begin", "mcgpu_exchange_end", "mcgpu_p2p_export", "mcgpu_p2p_attach",
+    "mcgpu_p2p_attach_local", "mcgpu_burnin_group", "mcgpu_tuning_counters", "mcgpu_burnin_some",
     "mcgpu_tune", "mcgpu_synchronize", "mcgpu_get_state", "mcgpu_get_factor", "mcgpu_get_musig",
     "mcgpu_get_trace", "mcgpu_history_read", "mcgpu_history_attach_host", "mcgpu_history_maxlike", "mcgpu_history_moments",
     "mcgpu_get_stats", "mcgpu_device_ptr", "mcgpu_loglik", "mcgpu_qriguess",
@@ -116,6 +119,20 @@ class DevicePtr:
         self.ptr, self.nbytes = ptr, nbytes
 
 
+def p2p_attach_local(engines):
+    """Several engines of ONE process (same or different devices) exchange peer to peer."""
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    _check(load().mcgpu_p2p_attach_local(arr, len(engines)), engines[0].h)
+    for e in engines:
+        e.p2p = True
+
+
+def burnin_group(engines, nburn):
+    """Burn-in of several sharded engines of ONE process with job-wide tuning counters."""
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    _check(load().mcgpu_burnin_group(arr, len(engines), nburn), engines[0].h)
+
+
 class Engine:
     """One GPU's share of an MCPar run.
 
@@ -139,6 +156,7 @@ class Engine:
         cfg.trace, cfg.history_steps = int(trace), history_steps
         self.cfg = cfg
         self.d, self.C, self.mode = nparam, nchain, mode
+        self.p2p = False
         self.h = C.c_void_p()
         _check(self.lib.mcgpu_create(C.byref(cfg), C.byref(self.h)))
 
@@ -219,6 +237,20 @@ class Engine:
 
     def exchange_end(self):
         self._ck(self.lib.mcgpu_exchange_end(self.h))
+
+    # -- peer-to-peer exchange (in-kernel stores over NVLink instead of an all-gather call) ----
+    def p2p_export(self):
+        """This engine's exchange-region handle (bytes) for mcgpu_p2p_attach in other processes."""
+        buf = C.create_string_buffer(P2P_HANDLE_BYTES)
+        self._ck(self.lib.mcgpu_p2p_export(self.h, buf, C.c_size_t(P2P_HANDLE_BYTES)))
+        return buf.raw
+
+    def p2p_attach(self, world, rank, handles):
+        """handles: the world exported handles in rank order (own entry is ignored)."""
+        blob = b"".join(handles)
+        assert len(blob) == world * P2P_HANDLE_BYTES
+        self._ck(self.lib.mcgpu_p2p_attach(self.h, world, rank, blob))
+        self.p2p = True
 
     def synchronize(self):
         self._ck(self.lib.mcgpu_synchronize(self.h))

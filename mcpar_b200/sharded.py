@@ -86,7 +86,16 @@ class ShardedRunner:
                 self.g.all_reduce_sum(self._cnt)
                 self.e.tune()
 
+    def enable_p2p(self, rank, world, all_gather_bytes):
+        """Switch the exchange from an all-gather call per window to in-kernel peer-to-peer stores
+        (mcgpu_p2p_*): export this engine's exchange-region handle, gather all handles in rank
+        order with `all_gather_bytes(bytes) -> [bytes]*world` (any host-side means), attach."""
+        handles = all_gather_bytes(self.e.p2p_export())
+        self.e.p2p_attach(world, rank, handles)
+
     def exchange(self):
+        if getattr(self.e, "p2p", False):   # the window kernels exchanged over NVLink themselves
+            return
         buf, off, own = self.e.exchange_begin()
         if buf.ptr not in self._views:
             self._views[buf.ptr] = self.as_tensor(buf)

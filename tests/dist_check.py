@@ -1,6 +1,7 @@
-"""Multi-process NCCL check (run under torchrun on >= 2 GPUs; tests/test_gpu_dist.py launches it):
-chains sharded one engine per rank, pool all-gathered in place and tuning counters all-reduced by
-mcpar_b200/sharded.py over NCCL, must reproduce the single-engine run bit for bit."""
+"""Multi-process check (run under torchrun on >= 2 GPUs; tests/test_gpu_dist.py launches it):
+chains sharded one engine per rank, tuning counters all-reduced over NCCL, the pool exchanged
+either by an in-place NCCL all-gather per window or by the window kernels themselves with
+peer-to-peer stores over NVLink (mcgpu_p2p_*), must reproduce the single-engine run bit for bit."""
 import os
 import sys
 import numpy as np
@@ -20,8 +21,13 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for lik, par, d, Cg, M, cg in [("dualgaussian", [5.0], 2, 4096, 16, 0), ("rosenbrock1", None, 2, 2048, 8, 32),
-                                   ("rosenbrock1", None, 16, 512, 8, 0)]:
+    def gather_bytes(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+
+    cases = [("dualgaussian", [5.0], 2, 4096, 16, 0), ("rosenbrock1", None, 2, 2048, 8, 32), ("rosenbrock1", None, 16, 512, 8, 0)]
+    for (lik, par, d, Cg, M, cg), xchg in [(c, x) for x in ("nccl", "p2p") for c in cases]:
         N, nburn, nsamp, sync, pl = Cg * world, 130, 60, 10, 0.7
         check_even_pool(Shard(rank, world, Cg), M)
         pin = tiled_pinit(N, d)
@@ -32,10 +38,13 @@ def main():
         e.set_stream(stream.cuda_stream)
         e.set_likelihood(lik, par); e.set_covariance(None); e.set_state(pin[rank * Cg:(rank + 1) * Cg])
         r = ShardedRunner(e, DistGroup(dist), lambda ptr: torch.as_tensor(ptr, device=dev))
+        if xchg == "p2p":
+            r.enable_p2p(rank, world, gather_bytes)
         r.burnin(nburn)
         r.sample(nsamp, sync)
         e.synchronize(); torch.cuda.synchronize()
         mine = e.state()["p"]; hist = e.history(); fac = e.factor()
+        dist.barrier()                                  # peers map this engine's exchange region until here
         e.close()
         gathered = [None] * world
         dist.all_gather_object(gathered, (mine, hist, fac))
@@ -45,7 +54,7 @@ def main():
             same = (np.array_equal(np.concatenate([g[0] for g in gathered]), one.state()["p"])
                     and np.array_equal(np.concatenate([g[1] for g in gathered], axis=1), one.history())
                     and all(np.array_equal(g[2], one.factor()) for g in gathered))
-            print("dist_check", lik, "d=%d" % d, "world=%d" % world, "OK" if same else "MISMATCH", flush=True)
+            print("dist_check", xchg, lik, "d=%d" % d, "world=%d" % world, "OK" if same else "MISMATCH", flush=True)
             ok = ok and same
             one.close()
     dist.barrier()

@@ -1,4 +1,4 @@
-"""NCCL path on >= 2 GPUs: launches tests/dist_check.py under torchrun (skipped on 1-GPU boxes)."""
+"""NCCL and peer-to-peer exchange on >= 2 GPUs: launches tests/dist_check.py under torchrun (skipped on 1-GPU boxes)."""
 import os
 import subprocess
 import sys
@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_sharded_nccl_equals_single_engine():
+def test_sharded_nccl_and_p2p_equal_single_engine():
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -18,4 +18,4 @@ def test_sharded_nccl_equals_single_engine():
                         "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(ROOT, "tests", "dist_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("OK") == 3 and "MISMATCH" not in r.stdout
+    assert r.stdout.count("OK") == 6 and "MISMATCH" not in r.stdout
