@@ -274,6 +274,33 @@ def main():
             r.enable_p2p(rank, world, gather_bytes)
         return r
 
+    if world > 1 and args.exchange == "p2p":
+        # probe with a throwaway engine that every rank can map every peer's exchange region (CUDA IPC +
+        # peer access); all ranks then take the same path.  Both paths are GPU paths of the engine.
+        pe, h = None, b""
+        try:
+            pe = engine.Engine(2, 64, nchain_total=64 * world, chain0=64 * rank, pool_m=world, device=local)
+            h = pe.p2p_export()
+        except engine.McgpuError as ex:
+            sys.stderr.write("rank %d: peer-to-peer export failed (%s)\n" % (rank, ex))
+        hs = gather_bytes(h)
+        ok = int(all(len(x) == engine.P2P_HANDLE_BYTES for x in hs))
+        if ok:
+            try:
+                pe.p2p_attach(world, rank, hs)
+            except engine.McgpuError as ex:
+                ok = 0
+                sys.stderr.write("rank %d: peer-to-peer attach failed (%s)\n" % (rank, ex))
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.barrier()
+        if pe is not None:
+            pe.close()
+        if int(flag.item()) == 0:
+            args.exchange = "nccl"
+            if rank == 0:
+                sys.stderr.write("peer-to-peer exchange unavailable on this box: using the NCCL all-gather exchange\n")
+
     runner = [make_runner(e)]
 
     def burn(n):
@@ -313,7 +340,11 @@ def main():
     ck = clocks.stop() if clocks else None
     ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [ms / K]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [float(x.item()) / K for x in allt]                # diagnostic: skew between GPUs
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     st = e.stats()
@@ -411,7 +442,7 @@ def main():
                                            if args.exchange == "p2p" else
                                            "chains sharded by global id; pool all-gather over NCCL each window")},
                 "clocks": ck, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "accept_rate": acc_rate, "posterior_mean": [float(x) for x in mean],
+                "per_rank_ms_per_step": per_rank_ms, "accept_rate": acc_rate, "posterior_mean": [float(x) for x in mean],
                 "posterior_var": [float(cov[i, i]) for i in range(d)]}
         print(json.dumps(line))
     if world > 1:

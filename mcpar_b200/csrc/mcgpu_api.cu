@@ -190,7 +190,7 @@ cudaError_t launch_steps_any(mcgpu_engine *e, int phase, const StepParams &p)
     w.pmh = reinterpret_cast<const double2*>(e->pprep); w.psd = e->pprep + (size_t)2 * e->d * e->mpad;
     w.pool_m = e->M; w.mpad = e->mpad; w.pool_next = p.pool_next; w.pool_stride = p.pool_stride;
     w.peers = p.peers; w.npeers = p.npeers; w.next_off = p.next_off; w.arr_off = p.arr_off;
-    w.arrivals = p.arrivals; w.wait_target = 0; w.xflag = p.xflag;   // the wide path waits in pool_prep
+    w.arrivals = p.arrivals; w.wait_target = p.wait_target; w.xflag = p.xflag;   // readers wait in pool_prep, publishers in the kernel
     w.hist = p.hist; w.thin = p.thin; w.hist_step0 = p.hist_step0;
     w.gm2 = reinterpret_cast<const double2*>(e->gm_t);
     w.gm_lw = e->gm_t ? e->gm_t + (size_t)2 * e->d * e->kpad : nullptr; w.kpad = e->kpad;
@@ -796,11 +796,15 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
         p.pool_next = publish;
         CK(launch_steps_any(e, PH_MIXED, p));
       } else {                                               // job-wide coin: runs of local / remote steps
-        if (e->wide && (e->t_main >= sync || p.wait_target)) {   // (mu, sig^2) pool -> (mu, -1/2sig^2, sig), slot-fastest
-          ++e->launches;                                          // (with a peer-to-peer exchange it also waits for the arrivals)
-          CK(fast::launch_pool_prep(pool_cur(e), e->M, e->mpad, e->d, reinterpret_cast<double2*>(e->pprep),
-                                    e->pprep + (size_t)2 * e->d * e->mpad, p.arrivals, p.wait_target, p.xflag, e->stream));
-        }
+        // wide kernels read the pool as (mu, -1/2sig^2, sig), slot-fastest: prepared right before the window's
+        // first remote launch (with a peer-to-peer exchange that kernel also waits for the arrivals, so the
+        // window's leading local steps overlap the exchange)
+        bool prepped = !e->wide;
+        auto pool_prep = [&]() -> cudaError_t {
+          prepped = true; ++e->launches;
+          return fast::launch_pool_prep(pool_cur(e), e->M, e->mpad, e->d, reinterpret_cast<double2*>(e->pprep),
+                                        e->pprep + (size_t)2 * e->d * e->mpad, p.arrivals, p.wait_target, p.xflag, e->stream);
+        };
         auto is_remote = [&](long long tt) {
           return tt >= sync && !(host_coin(e, (uint32_t)(e->nburn_total + tt)) <= e->cfg.pl);   // mcpar.cc:142-152
         };
@@ -823,6 +827,7 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
             while (k + len < n && is_remote(t + len) == rem) ++len;
             p.step0 = (uint32_t)(e->nburn_total + t); p.nsteps = len; p.t0 = (int)t;
             p.pool_next = (k + len == n) ? publish : nullptr;
+            if (rem && !prepped) CK(pool_prep());
             CK(launch_steps_any(e, rem ? PH_REMOTE : PH_LOCAL, p));
             k += len;
           }

@@ -156,18 +156,21 @@ __device__ __forceinline__ unsigned long long global_ns()
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// the calling thread waits (bounded as below) for the arrivals
+__device__ __forceinline__ void wait_arrivals_thread(const unsigned long long *arrivals, unsigned long long target, int *xflag)
+{
+  if (!target || ld_acquire_sys(arrivals) >= target) return;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(arrivals) < target) {
+    if (global_ns() - t0 > 10000000000ull) { atomicExch(xflag, 1); break; }
+    __nanosleep(100);
+  }
+}
 // one thread per CTA waits (bounded: 10 s, then the engine reports MCGPU_EPEER) until all pool slots of
 // the exchange have arrived in this GPU's memory; callers follow with __syncthreads()
 __device__ __forceinline__ void wait_arrivals(const unsigned long long *arrivals, unsigned long long target, int *xflag)
 {
-  if (threadIdx.x == 0 && target) {
-    if (ld_acquire_sys(arrivals) >= target) return;
-    const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(arrivals) < target) {
-      if (global_ns() - t0 > 10000000000ull) { atomicExch(xflag, 1); break; }
-      __nanosleep(100);
-    }
-  }
+  if (threadIdx.x == 0) wait_arrivals_thread(arrivals, target, xflag);
 }
 
 }  // namespace mcgpu

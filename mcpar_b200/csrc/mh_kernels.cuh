@@ -294,20 +294,12 @@ mh_steps_kernel(const StepParams p)
   const int leader = lane & ~(p.coin_group - 1);
 
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) sT[i] = p.factor[i];
-  if (MAIN) {
-    // peer-to-peer exchange: every main-phase launch (also a purely local one) waits until the pool it is
-    // entitled to read has arrived from all GPUs -- that also keeps any GPU from running more than one
-    // publication ahead of its peers (three pool buffers, mcgpu_api.cu)
-    if (p.wait_target) { wait_arrivals(p.arrivals, p.wait_target, p.xflag); __syncthreads(); }
+  if (MAIN)
     for (int k = threadIdx.x; k < p.nsteps; k += blockDim.x) sW[k] = 1.0 / (double)(p.t0 + k + 1);
-    if (CAN_REMOTE && p.t0 + p.nsteps > p.sync)
-      for (int i = threadIdx.x; i < Mpad * D; i += blockDim.x) {
-        if (i < p.pool_m * D) {
-          const double s2 = p.pool_cur[i * 2 + 1];
-          sPmh[i] = make_double2(p.pool_cur[i * 2], -0.5 / s2); sPs[i] = sqrt(s2);   // sigma = sqrt(sig^2), mcpar.cc:346
-        } else sPmh[i] = make_double2(1.0e300, -1.0);   // padding: (mu - x)^2 overflows, a = -inf, Q = 0
-      }
-  }
+  // The exchange pool is staged into shared memory right before the first step that reads it.  With a
+  // host-drawn plan (job-wide coin) that is the window's first remote step; with a peer-to-peer exchange
+  // the wait for the peers' publications sits there too, so the window's leading local steps overlap the
+  // exchange and absorb the skew between GPUs.  Without a plan the pool is staged before step 0.
   __syncthreads();
 
   double x[D], mu[D], ps[D];
@@ -323,6 +315,21 @@ mh_steps_kernel(const StepParams p)
   long long tkeep = MAIN ? (long long)(p.t0 / p.thin) - p.hist_step0 : 0;
 
   for (int k = 0; k < p.nsteps; ++k) {
+    if constexpr (CAN_REMOTE) {
+      bool stage_now;                                  // launch-uniform, from constant-bank operands only
+      if (PHASE == PH_MIXED && p.plan_valid) stage_now = ((p.plan_mask >> k) & 1u) && (p.plan_mask & ((1u << k) - 1u)) == 0u;
+      else stage_now = k == 0 && p.t0 + p.nsteps > p.sync;
+      if (stage_now) {
+        if (p.wait_target) { wait_arrivals(p.arrivals, p.wait_target, p.xflag); __syncthreads(); }
+        for (int i = threadIdx.x; i < Mpad * D; i += blockDim.x) {
+          if (i < p.pool_m * D) {
+            const double s2 = p.pool_cur[i * 2 + 1];
+            sPmh[i] = make_double2(p.pool_cur[i * 2], -0.5 / s2); sPs[i] = sqrt(s2);   // sigma = sqrt(sig^2), mcpar.cc:346
+          } else sPmh[i] = make_double2(1.0e300, -1.0);   // padding: (mu - x)^2 overflows, a = -inf, Q = 0
+        }
+        __syncthreads();
+      }
+    }
     const uint32_t step = p.step0 + (uint32_t)k;
     const int t = p.t0 + k;
     double u_acc;
@@ -532,6 +539,9 @@ mh_steps_kernel(const StepParams p)
         const long long s = gg / p.pool_stride;
         const double winv = 1.0 / (double)(p.t0 + p.nsteps);
         if (p.npeers > 0) {                            // sharded: store into every GPU's next pool over NVLink
+          // A GPU may not publish P+1 before all of P has reached it: its peers' last CTAs of the
+          // previous window may still read pool P-1, which P+2 will overwrite (three buffers).
+          wait_arrivals_thread(p.arrivals, p.wait_target, p.xflag);
           for (int r = 0; r < p.npeers; ++r) {
             double *dst = reinterpret_cast<double *>(p.peers[r] + p.next_off);
 #pragma unroll

@@ -384,6 +384,7 @@ mh_wide_kernel(const WideParams p)
           const long long s = gg / p.pool_stride;
           const double wi = 1.0 / (double)(p.t0 + p.nsteps);
           if (p.npeers > 0) {                          // sharded: store into every GPU's next pool over NVLink
+            wait_arrivals_thread(p.arrivals, p.wait_target, p.xflag);   // never more than one publication ahead (mh_kernels.cuh)
             for (int q = 0; q < p.npeers; ++q) {
               double *dst = reinterpret_cast<double *>(p.peers[q] + p.next_off);
               dst[(s * D + i0) * 2] = mu0[c];     dst[(s * D + i0) * 2 + 1] = ps0[c] * wi;
