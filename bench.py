@@ -417,12 +417,25 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
         except Exception:
             pass
-        ach = per_gpu * W["F_hw"] / 1e12
+        # a remote step adds (iterations + 1) x M x (3d + 1 flops + 1 exp [= 30]) per chain on top
+        # of the local-step figure F_hw; the remote fraction and the iterations are counted by the kernels
+        Mpool = args.pool if 0 < args.pool < N else N
+        f_rem = st["remote_steps"] / max(1, st["tried"])
+        iters = st["remote_iterations"] / max(1, st["remote_steps"])
+        F_rem = (iters + 1.0) * Mpool * (3 * d + 1 + 30.0)
+        F_tot = W["F_hw"] + f_rem * F_rem
+        ach = per_gpu * F_tot / 1e12
+        ach_local = per_gpu * W["F_hw"] / 1e12
         roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
                 "traffic": traffic,
-                "note": "achieved = chain-steps/s/GPU x F_hw (%g hardware-equivalent fp64 flops per chain-step, SURVEY.md 8d); "
+                "flops_per_chain_step": F_tot, "remote_fraction": f_rem, "remote_iterations_mean": iters,
+                "achieved_local_work_only": ach_local, "frac_local_work_only": ach_local / peak if peak else None,
+                "note": "achieved = chain-steps/s/GPU x algorithmic fp64 work per chain-step (SURVEY.md 8d, hardware-equivalent "
+                        "weights): F_hw = %g for the local step + remote_fraction x (iterations+1) x M x (3d+1 flops + exp=30) "
+                        "for the Murray rejection loop, fraction and iterations counted by the kernels in this run; "
+                        "frac_local_work_only ignores the remote loop's work (the round-1 figure); "
                         "peak = DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no fp64 figure); "
-                        "kernel time = CUDA events around each window launch" % W["F_hw"],
+                        "kernel time = CUDA events around each window launch; ncu pipe utilisation: profiles/README.md" % W["F_hw"],
                 "achieved_textbook_tflops": per_gpu * W["F_alg"] / 1e12,
                 "hbm": {"achieved": per_gpu * bytes_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": per_gpu * bytes_step / 1e9 / hbm_peak, "bytes_per_chain_step": bytes_step,

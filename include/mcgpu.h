@@ -90,8 +90,11 @@ typedef struct mcgpu_stats {
   int64_t burn_steps, main_steps;       /* steps taken so far                        */
   int64_t accepted, tried;              /* main phase, all hosted chains             */
   int64_t kernel_launches;              /* engine kernels launched since create      */
-  int64_t remote_steps;                 /* VERIFY: rank-steps that took the remote branch */
-  int64_t remote_iterations;            /* VERIFY: lock-step rejection iterations    */
+  int64_t remote_steps;                 /* VERIFY: rank-steps that took the remote branch;
+                                           NORMAL: chain-steps of the main phase that did   */
+  int64_t remote_iterations;            /* VERIFY: lock-step rejection iterations;
+                                           NORMAL: candidates tried by those chain-steps
+                                           (iterations of the loop mcpar.cc:331-409)        */
   int64_t history_rows;                 /* rows currently stored (kept steps * chains) */
   double  device_ms;                    /* CUDA-event time of burnin+sample calls    */
 } mcgpu_stats;

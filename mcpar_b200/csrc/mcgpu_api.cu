@@ -42,7 +42,7 @@ struct mcgpu_engine {
   // NORMAL / REPLAY_LOCAL state (SoA) or VERIFY state (AoS per rank)
   double *x = nullptr, *ly = nullptr, *mu = nullptr, *ps = nullptr;
   double *factor = nullptr;
-  unsigned long long *counts = nullptr;   // [0,1] window, [2,3] cumulative, [4,5] main-phase stats
+  unsigned long long *counts = nullptr;   // [0,1] window, [2,3] cumulative, [4,5] main-phase stats, [6,7] remote chain-steps / candidate iterations
   // exchange region (one allocation, IPC-exportable): 3 pool buffers [M][d][2] + the arrival counter
   char *xchg = nullptr; size_t pool_bytes = 0, xchg_bytes = 0;
   double *pool[3] = {nullptr, nullptr, nullptr}; int M = 0; long long stride = 1; bool pool_in_smem = true;
@@ -171,9 +171,12 @@ void fill_step_params(mcgpu_engine *e, StepParams &p)
   p.C = e->C; p.ld = e->ld; p.chain0 = e->cfg.chain0;
   p.factor = e->factor;
   p.key0 = (uint32_t)e->cfg.seed; p.key1 = (uint32_t)(e->cfg.seed >> 32);
+  for (int r = 0; r < 10; ++r) { p.rk[2 * r] = p.key0 + (uint32_t)r * 0x9E3779B9u; p.rk[2 * r + 1] = p.key1 + (uint32_t)r * 0xBB67AE85u; }
   p.sync = e->cfg.sync; p.coin_group = e->cfg.coin_group; p.pl = e->cfg.pl;
   p.pool_m = e->M; p.pool_stride = e->stride; p.pool_in_smem = e->pool_in_smem;
   p.thin = e->cfg.thin;
+  static const int exact_tests = getenv("MCGPU_EXACT_TESTS") ? atoi(getenv("MCGPU_EXACT_TESTS")) : 0;
+  p.exact_tests = exact_tests;
   p.Z = e->Zd; p.U = e->Ud; p.nz = e->nz; p.nu = e->nu; p.overrun = e->overrun;
   memcpy(p.lp, e->lp, sizeof p.lp); p.lik_dev = e->lik_dev; p.lik_k = e->lik_k;
   p.nburn_total = e->nburn_total;
@@ -186,7 +189,7 @@ cudaError_t launch_steps_any(mcgpu_engine *e, int phase, const StepParams &p)
     WideParams w; memset(&w, 0, sizeof w);
     w.x = p.x; w.ly = p.ly; w.mu = p.mu; w.ps = p.ps; w.C = p.C; w.chain0 = p.chain0;
     w.factor_cm = e->factor_cm; w.factor_rm = e->factor; w.diagonal = e->diag_d; w.counts = p.counts;
-    w.key0 = p.key0; w.key1 = p.key1; w.step0 = p.step0; w.nsteps = p.nsteps; w.t0 = p.t0;
+    w.key0 = p.key0; w.key1 = p.key1; memcpy(w.rk, p.rk, sizeof w.rk); w.step0 = p.step0; w.nsteps = p.nsteps; w.t0 = p.t0;
     w.pmh = reinterpret_cast<const double2*>(e->pprep); w.psd = e->pprep + (size_t)2 * e->d * e->mpad;
     w.pool_m = e->M; w.mpad = e->mpad; w.pool_next = p.pool_next; w.pool_stride = p.pool_stride;
     w.peers = p.peers; w.npeers = p.npeers; w.next_off = p.next_off; w.arr_off = p.arr_off;
@@ -466,7 +469,7 @@ int mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out)
     e->pool_in_smem = true;
     TRY(dalloc(e, &e->x, (size_t)d * e->ld)); TRY(dalloc(e, &e->ly, (size_t)e->ld));
     TRY(dalloc(e, &e->mu, (size_t)d * e->ld)); TRY(dalloc(e, &e->ps, (size_t)d * e->ld));
-    TRY(dalloc(e, &e->factor, (size_t)d * d)); TRY(dalloc(e, &e->counts, 6));
+    TRY(dalloc(e, &e->factor, (size_t)d * d)); TRY(dalloc(e, &e->counts, 8));
     e->pool_bytes = ((size_t)e->M * d * 16 + 255) / 256 * 256;
     e->xchg_bytes = 3 * e->pool_bytes + 256;
     TRY(dalloc(e, &e->xchg, e->xchg_bytes));
@@ -757,7 +760,7 @@ int mcgpu_sample_begin(mcgpu_engine *e, int nsamp)
   std::vector<double> eps(n, MCGPU_FPEPS);
   CK(cudaMemsetAsync(e->mu, 0, n * 8, e->stream));
   CK(cudaMemcpyAsync(e->ps, eps.data(), n * 8, cudaMemcpyHostToDevice, e->stream));
-  if (!e->verify) CK(cudaMemsetAsync(e->counts + 4, 0, 16, e->stream));
+  if (!e->verify) CK(cudaMemsetAsync(e->counts + 4, 0, 32, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return MCGPU_OK;
 }
@@ -1243,14 +1246,15 @@ int mcgpu_get_stats(mcgpu_engine *e, mcgpu_stats *out)
   memset(out, 0, sizeof *out);
   out->burn_steps = e->burn_done; out->main_steps = e->t_main; out->kernel_launches = e->launches;
   out->history_rows = e->hist_kept * e->C; out->device_ms = e->ms_accum;
-  unsigned long long h[6] = {0};
+  unsigned long long h[8] = {0};
   if (e->verify) {
     CK(cudaMemcpy(h, e->rstats, 32, cudaMemcpyDeviceToHost));
     out->remote_steps = (int64_t)h[0]; out->remote_iterations = (int64_t)h[1];
     out->accepted = (int64_t)h[2]; out->tried = (int64_t)h[3];
   } else {
-    CK(cudaMemcpy(h, e->counts, 48, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h, e->counts, 64, cudaMemcpyDeviceToHost));
     out->accepted = (int64_t)h[4]; out->tried = (int64_t)h[5];
+    out->remote_steps = (int64_t)h[6]; out->remote_iterations = (int64_t)h[7];
   }
   return MCGPU_OK;
 }

@@ -36,6 +36,23 @@ __device__ __forceinline__ Words philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return w;
 }
 
+// The same with the 10 round keys precomputed by the host (rk[2r] = k0 + r*W0, rk[2r+1] = k1 + r*W1): the
+// kernels pass the copy in their launch parameters, so every round key is a constant-bank operand of the
+// LOP3 and the per-round key additions (two issue slots each round) disappear.
+__device__ __forceinline__ Words philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20])
+{
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+  }
+  Words w; w.w0 = c0; w.w1 = c1; w.w2 = c2; w.w3 = c3;
+  return w;
+}
+
 // ---- draws ------------------------------------------------------------------------------
 // Every draw is ONE 32-bit Philox word (the reference's MKL streams deliver float32, i.e.
 // 24-bit, variates).  Words are addressed as a stream: word idx of (chain, step, base) is
@@ -69,6 +86,7 @@ struct StepParams {
   unsigned long long *counts;      // {accepted, tried} of the current tuning / stats window
   // schedule
   uint32_t key0, key1;             // Philox key = seed
+  uint32_t rk[20];                 // its 10 round keys (philox4x32_10_rk)
   uint32_t step0;                  // global step index of the first step of this launch
   int nsteps;                      // steps in this launch
   int t0;                          // main-phase index of the first step (main kernels)
@@ -85,6 +103,7 @@ struct StepParams {
   const unsigned long long *arrivals; unsigned long long wait_target; int *xflag;
   int pool_m; long long pool_stride;
   int pool_in_smem;
+  int exact_tests;                 // audit mode: accept / rejection tests always in fp64 (MCGPU_EXACT_TESTS=1)
   // sample history: rows (p..., logL), kept step major, then hosted chain
   double *hist; int thin; long long hist_step0;   // kept-step index base of the history buffer
   // replay-local streams
@@ -103,6 +122,7 @@ struct WideParams {
   const int *diagonal;            // device flag: factor has no off-diagonal entries
   unsigned long long *counts;
   uint32_t key0, key1, step0;
+  uint32_t rk[20];                 // Philox round keys (philox4x32_10_rk)
   int nsteps, t0;
   // remote pool, prepared, slot fastest: pmh [D][Mpad] = (mu, -1/(2 sig^2)) pairs, psd [D][Mpad] = sigma
   const double2 *pmh; const double *psd; int pool_m, mpad;

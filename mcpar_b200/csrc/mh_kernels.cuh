@@ -35,6 +35,9 @@ namespace mcgpu {
 namespace MCGPU_NS {
 
 enum { RNG_PHILOX = 0, RNG_REPLAY = 1 };
+#ifndef MCGPU_EXP_NOCOUNT
+#define MCGPU_EXP_NOCOUNT 0
+#endif
 
 // transcendental calls of the step kernels: table-driven routines in the production
 // unit, CUDA libm in the exact (verification) unit
@@ -132,11 +135,14 @@ __device__ __noinline__ Words philox_call(uint32_t c0, uint32_t c1, uint32_t c2,
 {
   return philox4x32_10(c0, c1, c2, c3, k0, k1);
 }
-template <int D>
-__device__ __forceinline__ Words philox_d(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+// RK: take the precomputed round keys from the launch parameters (the lean local / burn-in kernels; in
+// the two-path kernels, at their register cap, the in-line key schedule compiles without spills)
+template <int D, bool RK>
+__device__ __forceinline__ Words philox_d(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const StepParams &p)
 {
-  if (D <= 4) return philox4x32_10(c0, c1, c2, c3, k0, k1);
-  return philox_call(c0, c1, c2, c3, k0, k1);
+  if (D <= 4 && RK) return philox4x32_10_rk(c0, c1, c2, c3, p.rk);
+  if (D <= 4) return philox4x32_10(c0, c1, c2, c3, p.key0, p.key1);
+  return philox_call(c0, c1, c2, c3, p.key0, p.key1);
 }
 
 // proposal factor entry from shared memory.  At d > 4 the read is volatile: the d(d+1)/2
@@ -160,11 +166,12 @@ __device__ __forceinline__ float ex2_approx(float x)
 // The accept test  u < exp(delta) * cfac  (mcpar.cc:67-69 / :167-169).  Only the
 // decision is needed, so it is settled by rigorous fp32 bounds on exp(delta) and
 // computed exactly (fp64 exp) only when u falls between the bounds (~1e-4 of cases).
-__device__ __forceinline__ bool accept_test(double u, double delta, double cfac, const MathTables &T)
+__device__ __forceinline__ bool accept_test(double u, double delta, double cfac, const MathTables &T, int exact_tests)
 {
 #ifdef MCGPU_EXACT_TU
   return u < exp(delta) * cfac;
 #else
+  if (exact_tests) return u < mc_exp(delta, T) * cfac;   // audit mode (MCGPU_EXACT_TESTS): no fp32 short cut
   const float dc = fminf(fmaxf((float)delta, -80.0f), 80.0f);
   const double e = (double)ex2_approx(dc * 1.4426950408889634f);
   const double lo = (delta >= -80.0) ? e * cfac * (1.0 - 1.0e-4) : 0.0;   // valid lower bound (clamped above 80)
@@ -175,11 +182,27 @@ __device__ __forceinline__ bool accept_test(double u, double delta, double cfac,
 #endif
 }
 
-// exact rejection test pacpt = qimax / qisum (mcpar.cc:355-398) in fp64; out of line: it runs
-// for ~1e-4 of the candidates and must not bloat the hot loop's instruction footprint
+// One candidate of the remote rejection loop, exactly: draws (component pick, uniform, normals) from the
+// candidate's Philox blocks, x' = mu_c + sigma_c z and pacpt = qimax / qisum (mcpar.cc:337-398), all in
+// fp64.  Out of line: it runs for ~1e-3 of the candidates and must not bloat the hot loop.
 template <int D>
-__device__ __noinline__ bool remote_exact(const double2 *sPmh, int M, const double (&xc)[D], double u, const MathTables &T)
+__device__ __noinline__ bool remote_exact(uint32_t tlo, uint32_t thi, uint32_t step, uint32_t slot, uint32_t k0, uint32_t k1,
+                                          const double2 *sPmh, const double *sPs, int M, const MathTables &T)
 {
+  constexpr int NP = (D + 1) / 2;
+  Words blk = philox4x32_10(tlo, thi, step, slot, k0, k1);
+  const int c = (int)__umulhi(blk.w0, (uint32_t)M);
+  const double u = u32_mid(blk.w1);
+  double xc[D];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    const int qq = q + 1;
+    if ((qq & 1) == 0) blk = philox4x32_10(tlo, thi, step, slot + (uint32_t)(qq >> 1), k0, k1);
+    double za, zb;
+    normal_pair_t((qq & 1) ? blk.w2 : blk.w0, (qq & 1) ? blk.w3 : blk.w1, za, zb, T);
+    xc[2 * q] = sPmh[c * D + 2 * q].x + sPs[c * D + 2 * q] * za;
+    if (2 * q + 1 < D) xc[2 * q + 1] = sPmh[c * D + 2 * q + 1].x + sPs[c * D + 2 * q + 1] * zb;
+  }
   double qmax = MCGPU_FPEPS, qsum = MCGPU_FPEPS;
   for (int s = 0; s < M; ++s) {
     double a = 0.0;
@@ -198,49 +221,107 @@ __constant__ unsigned c_stride_mask[33] = {0u,
   0x00020001u, 0x00040001u, 0x00080001u, 0x00100001u, 0x00200001u, 0x00400001u, 0x00800001u, 0x01000001u,
   0x02000001u, 0x04000001u, 0x08000001u, 0x10000001u, 0x20000001u, 0x40000001u, 0x80000001u, 0x00000001u};
 
-// The rejection test of genRemote (mcpar.cc:355-406) for one candidate x' (xc):
-// decide  u < max_s Q_s(x') / sum_s Q_s(x')  over the pool.  Pool arrays in shared memory:
-// sPmh = (mu, -1/(2 sigma^2)) pairs, padded to a multiple of 8 slots whose Q is 0.  The sum is
-// bounded in fp32 (SFU exp2, chunks of 8 for ILP, one rescale per chunk); the max is exact
-// fp64; the exact fp64 sum is evaluated only if the bounds do not settle u.
-template <int D>
-__device__ __forceinline__ bool pool_test(const double2 *sPmh, int M, const double (&xc)[D], double u,
-                                          double &amax, const MathTables &T)
+// SFU approximations (fp32).  Documented error bounds used below, each with a margin of 3x or more:
+// lg2.approx |err| <= 2^-22 absolute on [0.5, 2] (2 ulp elsewhere); sin/cos.approx |err| <= 2^-20.9 on
+// [-pi, pi]; sqrt.approx and ex2.approx 2 ulp.
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sin_approx(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cos_approx(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// fp32 image of the Box-Muller pair of normal_pair_t (same words, same convention).  Returns a bound on
+// the absolute error of both normals:
+//   L = -2 ln v:  |dL| <= 1.39 dlg2 + 2.4e-7 (1 + L) <= 1.6e-6, with dlg2 = 1e-6 (4x the documented bound);
+//   r = sqrt L:   |dr| <= dL / (r~ + r) + 2e-7 r, and never more than sqrt(dL) = 1.3e-3;
+//   angle 2 pi (a - 1/2), |a - 1/2| <= 1/2: argument error <= 8e-7, sin/cos error <= 2e-6 (the
+//   approximation's 5.1e-7 tripled, plus the argument's);  z = r trig:  |dz| <= dr + r (2e-6 + 1.2e-7)
+//   <= 1.7e-6 / (r~ + 1.3e-3) + 2.4e-6 r~   (r~ >= 1.3e-3 or not).
+__device__ __forceinline__ float normal_pair_f32(uint32_t wa, uint32_t wb, float &z0, float &z1)
+{
+  const float v = ((float)wa + 1.0f) * 2.3283064365386963e-10f;                 // (0, 1]
+  const float r = sqrt_approx(-1.3862943611198906f * lg2_approx(v));
+  const float ang = 6.283185307179586f * ((float)wb * 2.3283064365386963e-10f - 0.5f);   // 2 pi u - pi in [-pi, pi]
+  z0 = -r * sin_approx(ang); z1 = -r * cos_approx(ang);                         // sin(t + pi) = -sin t, cos(t + pi) = -cos t
+  return fmaf(2.4e-6f, r, __fdividef(1.7e-6f, r + 1.3e-3f));
+}
+
+// One candidate of the remote rejection loop (genRemote, mcpar.cc:331-409), decision only: draw the
+// component c, the uniform u and the normals z from the candidate's Philox blocks, form
+// x' = mu_c + sigma_c z and decide  u < max_s Q_s(x') / sum_s Q_s(x')  over the pool.  Rejected candidates
+// leave no trace and the accepted one is re-materialised in fp64 by its chain afterwards, so everything
+// here runs in fp32 on an fp32 copy of the pool -- sPf = (mu, -log2(e)/(2 sigma^2)) pairs, sSf = sigma,
+// padded to a multiple of 8 slots whose Q is 0; SFU log2/sqrt/sin/cos/exp2; chunks of 8 slots for ILP with
+// one rescale per chunk -- under a rigorous bound on the relative error of
+//     R = sum_s exp(a_s - max a),   a_s = -sum_i (mu_si - x'_i)^2 / (2 sigma_si^2);
+// when the bound does not settle u the candidate is redone exactly in fp64 (remote_exact).
+// Error bound.  mu_s - x' is off by at most delta = zerr sigma_c,max (normals, normal_pair_f32) + 3 u24 (|mu|max + |x'|)
+// (roundings of mu_c, sigma_c, the fma and mu_s), u24 = 2^-24.  A term with |a_s| <= A then moves by at
+// most sqrt(2 A D) theta + (6 + D) u24 A, theta = delta / sigma_min.  Terms that matter have A <= 35 (the
+// bound is only used when max a > -10; terms 25 below the max contribute < 1.4e-11 each, and their own
+// error cannot lift them: sqrt(|a|) theta << |a| - 35).  Both a_s and the max move, so every term of R is
+// right to a factor exp(+-2 (8.4 sqrt(D) theta + (6 + D) 2.1e-6)); exp2.approx and the fp32 sum add
+// < 1e-6 M.  eps below covers all of it with margin.  theta >= 2e-3 (components far tighter than others or
+// than their distance from the origin: e.g. the first window, where sigma ~ 1e-7) goes to the exact test.
+// tests/test_gpu_audit.py checks the decisions against an all-fp64 run of the same kernels.
+template <int D, bool RK>
+__device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uint32_t step, uint32_t slot, const StepParams &p,
+                                                 const float2 *sPf, const float *sSf, const double2 *sPmh, const double *sPs,
+                                                 float mu_max, float isig_max, const MathTables &T)
 {
   constexpr int CH = 8;
-  constexpr float L2E = 1.4426950408889634f;
-  const int Mpad = (M + CH - 1) & ~(CH - 1);
-  double m = -INFINITY;                                // running max of a_s = log Q_s(x')
-  float S = 0.0f;                                      // sum_s exp(a_s - m), fp32
+  constexpr int NP = (D + 1) / 2;
+  const int M = p.pool_m, Mpad = (M + CH - 1) & ~(CH - 1);
+  Words blk = philox_d<D, RK>(tlo, thi, step, slot, p);
+  const int c = (int)__umulhi(blk.w0, (uint32_t)M);                 // viRngUniform(0, tchains), mcpar.cc:337
+  const double u = u32_mid(blk.w1);                                 // vsRngUniform, mcpar.cc:401
+  float xf[D], xabs = 0.0f, sgmax = 0.0f, zerr = 0.0f;
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {                                    // pair q = words (2+2q, 3+2q) of the candidate's stream
+    const int qq = q + 1;
+    if ((qq & 1) == 0) blk = philox_d<D, RK>(tlo, thi, step, slot + (uint32_t)(qq >> 1), p);
+    float za, zb;
+    zerr = fmaxf(zerr, normal_pair_f32((qq & 1) ? blk.w2 : blk.w0, (qq & 1) ? blk.w3 : blk.w1, za, zb));
+    {
+      const int i = 2 * q; const float sg = sSf[c * D + i];
+      xf[i] = fmaf(sg, za, sPf[c * D + i].x);                       // DIAGONAL storage, :348-350
+      xabs = fmaxf(xabs, fabsf(xf[i])); sgmax = fmaxf(sgmax, sg);
+    }
+    if (2 * q + 1 < D) {
+      const int i = 2 * q + 1; const float sg = sSf[c * D + i];
+      xf[i] = fmaf(sg, zb, sPf[c * D + i].x);
+      xabs = fmaxf(xabs, fabsf(xf[i])); sgmax = fmaxf(sgmax, sg);
+    }
+  }
+  const float theta = (1.9e-7f * (mu_max + xabs) + zerr * sgmax) * isig_max;
+  float m = -INFINITY;                                 // running max of a_s * log2(e)
+  float S = 0.0f;                                      // sum_s 2^(a_s - m)
   for (int s0 = 0; s0 < Mpad; s0 += CH) {
-    double a[CH];
+    float a[CH];
 #pragma unroll
     for (int q = 0; q < CH; ++q) {
-      double acc = 0.0;
+      float acc = 0.0f;
 #pragma unroll
-      for (int i = 0; i < D; ++i) { const double2 mh = sPmh[(s0 + q) * D + i]; const double xm = mh.x - xc[i]; acc += xm * xm * mh.y; }
+      for (int i = 0; i < D; ++i) { const float2 f = sPf[(s0 + q) * D + i]; const float xm = f.x - xf[i]; acc = fmaf(xm * xm, f.y, acc); }
       a[q] = acc;
     }
-    double mc = a[0];
+    float mc = a[0];
 #pragma unroll
-    for (int q = 1; q < CH; ++q) mc = a[q] > mc ? a[q] : mc;
-    const float mcf = (float)mc;
+    for (int q = 1; q < CH; ++q) mc = fmaxf(mc, a[q]);
     float sc = 0.0f;
 #pragma unroll
-    for (int q = 0; q < CH; ++q) sc += ex2_approx(((float)a[q] - mcf) * L2E);     // exp(a_q - mc), each <= 1
+    for (int q = 0; q < CH; ++q) sc += ex2_approx(a[q] - mc);                     // each <= 1
     const bool gt = mc > m;
-    const float e = ex2_approx(-fabsf((float)(m - mc)) * L2E);                    // exp(-|m - mc|); 0 on the first chunk
+    const float e = ex2_approx(-fabsf(m - mc));                                   // 0 on the first chunk
     S = gt ? fmaf(S, e, sc) : fmaf(sc, e, S);
     m = gt ? mc : m;
   }
-  amax = m;
-  if (m > -10.0) {                                     // then FPEPS/qmax < 2.3e-10 (mcpar.cc:357-358 offsets)
-    const double eps = 1.0e-4 + 2.0e-5 * (double)M;
+  if (m > -14.0f && theta < 2.0e-3f && !p.exact_tests) {   // max a > -9.7: then FPEPS/qmax < 2e-10 (mcpar.cc:357-358 offsets)
+    const double eps = 1.0e-4 + 1.0e-5 * (double)D + 2.0e-5 * (double)M + (double)(theta * (21.3f * sqrtf((float)D)));
     const double Sd = (double)S;
     if (u * (Sd * (1.0 + eps) + 3.0e-10) < 1.0) return true;      // u < r_lo
     if (u * (Sd * (1.0 - eps)) >= 1.0) return false;              // u >= r_hi
   }
-  return remote_exact<D>(sPmh, M, xc, u, T);            // rare: the fp32 bounds straddle u
+  return remote_exact<D>(tlo, thi, step, slot, p.key0, p.key1, sPmh, sPs, M, T);   // rare: the bounds straddle u (also the NaN path)
 }
 
 #ifndef MCGPU_MINB_LOCAL
@@ -261,6 +342,39 @@ __device__ __forceinline__ bool pool_test(const double2 *sPmh, int M, const doub
 // PH_REMOTE kernels instead of the mixed one.
 enum { PH_BURN = 0, PH_MIXED = 1, PH_LOCAL = 2, PH_REMOTE = 3 };
 
+// Stage the exchange pool [M][D][2] (mu, sigma^2) into shared memory as (mu, -1/(2 sigma^2)) pairs + sigma.
+// With a peer-to-peer exchange the CTA first waits until the pool has arrived from every GPU.  Out of
+// line: it runs once per launch from inside the step loop, whose register allocation it must not disturb.
+#ifndef MCGPU_STAGE_QUAL
+#define MCGPU_STAGE_QUAL __noinline__
+#endif
+template <int D>
+__device__ MCGPU_STAGE_QUAL void stage_pool(const double *pool_cur, int pool_m, const unsigned long long *arrivals,
+                                        unsigned long long wait_target, int *xflag, double2 *sPmh, double *sPs,
+                                        float2 *sPf, float *sSf, float *s_scal, int Mpad)
+{
+  if (wait_target) wait_arrivals(arrivals, wait_target, xflag);
+  if (threadIdx.x < 2) s_scal[threadIdx.x] = 0.0f;
+  __syncthreads();
+  float mumax = 0.0f, isig = 0.0f;
+  for (int i = threadIdx.x; i < Mpad * D; i += blockDim.x) {
+    if (i < pool_m * D) {
+      const double m = pool_cur[i * 2], s2 = pool_cur[i * 2 + 1];
+      const double h = -0.5 / s2, sd = sqrt(s2);       // sigma = sqrt(sig^2), mcpar.cc:346
+      sPmh[i] = make_double2(m, h); sPs[i] = sd;
+      sPf[i] = make_float2((float)m, (float)(h * 1.4426950408889634)); sSf[i] = (float)sd;
+      mumax = fmaxf(mumax, __double2float_ru(fabs(m))); isig = fmaxf(isig, __double2float_ru(1.0 / sd));
+    } else {                                           // padding: (mu - x)^2 overflows / is huge, a = -inf, Q = 0
+      sPmh[i] = make_double2(1.0e300, -1.0); sPf[i] = make_float2(1.0e18f, -1.0f); sSf[i] = 0.0f;
+    }
+  }
+  // max over the CTA (non-negative floats order like their bit patterns; NaN/inf sort above every
+  // number, which makes theta fail its test and sends every candidate to the exact path)
+  atomicMax(reinterpret_cast<int *>(&s_scal[0]), __float_as_int(mumax));
+  atomicMax(reinterpret_cast<int *>(&s_scal[1]), __float_as_int(isig));
+  __syncthreads();
+}
+
 template <int LIK, int D, int RNGK, int PHASE>
 __global__ void __launch_bounds__(128, (D <= 2 ? ((PHASE == PH_BURN || PHASE == PH_LOCAL) ? MCGPU_MINB_LOCAL : MCGPU_MINB) : 1))
 mh_steps_kernel(const StepParams p)
@@ -269,12 +383,17 @@ mh_steps_kernel(const StepParams p)
   constexpr bool CAN_REMOTE = RNGK == RNG_PHILOX && (PHASE == PH_MIXED || PHASE == PH_REMOTE);
   extern __shared__ double smem[];
   __shared__ unsigned char s_rank[4][32];               // per warp: lanes of the chains still in the remote loop
+  __shared__ unsigned int s_stat[2];                    // remote chain-steps of this CTA and the candidates they tried
+  __shared__ unsigned int s_itacc[128];                 // per chain: index of the accepted candidate of the current remote step
   // smem: math tables | [D*D] factor | [nsteps] 1/pwgt table | pool: mu, -1/(2 sig^2), sigma
   double *sT = smem + MCGPU_MATH_SMEM;
   double *sW = sT + D * D;
   double2 *sPmh = reinterpret_cast<double2*>(sW + ((p.nsteps + 1) & ~1));     // (mu, -1/(2 sig^2)) pairs, 16-byte aligned
   const int Mpad = (p.pool_m + 7) & ~7;
   double *sPs = reinterpret_cast<double*>(sPmh + Mpad * D);
+  float2 *sPf = reinterpret_cast<float2*>(sPs + Mpad * D);                    // fp32 copy: (mu, -log2(e)/(2 sig^2))
+  float *sSf = reinterpret_cast<float*>(sPf + Mpad * D);                      //            sigma
+  __shared__ float s_scal[2];                           // pool-wide max |mu| and max 1/sigma (error bound of pool_test)
   MathTables T;
 #ifndef MCGPU_EXACT_TU
   T.exp_tab = smem; T.log_tab = smem + MCGPU_EXP_TAB; T.trig_tab = T.log_tab + 2 * MCGPU_LOG_TAB;
@@ -294,12 +413,9 @@ mh_steps_kernel(const StepParams p)
   const int leader = lane & ~(p.coin_group - 1);
 
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) sT[i] = p.factor[i];
+  if (CAN_REMOTE && threadIdx.x < 2) s_stat[threadIdx.x] = 0u;
   if (MAIN)
     for (int k = threadIdx.x; k < p.nsteps; k += blockDim.x) sW[k] = 1.0 / (double)(p.t0 + k + 1);
-  // The exchange pool is staged into shared memory right before the first step that reads it.  With a
-  // host-drawn plan (job-wide coin) that is the window's first remote step; with a peer-to-peer exchange
-  // the wait for the peers' publications sits there too, so the window's leading local steps overlap the
-  // exchange and absorb the skew between GPUs.  Without a plan the pool is staged before step 0.
   __syncthreads();
 
   double x[D], mu[D], ps[D];
@@ -314,22 +430,15 @@ mh_steps_kernel(const StepParams p)
   int tmod = MAIN ? p.t0 % p.thin : 0;                // t % thin and t / thin without per-step divisions
   long long tkeep = MAIN ? (long long)(p.t0 / p.thin) - p.hist_step0 : 0;
 
+  // Stage the exchange pool into shared memory before the first step (with a peer-to-peer exchange this is
+  // where the CTA waits for the peers' publications).  Measured alternatives that defer the staging to the
+  // window's first remote step -- a barrier inside the step loop, or the loop split in two segments -- cost
+  // 3-9 % of the kernel's throughput on every GPU and bought 3 % at 8 GPUs: profiles/r01_history.md.
+  if constexpr (CAN_REMOTE) {
+    if (p.t0 + p.nsteps > p.sync)
+      stage_pool<D>(p.pool_cur, p.pool_m, p.arrivals, p.wait_target, p.xflag, sPmh, sPs, sPf, sSf, s_scal, Mpad);
+  }
   for (int k = 0; k < p.nsteps; ++k) {
-    if constexpr (CAN_REMOTE) {
-      bool stage_now;                                  // launch-uniform, from constant-bank operands only
-      if (PHASE == PH_MIXED && p.plan_valid) stage_now = ((p.plan_mask >> k) & 1u) && (p.plan_mask & ((1u << k) - 1u)) == 0u;
-      else stage_now = k == 0 && p.t0 + p.nsteps > p.sync;
-      if (stage_now) {
-        if (p.wait_target) { wait_arrivals(p.arrivals, p.wait_target, p.xflag); __syncthreads(); }
-        for (int i = threadIdx.x; i < Mpad * D; i += blockDim.x) {
-          if (i < p.pool_m * D) {
-            const double s2 = p.pool_cur[i * 2 + 1];
-            sPmh[i] = make_double2(p.pool_cur[i * 2], -0.5 / s2); sPs[i] = sqrt(s2);   // sigma = sqrt(sig^2), mcpar.cc:346
-          } else sPmh[i] = make_double2(1.0e300, -1.0);   // padding: (mu - x)^2 overflows, a = -inf, Q = 0
-        }
-        __syncthreads();
-      }
-    }
     const uint32_t step = p.step0 + (uint32_t)k;
     const int t = p.t0 + k;
     double u_acc;
@@ -339,7 +448,7 @@ mh_steps_kernel(const StepParams p)
     constexpr int ABLK = (2 * NP) / 4, AW = (2 * NP) % 4;   // accept uniform: word 2*NP of the local stream
     Words wacc;
     if (RNGK == RNG_PHILOX) {
-      wacc = philox4x32_10(glo, ghi, step, (uint32_t)ABLK, p.key0, p.key1);
+      wacc = philox_d<D, !CAN_REMOTE>(glo, ghi, step, (uint32_t)ABLK, p);
       u_acc = u32_mid(word_of(wacc, AW));
       if (PHASE == PH_MIXED) {
         if (p.plan_valid) remote = (p.plan_mask >> k) & 1u;   // job-wide coin, drawn by the host (launch-uniform)
@@ -369,112 +478,111 @@ mh_steps_kernel(const StepParams p)
 
     if constexpr (RNGK == RNG_PHILOX) {
       // ---- proposal generation: genLocal (mcpar.cc:302-312) and genRemote (:315-451) ----
-      // One loop serves both so that the Philox + Box-Muller code exists once (instruction
-      // cache).  Round 0 is the local round: every lane draws its own normals and applies
-      // x' = x + T z.  Remote rounds follow while chains of this warp are still in the
-      // reference's rejection loop: that loop tries candidate iterations it = 0,1,2,... until
-      // one is accepted; candidates are independent counter-based draws, so the warp
-      // evaluates 32 of them per round, spread over the chains still looping (finished
-      // chains' lanes help the stragglers), and each chain takes its FIRST accepted candidate
-      // in iteration order -- the sequential loop's outcome, without lock-step divergence.
+      // Remote steps first run the reference's rejection loop: it tries candidate iterations
+      // it = 0,1,2,... until one is accepted.  Candidates are independent counter-based draws that
+      // do not depend on the chain's state, so the warp evaluates 32 of them per round, spread over
+      // the chains still looping (finished chains' lanes help the stragglers), and each chain
+      // keeps the INDEX of its first accepted candidate in iteration order -- the sequential
+      // loop's outcome, without lock-step divergence.  Only decisions are needed here, so the
+      // candidates are evaluated in fp32 under rigorous bounds (remote_candidate).
       unsigned rm = CAN_REMOTE ? __ballot_sync(0xffffffffu, remote && live) : 0u;
-      bool local_round = PHASE == PH_REMOTE ? false : (CAN_REMOTE ? __any_sync(0xffffffffu, !remote) : true);
-      bool pending = CAN_REMOTE && remote && live;
-      uint32_t it_next = 0;
-      double amax_acc = 0.0;
-      while (local_round || rm) {
-        uint32_t tlo = glo, thi = ghi, slot = 0;
-        int n = 1, my_r = 0;
-        if (!local_round) {                             // schedule 32 candidates over the unfinished chains
-          n = __popc(rm);
+      const unsigned rm0 = rm;                          // the chains of this warp that take a remote step
+      if constexpr (CAN_REMOTE) {
+        bool pending = remote && live;
+        uint32_t it_next = 0;
+        if (rm) s_itacc[threadIdx.x] = 0u;
+        while (rm) {
+          // schedule 32 candidates over the unfinished chains
+          const int n = __popc(rm);
           const int r = lane % n, kk = lane / n;
-          my_r = __popc(rm & ((1u << lane) - 1u));      // rank of this lane's chain among the unfinished
+          const int my_r = __popc(rm & ((1u << lane) - 1u));      // rank of this lane's chain among the unfinished
           if (pending) s_rank[threadIdx.x >> 5][my_r] = (unsigned char)lane;
           __syncwarp();
           const int tgt = s_rank[threadIdx.x >> 5][r];  // lane owning the r-th unfinished chain
           __syncwarp();
           const uint32_t it = __shfl_sync(0xffffffffu, it_next, tgt) + (uint32_t)kk;
-          tlo = __shfl_sync(0xffffffffu, glo, tgt); thi = __shfl_sync(0xffffffffu, ghi, tgt);
-          slot = MCGPU_SLOT_REMOTE | (it << 6);
+          const uint32_t tlo = __shfl_sync(0xffffffffu, glo, tgt), thi = __shfl_sync(0xffffffffu, ghi, tgt);
+          const bool acc = remote_candidate<D, !CAN_REMOTE>(tlo, thi, step, MCGPU_SLOT_REMOTE | (it << 6), p, sPf, sSf, sPmh, sPs,
+                                                           s_scal[0], s_scal[1], T);
+          const unsigned accmask = __ballot_sync(0xffffffffu, acc);
+          if (pending) {
+            const unsigned cm = c_stride_mask[n] << my_r;             // lanes my_r, my_r+n, ... served this chain
+            const unsigned hit = accmask & cm;
+            if (hit) {                                                // lowest lane = lowest iteration index
+              s_itacc[threadIdx.x] = it_next + (uint32_t)__popc(cm & ((1u << (__ffs(hit) - 1)) - 1u));
+              pending = false;
+            } else {
+              it_next += (uint32_t)__popc(cm);
+              if (it_next >= (1u << 24) - 64u) { s_itacc[threadIdx.x] = it_next; pending = false; }   // slot space exhausted (never in practice)
+            }
+          }
+          rm = __ballot_sync(0xffffffffu, pending);
         }
+      }
+      // Materialise the proposal in fp64, once per step and with one copy of the Philox + Box-Muller
+      // code for both kinds: a local step draws its normals from the chain's local stream and
+      // applies x' = x + T z; a remote step re-draws its accepted candidate (same Philox blocks)
+      // and applies x' = mu_c + sigma_c z.
+      // Word stream: local pair q = words (2q, 2q+1); remote pair q = words (2+2q, 3+2q) behind the
+      // pick / rejection-uniform words of block 0.
+      {
+        const bool rem = CAN_REMOTE && remote;
+        uint32_t slot = 0;
+        Words blk;
+        if (rem) {
+          slot = MCGPU_SLOT_REMOTE | (s_itacc[threadIdx.x] << 6);
+          blk = philox_d<D, !CAN_REMOTE>(glo, ghi, step, slot, p);
+          cpick = (int)__umulhi(blk.w0, (uint32_t)p.pool_m);
+        } else if (ABLK == 0) blk = wacc;               // d = 2: the accept block also carries pair 0
+        const int woff = rem ? 1 : 0;                   // in units of pairs
         // normals are consumed as they are produced (no z[D] array: registers at d = 16):
         // local  x'_i = x_i + sum_{q<=i} T[i][q] z_q, accumulated column by column, which adds
-        //        the terms of every row in the same q = 0,1,.. order as the row-wise loop;
-        // remote x'_i = mu_c,i + sigma_c,i z_i needs the component first -> z kept in xz[]
+        //        the terms of every row in the same q = 0,1,.. order as the row-wise loop
         double xz[D];
-        if (local_round) {
 #pragma unroll
-          for (int i = 0; i < D; ++i) xz[i] = x[i];
-        }
-        // word stream: local pair q = words (2q, 2q+1); remote pair q = words (2+2q, 3+2q)
-        // behind the pick / rejection-uniform words of block 0
-        const int woff = local_round ? 0 : 1;           // in units of pairs
-        Words blk;
-        if (!local_round) blk = philox_d<D>(tlo, thi, step, slot, p.key0, p.key1);
-        else if (ABLK == 0) blk = wacc;                 // d = 2: the accept block also carries pair 0
-        const Words blk0 = blk;
+        for (int i = 0; i < D; ++i) xz[i] = rem ? sPmh[cpick * D + i].x : x[i];
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
           const int qq = q + woff;                      // pair position in the stream
-          if ((qq & 1) == 0 && !(qq == 0 && ABLK == 0 && local_round))
-            blk = philox_d<D>(tlo, thi, step, slot + (uint32_t)(qq >> 1), p.key0, p.key1);
+          if ((qq & 1) == 0 && !(qq == 0 && ABLK == 0 && !rem))
+            blk = philox_d<D, !CAN_REMOTE>(glo, ghi, step, slot + (uint32_t)(qq >> 1), p);
           const uint32_t wa = (qq & 1) ? blk.w2 : blk.w0, wb = (qq & 1) ? blk.w3 : blk.w1;
           double za, zb;
           normal_pair_t(wa, wb, za, zb, T);
-          if (local_round) {
+          if (!rem) {
 #pragma unroll
             for (int i = 2 * q; i < D; ++i) xz[i] += factor_at<D>(sT, i * D + 2 * q) * za;
 #pragma unroll
             for (int i = 2 * q + 1; i < D; ++i) xz[i] += factor_at<D>(sT, i * D + 2 * q + 1) * zb;
           } else {
-            xz[2 * q] = za;
-            if (2 * q + 1 < D) xz[2 * q + 1] = zb;
+            xz[2 * q] += sPs[cpick * D + 2 * q] * za;                                   // DIAGONAL storage, :348-350
+            if (2 * q + 1 < D) xz[2 * q + 1] += sPs[cpick * D + 2 * q + 1] * zb;
           }
         }
-        if (local_round) {
-          if (!remote) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) xt[i] = xz[i];
-          }
-          local_round = false;
-          continue;
-        }
-        if constexpr (CAN_REMOTE) {
-          const int c = (int)__umulhi(blk0.w0, (uint32_t)p.pool_m);    // viRngUniform(0, tchains), mcpar.cc:337
-          const double u = u32_mid(blk0.w1);                           // vsRngUniform, mcpar.cc:401
-          double xc[D], am;
-#pragma unroll
-          for (int i = 0; i < D; ++i) xc[i] = sPmh[c * D + i].x + sPs[c * D + i] * xz[i];   // DIAGONAL storage, :348-350
-          const bool acc = pool_test<D>(sPmh, p.pool_m, xc, u, am, T);
-          const unsigned accmask = __ballot_sync(0xffffffffu, acc);
-          int src = lane;
-          bool fin = false;
-          if (pending) {
-            const unsigned cm = c_stride_mask[n] << my_r;             // lanes my_r, my_r+n, ... served this chain
-            const unsigned hit = accmask & cm;
-            if (hit) { src = __ffs(hit) - 1; fin = true; }           // lowest lane = lowest iteration index
-            else it_next += (uint32_t)__popc(cm);
-          }
-          const int c_s = __shfl_sync(0xffffffffu, c, src);
-          const double am_s = __shfl_sync(0xffffffffu, am, src);
-#pragma unroll
-          for (int i = 0; i < D; ++i) { const double v = __shfl_sync(0xffffffffu, xc[i], src); if (fin) xt[i] = v; }
-          if (fin) { cpick = c_s; amax_acc = am_s; pending = false; }
-          if (it_next >= (1u << 24) - 64u) pending = false;          // slot space exhausted (never in practice)
-          rm = __ballot_sync(0xffffffffu, pending);
-        }
+        for (int i = 0; i < D; ++i) xt[i] = xz[i];
       }
       if constexpr (CAN_REMOTE) {
-        if (remote) {
-          // cfac = max_i Q_i(x_old) / max_i Q_i(x'), mcpar.cc:412-439
-          double aold = -INFINITY;
-          for (int s = 0; s < p.pool_m; ++s) {
-            double a = 0.0;
+        if (!MCGPU_EXP_NOCOUNT && rm0) {                // statistics: remote chain-steps and the iterations the reference's
+          unsigned wi = (rm0 >> lane) & 1u ? s_itacc[threadIdx.x] + 1u : 0u;   // loop (mcpar.cc:331-409) would have run for them
 #pragma unroll
-            for (int i = 0; i < D; ++i) { const double2 mh = sPmh[s * D + i]; const double xm = mh.x - x[i]; a += xm * xm * mh.y; }
-            aold = a > aold ? a : aold;
+          for (int o = 16; o > 0; o >>= 1) wi += __shfl_xor_sync(0xffffffffu, wi, o);
+          if (lane == 0) { atomicAdd(&s_stat[0], (unsigned)__popc(rm0)); atomicAdd(&s_stat[1], wi); }
+        }
+        if (remote) {
+          // cfac = max_i Q_i(x_old) / max_i Q_i(x'), mcpar.cc:412-439: both maxima in fp64, one pass over the pool
+          double aold = -INFINITY, anew = -INFINITY;
+          for (int s = 0; s < p.pool_m; ++s) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              const double2 mh = sPmh[s * D + i];
+              const double xm = mh.x - x[i], ym = mh.x - xt[i];
+              a += xm * xm * mh.y; b += ym * ym * mh.y;
+            }
+            aold = a > aold ? a : aold; anew = b > anew ? b : anew;
           }
-          double qmax = MC_EXP(amax_acc);
+          double qmax = MC_EXP(anew);
           qmax = qmax > MCGPU_FPEPS ? qmax : MCGPU_FPEPS;              // qimax starts at FPEPS, :357
           cfac = MC_EXP(aold) / qmax;
         }
@@ -494,7 +602,7 @@ mh_steps_kernel(const StepParams p)
     }
 
     const double lyt = Lik<LIK, D>::eval(xt, p, T);
-    const bool a = accept_test(u_acc, lyt - ly, MAIN ? cfac : 1.0, T);   // mcpar.cc:67-69 / :167-169
+    const bool a = accept_test(u_acc, lyt - ly, MAIN ? cfac : 1.0, T, p.exact_tests);   // mcpar.cc:67-69 / :167-169
     if (a) {
       ly = lyt;
 #pragma unroll
@@ -568,6 +676,12 @@ mh_steps_kernel(const StepParams p)
   if (lane == 0) {
     atomicAdd(p.counts, (unsigned long long)wacc);
     atomicAdd(p.counts + 1, (unsigned long long)nlive * (unsigned long long)p.nsteps);
+  }
+  if constexpr (CAN_REMOTE) {                          // main-phase statistics: counts[2] remote chain-steps, [3] candidates
+    __syncthreads();
+    if (threadIdx.x == 0 && s_stat[0]) {
+      atomicAdd(p.counts + 2, (unsigned long long)s_stat[0]); atomicAdd(p.counts + 3, (unsigned long long)s_stat[1]);
+    }
   }
 }
 

@@ -205,7 +205,7 @@ mh_wide_kernel(const WideParams p)
   const long long jb = ((long long)blockIdx.x * (blockDim.x / L) + gib) * NCH;
   long long jc[NCH]; bool live[NCH]; uint32_t glo[NCH], ghi[NCH];
   double x0[NCH], x1[NCH], ly[NCH], mu0[NCH], mu1[NCH], ps0[NCH], ps1[NCH];
-  unsigned int nacc[NCH];
+  unsigned int nacc[NCH], nit = 0;                // accepted steps; candidate iterations of the remote steps
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     live[c] = jb + c < p.C;
@@ -230,7 +230,7 @@ mh_wide_kernel(const WideParams p)
     int cpick[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const Words wacc = philox4x32_10(glo[c], ghi[c], step, (uint32_t)ABLK, p.key0, p.key1);
+      const Words wacc = philox4x32_10_rk(glo[c], ghi[c], step, (uint32_t)ABLK, p.rk);
       u_acc[c] = u32_mid(word_of(wacc, AW));
       cfac[c] = 1.0; cpick[c] = 0; xt0[c] = x0[c]; xt1[c] = x1[c];
     }
@@ -240,7 +240,7 @@ mh_wide_kernel(const WideParams p)
       double za[NCH], zb[NCH];
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        const Words b = philox4x32_10(glo[c], ghi[c], step, (uint32_t)(r >> 1), p.key0, p.key1);
+        const Words b = philox4x32_10_rk(glo[c], ghi[c], step, (uint32_t)(r >> 1), p.rk);
         normal_pair_t((r & 1) ? b.w2 : b.w0, (r & 1) ? b.w3 : b.w1, za[c], zb[c], T);
       }
       if (diag) {
@@ -278,12 +278,12 @@ mh_wide_kernel(const WideParams p)
         double c0[NCH], c1[NCH], u[NCH]; int cc[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const Words w0 = philox4x32_10(glo[c], ghi[c], step, slot, p.key0, p.key1);   // same block in every lane of the group
+          const Words w0 = philox4x32_10_rk(glo[c], ghi[c], step, slot, p.rk);   // same block in every lane of the group
           cc[c] = (int)__umulhi(w0.w0, (uint32_t)p.pool_m);                              // viRngUniform, mcpar.cc:337
           u[c] = u32_mid(w0.w1);                                                         // vsRngUniform, mcpar.cc:401
           const int qq = r + 1;                     // lane r's pair = words (2+2r, 3+2r) of the candidate's stream
           Words b = w0;
-          if ((qq >> 1) != 0) b = philox4x32_10(glo[c], ghi[c], step, slot + (uint32_t)(qq >> 1), p.key0, p.key1);
+          if ((qq >> 1) != 0) b = philox4x32_10_rk(glo[c], ghi[c], step, slot + (uint32_t)(qq >> 1), p.rk);
           double za, zb;
           normal_pair_t((qq & 1) ? b.w2 : b.w0, (qq & 1) ? b.w3 : b.w1, za, zb, T);
           c0[c] = __ldg(p.pmh + (size_t)i0 * p.mpad + cc[c]).x + __ldg(p.psd + (size_t)i0 * p.mpad + cc[c]) * za;   // DIAGONAL storage, :348-350
@@ -317,7 +317,7 @@ mh_wide_kernel(const WideParams p)
         bool alldone = true;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          if (!done[c] && (acc[c] || it >= (1u << 24) - 2u)) { xt0[c] = c0[c]; xt1[c] = c1[c]; cpick[c] = cc[c]; amax_acc[c] = am[c]; done[c] = true; }
+          if (!done[c] && (acc[c] || it >= (1u << 24) - 2u)) { xt0[c] = c0[c]; xt1[c] = c1[c]; cpick[c] = cc[c]; amax_acc[c] = am[c]; done[c] = true; nit += live[c] ? it + 1u : 0u; }
           alldone = alldone && done[c];
         }
         if (__all_sync(0xffffffffu, alldone)) break;
@@ -349,7 +349,7 @@ mh_wide_kernel(const WideParams p)
     const double pwgt = (double)(t + 1), winv = 1.0 / pwgt;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const bool a = accept_test(u_acc[c], lyt[c] - ly[c], MAIN ? cfac[c] : 1.0, T);   // same inputs in every lane of the group
+      const bool a = accept_test(u_acc[c], lyt[c] - ly[c], MAIN ? cfac[c] : 1.0, T, 0);   // same inputs in every lane of the group
       if (a) { ly[c] = lyt[c]; x0[c] = xt0[c]; x1[c] = xt1[c]; }
       nacc[c] += a ? 1u : 0u;
       if (MAIN) {
@@ -408,6 +408,15 @@ mh_wide_kernel(const WideParams p)
   if ((threadIdx.x & 31) == 0) {
     atomicAdd(p.counts, (unsigned long long)wacc);
     atomicAdd(p.counts + 1, (unsigned long long)nlive * (unsigned long long)p.nsteps);
+  }
+  if (PHASE == PH_REMOTE) {                     // main-phase statistics: counts[2] remote chain-steps, [3] candidates
+    unsigned int wi = r == 0 ? nit : 0u;        // every lane of a group counted the same
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wi += __shfl_xor_sync(0xffffffffu, wi, o);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(p.counts + 2, (unsigned long long)nlive * (unsigned long long)p.nsteps);
+      atomicAdd(p.counts + 3, (unsigned long long)wi);
+    }
   }
 }
 

@@ -1,0 +1,31 @@
+"""Helper of tests/test_gpu_audit.py: one normal-mode run, history + final state saved to an .npz.
+Run in a fresh process because MCGPU_EXACT_TESTS is read once per process."""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import tiled_pinit                        # noqa: E402
+from mcpar_b200 import engine                           # noqa: E402
+
+
+def run(lik, par, d, N, M, pl, cg, nburn, nsamp):
+    e = engine.Engine(d, N, mode="normal", pool_m=M, pl=pl, coin_group=cg, history_steps=nsamp)
+    e.run(nsamp, nburn, tiled_pinit(N, d), lik, par)
+    out = dict(hist=e.history(), p=e.state()["p"], pool=e.musig(), acc=np.array(e.stats()["accepted"]),
+               rit=np.array(e.stats()["remote_iterations"]))
+    e.close()
+    return out
+
+
+CASES = {
+    "dgauss": ("dualgaussian", [5.0], 2, 8192, 16, 0.5, 0, 150, 300),
+    "rosen2": ("rosenbrock1", None, 2, 4096, 32, 0.5, 0, 150, 300),
+    "rosen2_groups": ("rosenbrock1", None, 2, 4096, 12, 0.6, 8, 150, 200),
+    "rosen4": ("rosenbrock1", None, 4, 2048, 8, 0.5, 0, 150, 200),
+}
+
+if __name__ == "__main__":
+    name, path = sys.argv[1], sys.argv[2]
+    np.savez(path, **run(*CASES[name]))

@@ -244,6 +244,11 @@ def test_normal_mode_matches_counter_oracle(lik, d, N, par, pool_m, pl, cg):
     s = e.stats()
     assert abs(s["accepted"] - int(o["counts"][0])) <= max(2, nsamp * N // 5000)
     assert o["remote"][nburn:].any(), "test must exercise the remote branch"
+    # the kernels count the remote chain-steps and the candidates their rejection loops tried
+    # (mcpar.cc:331-409); trajectories that diverge by an ulp may shift the candidate count slightly
+    assert s["remote_steps"] == int(o["remote"][nburn:].sum())
+    ri = int(o["remote_iters"][0])
+    assert abs(s["remote_iterations"] - ri) <= max(2, ri // 200), (s["remote_iterations"], ri)
     e.close()
 
 
