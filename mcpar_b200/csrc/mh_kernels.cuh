@@ -214,6 +214,10 @@ __device__ __noinline__ bool remote_exact(uint32_t tlo, uint32_t thi, uint32_t s
   return u < qmax / qsum;
 }
 
+// c_recip[n] = ceil(2^16 / n): (lane * c_recip[n]) >> 16 == lane / n for lane < 32, n <= 32
+__constant__ unsigned c_recip[33] = {0u, 65536u, 32768u, 21846u, 16384u, 13108u, 10923u, 9363u, 8192u, 7282u, 6554u, 5958u, 5462u,
+  5042u, 4682u, 4370u, 4096u, 3856u, 3641u, 3450u, 3277u, 3121u, 2979u, 2850u, 2731u, 2622u, 2521u, 2428u, 2341u, 2260u, 2185u,
+  2115u, 2048u};
 // c_stride_mask[n]: bits 0, n, 2n, ... below 32
 __constant__ unsigned c_stride_mask[33] = {0u,
   0xffffffffu, 0x55555555u, 0x49249249u, 0x11111111u, 0x42108421u, 0x41041041u, 0x10204081u, 0x01010101u,
@@ -236,10 +240,11 @@ __device__ __forceinline__ float cos_approx(float x) { float y; asm("cos.approx.
 //   angle 2 pi (a - 1/2), |a - 1/2| <= 1/2: argument error <= 8e-7, sin/cos error <= 2e-6 (the
 //   approximation's 5.1e-7 tripled, plus the argument's);  z = r trig:  |dz| <= dr + r (2e-6 + 1.2e-7)
 //   <= 1.7e-6 / (r~ + 1.3e-3) + 2.4e-6 r~   (r~ >= 1.3e-3 or not).
-__device__ __forceinline__ float normal_pair_f32(uint32_t wa, uint32_t wb, float &z0, float &z1)
+__device__ __forceinline__ float normal_pair_f32(uint32_t wa, uint32_t wb, float &z0, float &z1, float &lg)
 {
   const float v = ((float)wa + 1.0f) * 2.3283064365386963e-10f;                 // (0, 1]
-  const float r = sqrt_approx(-1.3862943611198906f * lg2_approx(v));
+  lg = lg2_approx(v);                                                           // = -(z0^2 + z1^2)/2 * log2(e), in [-32, 0]
+  const float r = sqrt_approx(-1.3862943611198906f * lg);
   const float ang = 6.283185307179586f * ((float)wb * 2.3283064365386963e-10f - 0.5f);   // 2 pi u - pi in [-pi, pi]
   z0 = -r * sin_approx(ang); z1 = -r * cos_approx(ang);                         // sin(t + pi) = -sin t, cos(t + pi) = -cos t
   return fmaf(2.4e-6f, r, __fdividef(1.7e-6f, r + 1.3e-3f));
@@ -274,13 +279,14 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
   Words blk = philox_d<D, RK>(tlo, thi, step, slot, p);
   const int c = (int)__umulhi(blk.w0, (uint32_t)M);                 // viRngUniform(0, tchains), mcpar.cc:337
   const double u = u32_mid(blk.w1);                                 // vsRngUniform, mcpar.cc:401
-  float xf[D], xabs = 0.0f, sgmax = 0.0f, zerr = 0.0f;
+  float xf[D], xabs = 0.0f, sgmax = 0.0f, zerr = 0.0f, ref = 0.0f;
 #pragma unroll
   for (int q = 0; q < NP; ++q) {                                    // pair q = words (2+2q, 3+2q) of the candidate's stream
     const int qq = q + 1;
     if ((qq & 1) == 0) blk = philox_d<D, RK>(tlo, thi, step, slot + (uint32_t)(qq >> 1), p);
-    float za, zb;
-    zerr = fmaxf(zerr, normal_pair_f32((qq & 1) ? blk.w2 : blk.w0, (qq & 1) ? blk.w3 : blk.w1, za, zb));
+    float za, zb, lg;
+    zerr = fmaxf(zerr, normal_pair_f32((qq & 1) ? blk.w2 : blk.w0, (qq & 1) ? blk.w3 : blk.w1, za, zb, lg));
+    ref += lg;                                                      // a_c * log2(e) of the picked component itself
     {
       const int i = 2 * q; const float sg = sSf[c * D + i];
       xf[i] = fmaf(sg, za, sPf[c * D + i].x);                       // DIAGONAL storage, :348-350
@@ -293,33 +299,61 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
     }
   }
   const float theta = (1.9e-7f * (mu_max + xabs) + zerr * sgmax) * isig_max;
-  float m = -INFINITY;                                 // running max of a_s * log2(e)
-  float S = 0.0f;                                      // sum_s 2^(a_s - m)
-  for (int s0 = 0; s0 < Mpad; s0 += CH) {
-    float a[CH];
+  const double eps = 1.0e-4 + 1.0e-5 * (double)D + 2.0e-5 * (double)M + (double)(theta * (21.3f * sqrtf((float)D)));
+  if constexpr (D <= 4) {
+    // Exponents are taken relative to the picked component's own a_c = log2 v (>= -32 per normal pair), which
+    // the Box-Muller step already has: 2^(a_s - a_c) <= 2^64 cannot overflow, so the sum needs no running
+    // maximum and no rescaling -- the accumulator simply starts at -a_c.
+    float mr = -INFINITY, S = 0.0f;                    // max_s and sum_s of 2^(a_s - a_c)
+    for (int s0 = 0; s0 < Mpad; s0 += CH) {
 #pragma unroll
-    for (int q = 0; q < CH; ++q) {
-      float acc = 0.0f;
+      for (int q = 0; q < CH; ++q) {
+        float acc = -ref;
+        if constexpr (D == 2) {                        // one 16-byte shared-memory load per slot (sPf is 16-byte aligned)
+          const float4 f = reinterpret_cast<const float4 *>(sPf)[s0 + q];
+          const float xm0 = f.x - xf[0], xm1 = f.z - xf[1];
+          acc = fmaf(xm0 * xm0, f.y, acc); acc = fmaf(xm1 * xm1, f.w, acc);
+        } else {
 #pragma unroll
-      for (int i = 0; i < D; ++i) { const float2 f = sPf[(s0 + q) * D + i]; const float xm = f.x - xf[i]; acc = fmaf(xm * xm, f.y, acc); }
-      a[q] = acc;
+          for (int i = 0; i < D; ++i) { const float2 f = sPf[(s0 + q) * D + i]; const float xm = f.x - xf[i]; acc = fmaf(xm * xm, f.y, acc); }
+        }
+        mr = fmaxf(mr, acc);
+        S += ex2_approx(acc);
+      }
     }
-    float mc = a[0];
+    if (mr + ref > -14.0f && theta < 2.0e-3f && !p.exact_tests) {   // max a > -9.7: then FPEPS/qmax < 2e-10 (mcpar.cc:357-358 offsets)
+      const double Sd = (double)S, Ed = (double)ex2_approx(mr);     // R = S / E
+      if (u * (Sd * (1.0 + eps) + 3.0e-10 * Ed) < Ed) return true;  // u < r_lo
+      if (u * (Sd * (1.0 - eps)) >= Ed) return false;               // u >= r_hi
+    }
+  } else {
+    float m = -INFINITY;                               // running max of a_s * log2(e)
+    float S = 0.0f;                                    // sum_s 2^(a_s - m)
+    for (int s0 = 0; s0 < Mpad; s0 += CH) {
+      float a[CH];
 #pragma unroll
-    for (int q = 1; q < CH; ++q) mc = fmaxf(mc, a[q]);
-    float sc = 0.0f;
+      for (int q = 0; q < CH; ++q) {
+        float acc = 0.0f;
 #pragma unroll
-    for (int q = 0; q < CH; ++q) sc += ex2_approx(a[q] - mc);                     // each <= 1
-    const bool gt = mc > m;
-    const float e = ex2_approx(-fabsf(m - mc));                                   // 0 on the first chunk
-    S = gt ? fmaf(S, e, sc) : fmaf(sc, e, S);
-    m = gt ? mc : m;
-  }
-  if (m > -14.0f && theta < 2.0e-3f && !p.exact_tests) {   // max a > -9.7: then FPEPS/qmax < 2e-10 (mcpar.cc:357-358 offsets)
-    const double eps = 1.0e-4 + 1.0e-5 * (double)D + 2.0e-5 * (double)M + (double)(theta * (21.3f * sqrtf((float)D)));
-    const double Sd = (double)S;
-    if (u * (Sd * (1.0 + eps) + 3.0e-10) < 1.0) return true;      // u < r_lo
-    if (u * (Sd * (1.0 - eps)) >= 1.0) return false;              // u >= r_hi
+        for (int i = 0; i < D; ++i) { const float2 f = sPf[(s0 + q) * D + i]; const float xm = f.x - xf[i]; acc = fmaf(xm * xm, f.y, acc); }
+        a[q] = acc;
+      }
+      float mc = a[0];
+#pragma unroll
+      for (int q = 1; q < CH; ++q) mc = fmaxf(mc, a[q]);
+      float sc = 0.0f;
+#pragma unroll
+      for (int q = 0; q < CH; ++q) sc += ex2_approx(a[q] - mc);                   // each <= 1
+      const bool gt = mc > m;
+      const float e = ex2_approx(-fabsf(m - mc));                                 // 0 on the first chunk
+      S = gt ? fmaf(S, e, sc) : fmaf(sc, e, S);
+      m = gt ? mc : m;
+    }
+    if (m > -14.0f && theta < 2.0e-3f && !p.exact_tests) {
+      const double Sd = (double)S;
+      if (u * (Sd * (1.0 + eps) + 3.0e-10) < 1.0) return true;      // u < r_lo
+      if (u * (Sd * (1.0 - eps)) >= 1.0) return false;              // u >= r_hi
+    }
   }
   return remote_exact<D>(tlo, thi, step, slot, p.key0, p.key1, sPmh, sPs, M, T);   // rare: the bounds straddle u (also the NaN path)
 }
@@ -494,7 +528,7 @@ mh_steps_kernel(const StepParams p)
         while (rm) {
           // schedule 32 candidates over the unfinished chains
           const int n = __popc(rm);
-          const int r = lane % n, kk = lane / n;
+          const int kk = (int)(((unsigned)lane * c_recip[n]) >> 16), r = lane - kk * n;   // lane / n, lane % n
           const int my_r = __popc(rm & ((1u << lane) - 1u));      // rank of this lane's chain among the unfinished
           if (pending) s_rank[threadIdx.x >> 5][my_r] = (unsigned char)lane;
           __syncwarp();
