@@ -55,7 +55,7 @@ bool steps_supported(int lik, int d)
 
 size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem)
 {
-  return sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)d * d + (size_t)((nsteps + 1) & ~1) + (pool_in_smem ? (size_t)((pool_m + 7) & ~7) * d * 5 : 0));   // pool: (mu, h) + sigma in fp64, (mu, h) + sigma in fp32
+  return sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)d * d + (size_t)((nsteps + 1) & ~1) + (pool_in_smem ? (size_t)((pool_m + 7) & ~7) * d * 5 : 0));   // pool: (mu, h) + sigma in fp64; (g mu, g) + (sigma, mu) in fp32
 }
 
 cudaError_t launch_steps(int lik, int d, int rngk, int phase, const StepParams &p, cudaStream_t st)

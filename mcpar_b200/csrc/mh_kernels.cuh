@@ -135,8 +135,7 @@ __device__ __noinline__ Words philox_call(uint32_t c0, uint32_t c1, uint32_t c2,
 {
   return philox4x32_10(c0, c1, c2, c3, k0, k1);
 }
-// RK: take the precomputed round keys from the launch parameters (the lean local / burn-in kernels; in
-// the two-path kernels, at their register cap, the in-line key schedule compiles without spills)
+// RK: take the precomputed round keys from the launch parameters (constant-bank operands of the LOP3s)
 template <int D, bool RK>
 __device__ __forceinline__ Words philox_d(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const StepParams &p)
 {
@@ -254,13 +253,13 @@ __device__ __forceinline__ float normal_pair_f32(uint32_t wa, uint32_t wb, float
 // component c, the uniform u and the normals z from the candidate's Philox blocks, form
 // x' = mu_c + sigma_c z and decide  u < max_s Q_s(x') / sum_s Q_s(x')  over the pool.  Rejected candidates
 // leave no trace and the accepted one is re-materialised in fp64 by its chain afterwards, so everything
-// here runs in fp32 on an fp32 copy of the pool -- sPf = (mu, -log2(e)/(2 sigma^2)) pairs, sSf = sigma,
+// here runs in fp32 on an fp32 copy of the pool -- sPf = (g mu, g) with g = sqrt(log2(e)/(2 sigma^2)), sSf = (sigma, mu),
 // padded to a multiple of 8 slots whose Q is 0; SFU log2/sqrt/sin/cos/exp2; chunks of 8 slots for ILP with
 // one rescale per chunk -- under a rigorous bound on the relative error of
 //     R = sum_s exp(a_s - max a),   a_s = -sum_i (mu_si - x'_i)^2 / (2 sigma_si^2);
 // when the bound does not settle u the candidate is redone exactly in fp64 (remote_exact).
-// Error bound.  mu_s - x' is off by at most delta = zerr sigma_c,max (normals, normal_pair_f32) + 3 u24 (|mu|max + |x'|)
-// (roundings of mu_c, sigma_c, the fma and mu_s), u24 = 2^-24.  A term with |a_s| <= A then moves by at
+// Error bound.  mu_s - x' (formed as (g mu - g x') / g) is off by at most delta = zerr sigma_c,max (normals,
+// normal_pair_f32) + 3 u24 (|mu|max + |x'|) (roundings of mu_c, sigma_c, g mu_s, g and the fmas), u24 = 2^-24.  A term with |a_s| <= A then moves by at
 // most sqrt(2 A D) theta + (6 + D) u24 A, theta = delta / sigma_min.  Terms that matter have A <= 35 (the
 // bound is only used when max a > -10; terms 25 below the max contribute < 1.4e-11 each, and their own
 // error cannot lift them: sqrt(|a|) theta << |a| - 35).  Both a_s and the max move, so every term of R is
@@ -270,7 +269,7 @@ __device__ __forceinline__ float normal_pair_f32(uint32_t wa, uint32_t wb, float
 // tests/test_gpu_audit.py checks the decisions against an all-fp64 run of the same kernels.
 template <int D, bool RK>
 __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uint32_t step, uint32_t slot, const StepParams &p,
-                                                 const float2 *sPf, const float *sSf, const double2 *sPmh, const double *sPs,
+                                                 const float2 *sPf, const float2 *sSf, const double2 *sPmh, const double *sPs,
                                                  float mu_max, float isig_max, const MathTables &T)
 {
   constexpr int CH = 8;
@@ -288,14 +287,14 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
     zerr = fmaxf(zerr, normal_pair_f32((qq & 1) ? blk.w2 : blk.w0, (qq & 1) ? blk.w3 : blk.w1, za, zb, lg));
     ref += lg;                                                      // a_c * log2(e) of the picked component itself
     {
-      const int i = 2 * q; const float sg = sSf[c * D + i];
-      xf[i] = fmaf(sg, za, sPf[c * D + i].x);                       // DIAGONAL storage, :348-350
-      xabs = fmaxf(xabs, fabsf(xf[i])); sgmax = fmaxf(sgmax, sg);
+      const int i = 2 * q; const float2 sm = sSf[c * D + i];
+      xf[i] = fmaf(sm.x, za, sm.y);                                 // DIAGONAL storage, :348-350
+      xabs = fmaxf(xabs, fabsf(xf[i])); sgmax = fmaxf(sgmax, sm.x);
     }
     if (2 * q + 1 < D) {
-      const int i = 2 * q + 1; const float sg = sSf[c * D + i];
-      xf[i] = fmaf(sg, zb, sPf[c * D + i].x);
-      xabs = fmaxf(xabs, fabsf(xf[i])); sgmax = fmaxf(sgmax, sg);
+      const int i = 2 * q + 1; const float2 sm = sSf[c * D + i];
+      xf[i] = fmaf(sm.x, zb, sm.y);
+      xabs = fmaxf(xabs, fabsf(xf[i])); sgmax = fmaxf(sgmax, sm.x);
     }
   }
   const float theta = (1.9e-7f * (mu_max + xabs) + zerr * sgmax) * isig_max;
@@ -311,11 +310,11 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
         float acc = -ref;
         if constexpr (D == 2) {                        // one 16-byte shared-memory load per slot (sPf is 16-byte aligned)
           const float4 f = reinterpret_cast<const float4 *>(sPf)[s0 + q];
-          const float xm0 = f.x - xf[0], xm1 = f.z - xf[1];
-          acc = fmaf(xm0 * xm0, f.y, acc); acc = fmaf(xm1 * xm1, f.w, acc);
+          const float y0 = fmaf(-f.y, xf[0], f.x), y1 = fmaf(-f.w, xf[1], f.z);   // g (mu - x'): two FFMA per dimension
+          acc = fmaf(-y0, y0, acc); acc = fmaf(-y1, y1, acc);
         } else {
 #pragma unroll
-          for (int i = 0; i < D; ++i) { const float2 f = sPf[(s0 + q) * D + i]; const float xm = f.x - xf[i]; acc = fmaf(xm * xm, f.y, acc); }
+          for (int i = 0; i < D; ++i) { const float2 f = sPf[(s0 + q) * D + i]; const float y = fmaf(-f.y, xf[i], f.x); acc = fmaf(-y, y, acc); }
         }
         mr = fmaxf(mr, acc);
         S += ex2_approx(acc);
@@ -335,7 +334,7 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
       for (int q = 0; q < CH; ++q) {
         float acc = 0.0f;
 #pragma unroll
-        for (int i = 0; i < D; ++i) { const float2 f = sPf[(s0 + q) * D + i]; const float xm = f.x - xf[i]; acc = fmaf(xm * xm, f.y, acc); }
+        for (int i = 0; i < D; ++i) { const float2 f = sPf[(s0 + q) * D + i]; const float y = fmaf(-f.y, xf[i], f.x); acc = fmaf(-y, y, acc); }
         a[q] = acc;
       }
       float mc = a[0];
@@ -385,7 +384,7 @@ enum { PH_BURN = 0, PH_MIXED = 1, PH_LOCAL = 2, PH_REMOTE = 3 };
 template <int D>
 __device__ MCGPU_STAGE_QUAL void stage_pool(const double *pool_cur, int pool_m, const unsigned long long *arrivals,
                                         unsigned long long wait_target, int *xflag, double2 *sPmh, double *sPs,
-                                        float2 *sPf, float *sSf, float *s_scal, int Mpad)
+                                        float2 *sPf, float2 *sSf, float *s_scal, int Mpad)
 {
   if (wait_target) wait_arrivals(arrivals, wait_target, xflag);
   if (threadIdx.x < 2) s_scal[threadIdx.x] = 0.0f;
@@ -396,10 +395,11 @@ __device__ MCGPU_STAGE_QUAL void stage_pool(const double *pool_cur, int pool_m, 
       const double m = pool_cur[i * 2], s2 = pool_cur[i * 2 + 1];
       const double h = -0.5 / s2, sd = sqrt(s2);       // sigma = sqrt(sig^2), mcpar.cc:346
       sPmh[i] = make_double2(m, h); sPs[i] = sd;
-      sPf[i] = make_float2((float)m, (float)(h * 1.4426950408889634)); sSf[i] = (float)sd;
+      const double g = sqrt(-h * 1.4426950408889634);   // sqrt(log2(e) / (2 sigma^2)): a_s log2(e) = -sum_i (g mu - g x)^2
+      sPf[i] = make_float2((float)(g * m), (float)g); sSf[i] = make_float2((float)sd, (float)m);
       mumax = fmaxf(mumax, __double2float_ru(fabs(m))); isig = fmaxf(isig, __double2float_ru(1.0 / sd));
     } else {                                           // padding: (mu - x)^2 overflows / is huge, a = -inf, Q = 0
-      sPmh[i] = make_double2(1.0e300, -1.0); sPf[i] = make_float2(1.0e18f, -1.0f); sSf[i] = 0.0f;
+      sPmh[i] = make_double2(1.0e300, -1.0); sPf[i] = make_float2(1.0e18f, 0.0f); sSf[i] = make_float2(0.0f, 0.0f);
     }
   }
   // max over the CTA (non-negative floats order like their bit patterns; NaN/inf sort above every
@@ -425,8 +425,8 @@ mh_steps_kernel(const StepParams p)
   double2 *sPmh = reinterpret_cast<double2*>(sW + ((p.nsteps + 1) & ~1));     // (mu, -1/(2 sig^2)) pairs, 16-byte aligned
   const int Mpad = (p.pool_m + 7) & ~7;
   double *sPs = reinterpret_cast<double*>(sPmh + Mpad * D);
-  float2 *sPf = reinterpret_cast<float2*>(sPs + Mpad * D);                    // fp32 copy: (mu, -log2(e)/(2 sig^2))
-  float *sSf = reinterpret_cast<float*>(sPf + Mpad * D);                      //            sigma
+  float2 *sPf = reinterpret_cast<float2*>(sPs + Mpad * D);                    // fp32 copy: (g mu, g), g = sqrt(log2(e)/(2 sig^2))
+  float2 *sSf = sPf + Mpad * D;                                               //            (sigma, mu)
   __shared__ float s_scal[2];                           // pool-wide max |mu| and max 1/sigma (error bound of pool_test)
   MathTables T;
 #ifndef MCGPU_EXACT_TU
@@ -482,7 +482,7 @@ mh_steps_kernel(const StepParams p)
     constexpr int ABLK = (2 * NP) / 4, AW = (2 * NP) % 4;   // accept uniform: word 2*NP of the local stream
     Words wacc;
     if (RNGK == RNG_PHILOX) {
-      wacc = philox_d<D, !CAN_REMOTE>(glo, ghi, step, (uint32_t)ABLK, p);
+      wacc = philox_d<D, true>(glo, ghi, step, (uint32_t)ABLK, p);
       u_acc = u32_mid(word_of(wacc, AW));
       if (PHASE == PH_MIXED) {
         if (p.plan_valid) remote = (p.plan_mask >> k) & 1u;   // job-wide coin, drawn by the host (launch-uniform)
@@ -536,7 +536,7 @@ mh_steps_kernel(const StepParams p)
           __syncwarp();
           const uint32_t it = __shfl_sync(0xffffffffu, it_next, tgt) + (uint32_t)kk;
           const uint32_t tlo = __shfl_sync(0xffffffffu, glo, tgt), thi = __shfl_sync(0xffffffffu, ghi, tgt);
-          const bool acc = remote_candidate<D, !CAN_REMOTE>(tlo, thi, step, MCGPU_SLOT_REMOTE | (it << 6), p, sPf, sSf, sPmh, sPs,
+          const bool acc = remote_candidate<D, true>(tlo, thi, step, MCGPU_SLOT_REMOTE | (it << 6), p, sPf, sSf, sPmh, sPs,
                                                            s_scal[0], s_scal[1], T);
           const unsigned accmask = __ballot_sync(0xffffffffu, acc);
           if (pending) {
@@ -565,7 +565,7 @@ mh_steps_kernel(const StepParams p)
         Words blk;
         if (rem) {
           slot = MCGPU_SLOT_REMOTE | (s_itacc[threadIdx.x] << 6);
-          blk = philox_d<D, !CAN_REMOTE>(glo, ghi, step, slot, p);
+          blk = philox_d<D, true>(glo, ghi, step, slot, p);
           cpick = (int)__umulhi(blk.w0, (uint32_t)p.pool_m);
         } else if (ABLK == 0) blk = wacc;               // d = 2: the accept block also carries pair 0
         const int woff = rem ? 1 : 0;                   // in units of pairs
@@ -579,7 +579,7 @@ mh_steps_kernel(const StepParams p)
         for (int q = 0; q < NP; ++q) {
           const int qq = q + woff;                      // pair position in the stream
           if ((qq & 1) == 0 && !(qq == 0 && ABLK == 0 && !rem))
-            blk = philox_d<D, !CAN_REMOTE>(glo, ghi, step, slot + (uint32_t)(qq >> 1), p);
+            blk = philox_d<D, true>(glo, ghi, step, slot + (uint32_t)(qq >> 1), p);
           const uint32_t wa = (qq & 1) ? blk.w2 : blk.w0, wb = (qq & 1) ? blk.w3 : blk.w1;
           double za, zb;
           normal_pair_t(wa, wb, za, zb, T);
