@@ -14,17 +14,20 @@
 int main(int argc, char *argv[])
 {
   const int nparam = 2;
+  int ngpu = 1;
   int ranks = 1, nsamp = 8;
   for (int i = 1; i < argc; ++i) {
     if (!strncmp(argv[i], "--ranks=", 8)) ranks = atoi(argv[i] + 8);
+    else if (!strncmp(argv[i], "--ngpu=", 7)) ngpu = atoi(argv[i] + 7);
     else if (!strncmp(argv[i], "--nsamp=", 8)) nsamp = atoi(argv[i] + 8);
   }
   try {
     DualGaussian L(5.0);
     MCout rslts(nparam, &std::cout, 0);
     MCPar mcpar(nparam, 4, ranks, 0);
+    mcpar.ngpu = ngpu;
     Real pinit[8] = {0.0, 0.0, 2.0, 2.0, 0.0, 1.5, 0.0, -2.0};
-    mcpar.run(nsamp, 500, pinit, L, rslts);
+    if (mcpar.run(nsamp, 500, pinit, L, rslts) != MCPar::OK) return 2;
 
     // per-rank files, as each MPI rank wrote its own (mcpar-dgauss.cc:38-47): rank r's rows
     const int per_rank = rslts.size() / ranks;

@@ -12,10 +12,11 @@
 int main(int argc, char *argv[])
 {
   const int nparam = 2;
-  int nsamp = 100000, ranks = 1, npos = 0;
+  int nsamp = 100000, ranks = 1, npos = 0, ngpu = 1;
   int pool = 0, thin = 1;
   for (int i = 1; i < argc; ++i) {
     if (!strncmp(argv[i], "--ranks=", 8)) ranks = atoi(argv[i] + 8);
+    else if (!strncmp(argv[i], "--ngpu=", 7)) ngpu = atoi(argv[i] + 7);
     else if (!strncmp(argv[i], "--pool=", 7)) pool = atoi(argv[i] + 7);
     else if (!strncmp(argv[i], "--thin=", 7)) thin = atoi(argv[i] + 7);
     else if (npos++ == 0) nsamp = atoi(argv[i]);
@@ -25,9 +26,9 @@ int main(int argc, char *argv[])
     MCout rslts(nparam, &std::cout, 0);
     std::cout << "nsamp = " << nsamp << "\n";
     MCPar mcpar(nparam, 4, ranks, 0);
-    mcpar.pool_m = pool; mcpar.thin = thin;
+    mcpar.pool_m = pool; mcpar.thin = thin; mcpar.ngpu = ngpu;
     Real pinit[8] = {0.0, 0.0, 2.0, 2.0, 0.0, 1.5, 0.0, -2.0};
-    mcpar.run(nsamp, 500, pinit, L, rslts);
+    if (mcpar.run(nsamp, 500, pinit, L, rslts) != MCPar::OK) return 2;
     rslts.output();
   } catch (const char *msg) {
     std::cerr << msg << "\n";

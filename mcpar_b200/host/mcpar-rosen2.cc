@@ -13,9 +13,10 @@
 int main(int argc, char *argv[])
 {
   const int nparam = 16;
-  int nsamp = 10000, ranks = 1, npos = 0, pool = 0, thin = 1;
+  int nsamp = 10000, ranks = 1, npos = 0, pool = 0, thin = 1, ngpu = 1;
   for (int i = 1; i < argc; ++i) {
     if (!strncmp(argv[i], "--ranks=", 8)) ranks = atoi(argv[i] + 8);
+    else if (!strncmp(argv[i], "--ngpu=", 7)) ngpu = atoi(argv[i] + 7);
     else if (!strncmp(argv[i], "--pool=", 7)) pool = atoi(argv[i] + 7);
     else if (!strncmp(argv[i], "--thin=", 7)) thin = atoi(argv[i] + 7);
     else if (npos++ == 0) nsamp = atoi(argv[i]);
@@ -25,7 +26,7 @@ int main(int argc, char *argv[])
     MCout rslts(nparam, &std::cout, 0);
     std::cout << "nsamp = " << nsamp << "\n";
     MCPar mcpar(nparam, 4, ranks, 0);
-    mcpar.pool_m = pool; mcpar.thin = thin;
+    mcpar.pool_m = pool; mcpar.thin = thin; mcpar.ngpu = ngpu;
     // the 2-D demo's four starting points, repeated over the 8 coordinate pairs
     const Real p4[8] = {0.0, 0.0, 2.0, 2.0, 0.0, 1.5, 0.0, -2.0};
     std::vector<Real> pinit(4 * nparam);
@@ -39,7 +40,7 @@ int main(int argc, char *argv[])
       incov[(2 * b) * nparam + 2 * b] = s * 0.5;      incov[(2 * b) * nparam + 2 * b + 1] = s * 1.0;
       incov[(2 * b + 1) * nparam + 2 * b] = s * 1.0;  incov[(2 * b + 1) * nparam + 2 * b + 1] = s * 2.505;
     }
-    mcpar.run(nsamp, 500, &pinit[0], L, rslts, &incov[0]);
+    if (mcpar.run(nsamp, 500, &pinit[0], L, rslts, &incov[0]) != MCPar::OK) return 2;
     rslts.output();
   } catch (const char *msg) {
     std::cerr << msg << "\n";

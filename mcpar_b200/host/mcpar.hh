@@ -3,6 +3,7 @@
 // mpisiz is the number of rank-sized chain groups (nc chains each) and mpirank must be 0.
 #ifndef MCPAR_B200_MCPAR_HH_
 #define MCPAR_B200_MCPAR_HH_
+#include <vector>
 #include "vlfunc.hh"
 #include "mcout.hh"
 
@@ -19,7 +20,11 @@ public:
   int logstep;
 
   // engine options beyond the reference's constructor (set before run())
-  int device;                   // CUDA ordinal
+  int device;                   // CUDA ordinal (of the first GPU)
+  int ngpu;                     // GPUs to shard the rank-sized chain groups over (mpisiz % ngpu == 0 and
+                                // (mpisiz / ngpu) * nc a multiple of 32); the engines exchange their
+                                // (mu, sigma^2) slots peer to peer (mcgpu_p2p_attach_local), replacing
+                                // MPI_Allgather (src/mcpar.cc:127-140).  More engines than devices share devices.
   int pool_m;                   // remote-mixture pool size; 0 = every chain, as the reference
   int thin;                     // keep every thin-th step
   unsigned long long seed;      // Philox key; reference seed by default (mcpar.cc:271)
@@ -35,7 +40,8 @@ public:
 
 private:
   int nparam, nchain, size, rank, tchains;
-  mcgpu_engine *eng;
+  std::vector<mcgpu_engine *> engs;
+  void destroy_engines();
   double mdevice_ms, maccept;
   MCPar(const MCPar &); MCPar &operator=(const MCPar &);
 };

@@ -86,3 +86,21 @@ def test_mcpar_rosen2_d16(tmp_path):
     blk = (2.38 ** 2 / 16) * np.array([[0.5, 1.0], [1.0, 2.505]])
     exp = _engine_rows("rosenbrock1", None, 16, 2, 20, 500, np.kron(np.eye(8), blk))
     assert np.allclose(got, exp, rtol=2e-5, atol=1e-6)
+
+
+def test_mcpar_rosen1_ngpu_equals_single_engine(tmp_path):
+    """--ngpu=2: the ranks are sharded over two engines (two GPUs when the box has them, one shared
+    device otherwise) that exchange their (mu, sigma^2) slots peer to peer inside the window
+    kernels; stdout must be the single-engine run's, row for row."""
+    nsamp, ranks = 40, 16                                                 # 8 ranks x 4 chains = 32 chains per engine
+    outs = []
+    for extra in ([], ["--ngpu=2"]):
+        r = subprocess.run([os.path.join(BIN, "mcpar-rosen1"), str(nsamp), "--ranks=%d" % ranks] + extra, cwd=tmp_path,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout)
+    assert len(outs[0].splitlines()) == 1 + nsamp * 4 * ranks
+    assert outs[0] == outs[1]
+    r = subprocess.run([os.path.join(BIN, "mcpar-rosen1"), "10", "--ranks=3", "--ngpu=2"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 2 and "ngpu" in r.stderr                        # ranks must split evenly, 32-chain blocks
