@@ -363,8 +363,10 @@ def main():
         e.close(); del flush; torch.cuda.empty_cache()
         host_rows = torch.empty((kept_e, Cg, d + 1), dtype=torch.float64).pin_memory().numpy()
         host_pin = torch.from_numpy(np.ascontiguousarray(pin)).pin_memory().numpy()
-        best = None
-        for rep in range(3):
+        host_rows32 = torch.empty((kept_e, Cg, d + 1), dtype=torch.float32).pin_memory().numpy()
+        best = None; best32 = None
+        for rep in range(6):                    # reps 0-2: fp64 sink (the e2e figure); 3-5: fp32 sink (reported beside it)
+            sink_rows = host_rows if rep < 3 else host_rows32
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -375,7 +377,7 @@ def main():
             e.set_likelihood(W["lik"], W["par"]); e.set_covariance(incov_for(args.workload))
             t1 = time.perf_counter()
             e.set_state(host_pin)                                       # H2D inside the timed region
-            e.attach_host_sink(host_rows)                               # D2H drains on a side stream per window
+            e.attach_host_sink(sink_rows)                               # D2H drains on a side stream per window
             runner[0] = make_runner(e)
             burn(nb_e)
             e.sample_begin(ns_e)
@@ -392,15 +394,21 @@ def main():
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             sec = float(tt.item())
-            if best is None or sec < best:
-                best = sec
+            if rep < 3:
+                best = sec if best is None or sec < best else best
+            else:
+                best32 = sec if best32 is None or sec < best32 else best32
         nwin = (nb_e + ns_e) // sync
         e2e = {"value": N * (nb_e + ns_e) / best, "unit": UNIT,
                "h2d_bytes_per_step": int(pin.nbytes // nwin),
                "d2h_bytes_per_step": int((host_rows.nbytes + fin.nbytes) // nwin),
                "job": "set_state(host pinit) + burnin 500 + 1000 steps + history(thin %d) and final logL to pinned host; "
                       "bytes are per 10-step window of the 150-window job; best of 3" % thin,
-               "seconds": best}
+               "seconds": best,
+               "fp32_sink": {"value": N * (nb_e + ns_e) / best32, "seconds": best32,
+                             "d2h_bytes_per_step": int((host_rows32.nbytes + fin.nbytes) // nwin),
+                             "note": "same job with the rows narrowed on the device to fp32, the element type of the "
+                                     "reference's MCout (mcgpu_history_attach_host_f32); compute stays fp64"}}
 
     if rank == 0:
         peak = engine.measure_fp64_peak(local)

@@ -202,12 +202,25 @@ int  mcgpu_history_read(mcgpu_engine *e, int64_t first_step, int64_t count, doub
  * MCout::output/collect do with MPI_Gather, mcout.cc:30-94).  mcgpu_synchronize waits
  * for the drain.  NULL detaches. */
 int  mcgpu_history_attach_host(mcgpu_engine *e, double *rows, size_t capacity_steps);
+/* The same with fp32 rows -- the element type of the reference's MCout (src/mcout.hh:21-23 holds
+ * floats): the rows are narrowed on the device and half the bytes cross PCIe.  The device history
+ * (mcgpu_history_read, maxlike, moments) stays fp64. */
+int  mcgpu_history_attach_host_f32(mcgpu_engine *e, float *rows, size_t capacity_steps);
 /* MCout::maxlike's local part (mcout.cc:96-127): arg-max of logL over the stored
  * history; out = nparam parameters then the value. */
 int  mcgpu_history_maxlike(mcgpu_engine *e, double *out);
 /* posterior moments accumulated over the stored history on the device:
  * mean[d], cov[d][d] over all rows (for checks that cannot afford the D2H). */
 int  mcgpu_history_moments(mcgpu_engine *e, double *mean, double *cov);
+
+/* Checkpoint / restart (NORMAL mode; the reference has none).  The blob holds the chain state, the
+ * running moments, the tuned proposal factor, the counters, the exchange pools and the schedule;
+ * an engine created with the same configuration and likelihood continues the run bit for bit after
+ * load (with a peer-to-peer exchange, all peers restore the same checkpoint).  The sample history
+ * is not part of it: rows kept before the checkpoint must have been read or drained. */
+int  mcgpu_checkpoint_size(mcgpu_engine *e, size_t *bytes);
+int  mcgpu_checkpoint_save(mcgpu_engine *e, void *buf, size_t bytes);
+int  mcgpu_checkpoint_load(mcgpu_engine *e, const void *buf, size_t bytes);
 
 int  mcgpu_get_stats(mcgpu_engine *e, mcgpu_stats *out);
 

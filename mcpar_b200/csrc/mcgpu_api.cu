@@ -79,6 +79,7 @@ struct mcgpu_engine {
 
   // host sink of the sample history: rows drain to it on the side stream as windows finish
   double *sink = nullptr; size_t sink_rows_cap = 0; long long sink_sent = 0; bool sink_registered = false;
+  bool sink_f32 = false; float *hist_f32 = nullptr;       // fp32 sink (the reference's MCout element type): device mirror of the history
   cudaEvent_t sink_ev = nullptr;
 };
 
@@ -281,6 +282,12 @@ int check_overrun(mcgpu_engine *e)
 }
 
 // ---- small utility kernels -------------------------------------------------
+// history rows fp64 -> fp32 for the fp32 host sink (grid-stride)
+__global__ void narrow_rows_kernel(const double *src, float *dst, size_t n)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (float)src[i];
+}
+
 __global__ void argmax_rows_kernel(const double *rows, long long nrows, int ncol, double *best_val, long long *best_row)
 {
   __shared__ double sv[256]; __shared__ long long sr[256];
@@ -533,7 +540,7 @@ int mcgpu_destroy(mcgpu_engine *e)
   void *ptrs[] = {e->x, e->ly, e->mu, e->ps, e->factor, e->counts, e->xchg, e->xflag_d, e->peers_d, e->hist, e->overrun,
                   e->Zd, e->Ud, e->Id, e->ptrial, e->sig, e->mutrial, e->sigtrial, e->musig, e->snap[0], e->snap[1],
                   e->soff, e->cursors, e->irate_d, e->rstats, e->tr_accept, e->tr_remote, e->tr_trial_ly,
-                  e->tr_trial_p, e->tr_cfac, e->tr_iters, e->lik_dev, e->factor_cm, e->diag_d, e->pprep, e->gm_t};
+                  e->tr_trial_p, e->tr_cfac, e->tr_iters, e->lik_dev, e->factor_cm, e->diag_d, e->pprep, e->gm_t, e->hist_f32};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (void *q : e->peer_opened) cudaIpcCloseMemHandle(q);
   for (int i = 0; i < 2; ++i) { if (e->pin[i]) cudaFreeHost(e->pin[i]); if (e->pin_ev[i]) cudaEventDestroy(e->pin_ev[i]); }
@@ -843,6 +850,12 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
       const size_t row_bytes = (size_t)(e->d + 1) * 8 * e->C;
       CK(cudaEventRecord(e->sink_ev, e->stream));
       CK(cudaStreamWaitEvent(e->side, e->sink_ev, 0));
+      if (e->sink_f32) {                                     // narrow on the device, then move half the bytes
+        const size_t n0 = (size_t)e->sink_sent * e->C * (e->d + 1), n = (size_t)(e->hist_kept - e->sink_sent) * e->C * (e->d + 1);
+        narrow_rows_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, e->side>>>(e->hist + n0, e->hist_f32 + n0, n);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync((float*)(void*)e->sink + n0, e->hist_f32 + n0, n * sizeof(float), cudaMemcpyDeviceToHost, e->side));
+      } else
       CK(cudaMemcpyAsync((char*)e->sink + (size_t)e->sink_sent * row_bytes, (const char*)e->hist + (size_t)e->sink_sent * row_bytes,
                          (size_t)(e->hist_kept - e->sink_sent) * row_bytes, cudaMemcpyDeviceToHost, e->side));
       e->sink_sent = e->hist_kept;
@@ -1028,13 +1041,19 @@ int mcgpu_synchronize(mcgpu_engine *e)
   return MCGPU_OK;
 }
 
-int mcgpu_history_attach_host(mcgpu_engine *e, double *rows, size_t capacity_steps)
+static int attach_host_sink(mcgpu_engine *e, void *rows_v, size_t capacity_steps, bool f32);
+
+int mcgpu_history_attach_host(mcgpu_engine *e, double *rows, size_t capacity_steps) { return attach_host_sink(e, rows, capacity_steps, false); }
+int mcgpu_history_attach_host_f32(mcgpu_engine *e, float *rows, size_t capacity_steps) { return attach_host_sink(e, rows, capacity_steps, true); }
+
+static int attach_host_sink(mcgpu_engine *e, void *rows_v, size_t capacity_steps, bool f32)
 {
   if (!e) return MCGPU_EINVAL;
+  double *rows = static_cast<double*>(rows_v);
   DeviceGuard g(e->dev);
   CK(cudaStreamSynchronize(e->side));
   if (e->sink && e->sink_registered) { cudaHostUnregister(e->sink); e->sink_registered = false; }
-  e->sink = nullptr; e->sink_rows_cap = 0;
+  e->sink = nullptr; e->sink_rows_cap = 0; e->sink_f32 = false;
   if (!rows) return MCGPU_OK;
   if (!e->hist) return fail(e, MCGPU_ESTATE, "engine was created with history_steps = 0");
   if ((long long)capacity_steps < e->hist_cap) return fail(e, MCGPU_EINVAL, "host sink smaller than history_steps");
@@ -1042,9 +1061,11 @@ int mcgpu_history_attach_host(mcgpu_engine *e, double *rows, size_t capacity_ste
   const bool pinned = cudaPointerGetAttributes(&at, rows) == cudaSuccess && at.type == cudaMemoryTypeHost;
   cudaGetLastError();
   if (!pinned) {                                           // page-lock the caller's buffer for DMA
-    CK(cudaHostRegister(rows, capacity_steps * (size_t)e->C * (e->d + 1) * 8, cudaHostRegisterDefault));
+    CK(cudaHostRegister(rows, capacity_steps * (size_t)e->C * (e->d + 1) * (f32 ? 4 : 8), cudaHostRegisterDefault));
     e->sink_registered = true;
   }
+  if (f32 && !e->hist_f32) CK(cudaMalloc((void**)&e->hist_f32, (size_t)e->hist_cap * e->C * (e->d + 1) * sizeof(float)));
+  e->sink_f32 = f32;
   if (!e->sink_ev) CK(cudaEventCreateWithFlags(&e->sink_ev, cudaEventDisableTiming));
   e->sink = rows; e->sink_rows_cap = capacity_steps; e->sink_sent = e->hist_kept;
   return MCGPU_OK;
@@ -1234,6 +1255,87 @@ int mcgpu_history_moments(mcgpu_engine *e, double *mean, double *cov)
   int q = d;
   for (int i = 0; i < d; ++i)
     for (int j = i; j < d; ++j, ++q) { const double c = h[q] / n - mean[i] * mean[j]; cov[i * d + j] = c; cov[j * d + i] = c; }
+  return MCGPU_OK;
+}
+
+// ---- checkpoint / restart ---------------------------------------------------------------------
+// Everything a NORMAL-mode engine needs to continue a run bit for bit: chain state, running moments,
+// the tuned proposal factor, tuning / statistics counters, the exchange pools and the schedule.
+// The sample history is not part of it (rows kept so far must have been read or drained).
+namespace {
+struct CkptHeader {
+  char magic[8]; int32_t abi, d, lik, wide, M, sync, thin, coin_group; int64_t C, N, chain0, ld;
+  int64_t burn_done, t_main, npub; int32_t nsamp, irate, nburn_total, sampling, tune_pending, have_factor;
+  uint64_t seed; double pl;
+};
+size_t ckpt_bytes(const mcgpu_engine *e)
+{
+  return sizeof(CkptHeader) + ((size_t)3 * e->d * e->ld + e->ld + (size_t)e->d * e->d) * 8 + 8 * 8 + 3 * e->pool_bytes;
+}
+}  // namespace
+
+int mcgpu_checkpoint_size(mcgpu_engine *e, size_t *bytes)
+{
+  if (!e || !bytes) return MCGPU_EINVAL;
+  if (e->verify || e->replay_local) return fail(e, MCGPU_ESTATE, "checkpoints exist in NORMAL mode only");
+  *bytes = ckpt_bytes(e);
+  return MCGPU_OK;
+}
+
+int mcgpu_checkpoint_save(mcgpu_engine *e, void *buf, size_t bytes)
+{
+  if (!e || !buf) return MCGPU_EINVAL;
+  if (e->verify || e->replay_local) return fail(e, MCGPU_ESTATE, "checkpoints exist in NORMAL mode only");
+  if (bytes < ckpt_bytes(e)) return fail(e, MCGPU_EINVAL, "checkpoint buffer too small (mcgpu_checkpoint_size)");
+  if (!e->have_state) return fail(e, MCGPU_ESTATE, "nothing to save: set_state first");
+  if (e->exchange_pending) return fail(e, MCGPU_ESTATE, "finish the pending exchange first");
+  DeviceGuard g(e->dev);
+  CkptHeader h; memset(&h, 0, sizeof h);
+  memcpy(h.magic, "MCGPUCK1", 8);
+  h.abi = MCGPU_ABI_VERSION; h.d = e->d; h.lik = e->lik; h.wide = e->wide; h.M = e->M; h.sync = e->cfg.sync; h.thin = e->cfg.thin;
+  h.coin_group = e->cfg.coin_group; h.C = e->C; h.N = e->N; h.chain0 = e->cfg.chain0; h.ld = e->ld;
+  h.burn_done = e->burn_done; h.t_main = e->t_main; h.npub = e->npub; h.nsamp = e->nsamp; h.irate = e->irate;
+  h.nburn_total = e->nburn_total; h.sampling = e->sampling; h.tune_pending = e->tune_pending; h.have_factor = e->have_factor;
+  h.seed = e->cfg.seed; h.pl = e->cfg.pl;
+  char *q = static_cast<char*>(buf);
+  memcpy(q, &h, sizeof h); q += sizeof h;
+  const size_t ns = (size_t)e->d * e->ld * 8;
+  struct { const void *src; size_t n; } parts[] = {{e->x, ns}, {e->mu, ns}, {e->ps, ns}, {e->ly, (size_t)e->ld * 8},
+                                                   {e->factor, (size_t)e->d * e->d * 8}, {e->counts, 64}, {e->xchg, 3 * e->pool_bytes}};
+  for (auto &pt : parts) { CK(cudaMemcpyAsync(q, pt.src, pt.n, cudaMemcpyDeviceToHost, e->stream)); q += pt.n; }
+  CK(cudaStreamSynchronize(e->stream));
+  return MCGPU_OK;
+}
+
+int mcgpu_checkpoint_load(mcgpu_engine *e, const void *buf, size_t bytes)
+{
+  if (!e || !buf) return MCGPU_EINVAL;
+  if (e->verify || e->replay_local) return fail(e, MCGPU_ESTATE, "checkpoints exist in NORMAL mode only");
+  if (e->lik < 0) return fail(e, MCGPU_ESTATE, "set_likelihood first (the likelihood is not part of a checkpoint)");
+  if (bytes < ckpt_bytes(e)) return fail(e, MCGPU_EINVAL, "checkpoint truncated");
+  CkptHeader h; memcpy(&h, buf, sizeof h);
+  if (memcmp(h.magic, "MCGPUCK1", 8) || h.abi != MCGPU_ABI_VERSION) return fail(e, MCGPU_EINVAL, "not a checkpoint of this ABI");
+  if (h.d != e->d || h.C != e->C || h.N != e->N || h.chain0 != e->cfg.chain0 || h.ld != e->ld || h.M != e->M || h.lik != e->lik ||
+      h.wide != (int)e->wide || h.sync != e->cfg.sync || h.thin != e->cfg.thin || h.coin_group != e->cfg.coin_group ||
+      h.seed != e->cfg.seed || h.pl != e->cfg.pl)
+    return fail(e, MCGPU_EINVAL, "checkpoint was taken by an engine of a different shape / likelihood / seed");
+  const long long need = ((long long)h.nsamp + e->cfg.thin - 1) / e->cfg.thin;
+  if (h.sampling && e->hist && need > e->hist_cap) return fail(e, MCGPU_EINVAL, "history_steps too small for the checkpointed run");
+  DeviceGuard g(e->dev);
+  const char *q = static_cast<const char*>(buf) + sizeof h;
+  const size_t ns = (size_t)e->d * e->ld * 8;
+  struct { void *dst; size_t n; } parts[] = {{e->x, ns}, {e->mu, ns}, {e->ps, ns}, {e->ly, (size_t)e->ld * 8},
+                                             {e->factor, (size_t)e->d * e->d * 8}, {e->counts, 64}, {e->xchg, 3 * e->pool_bytes}};
+  for (auto &pt : parts) { CK(cudaMemcpyAsync(pt.dst, q, pt.n, cudaMemcpyHostToDevice, e->stream)); q += pt.n; }
+  if (e->p2p) {   // peers restore the same epoch: every publication up to npub counts as arrived
+    const unsigned long long arrived = (unsigned long long)e->M * arrivals_per_slot(e) * (unsigned long long)h.npub;
+    CK(cudaMemcpyAsync(e->xchg + 3 * e->pool_bytes, &arrived, sizeof arrived, cudaMemcpyHostToDevice, e->stream));
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  e->burn_done = h.burn_done; e->t_main = h.t_main; e->npub = h.npub; e->nsamp = h.nsamp; e->irate = h.irate;
+  e->nburn_total = h.nburn_total; e->sampling = h.sampling != 0; e->tune_pending = h.tune_pending != 0;
+  e->have_factor = h.have_factor != 0; e->have_state = true; e->exchange_pending = false;
+  e->hist_kept = (e->t_main + e->cfg.thin - 1) / e->cfg.thin; e->sink_sent = e->hist_kept;
   return MCGPU_OK;
 }
 

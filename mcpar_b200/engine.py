@@ -25,7 +25,9 @@ EXPORTS = [
     "mcgpu_exchange_begin", "mcgpu_exchange_end", "mcgpu_p2p_export", "mcgpu_p2p_attach",
     "mcgpu_p2p_attach_local", "mcgpu_burnin_group", "mcgpu_tuning_counters", "mcgpu_burnin_some",
     "mcgpu_tune", "mcgpu_synchronize", "mcgpu_get_state", "mcgpu_get_factor", "mcgpu_get_musig",
-    "mcgpu_get_trace", "mcgpu_history_read", "mcgpu_history_attach_host", "mcgpu_history_maxlike", "mcgpu_history_moments",
+    "mcgpu_get_trace", "mcgpu_history_read", "mcgpu_history_attach_host", "mcgpu_history_attach_host_f32",
+    "mcgpu_history_maxlike", "mcgpu_history_moments",
+    "mcgpu_checkpoint_size", "mcgpu_checkpoint_save", "mcgpu_checkpoint_load",
     "mcgpu_get_stats", "mcgpu_device_ptr", "mcgpu_loglik", "mcgpu_qriguess",
     "mcgpu_measure_fp64_peak",
 ]
@@ -307,15 +309,17 @@ class Engine:
         return rows
 
     def attach_host_sink(self, rows):
-        """rows: C-contiguous float64 [capacity_steps][nchain][nparam+1] host array (kept alive
-        by the caller); subsequent sample() calls drain into it asynchronously."""
+        """rows: C-contiguous float64 (or float32: the reference's MCout element type; narrowed on the
+        device) [capacity_steps][nchain][nparam+1] host array (kept alive by the caller); subsequent
+        sample() calls drain into it asynchronously."""
         if rows is None:
             self._ck(self.lib.mcgpu_history_attach_host(self.h, None, C.c_size_t(0)))
             self._sink = None
             return
-        assert rows.dtype == np.float64 and rows.flags.c_contiguous and rows.shape[1:] == (self.C, self.d + 1)
+        assert rows.dtype in (np.float64, np.float32) and rows.flags.c_contiguous and rows.shape[1:] == (self.C, self.d + 1)
         self._sink = rows
-        self._ck(self.lib.mcgpu_history_attach_host(self.h, _p(rows), C.c_size_t(rows.shape[0])))
+        fn = self.lib.mcgpu_history_attach_host if rows.dtype == np.float64 else self.lib.mcgpu_history_attach_host_f32
+        self._ck(fn(self.h, _p(rows), C.c_size_t(rows.shape[0])))
 
     def maxlike(self):
         out = np.empty(self.d + 1)
@@ -326,6 +330,19 @@ class Engine:
         mean = np.empty(self.d); cov = np.empty((self.d, self.d))
         self._ck(self.lib.mcgpu_history_moments(self.h, _p(mean), _p(cov)))
         return mean, cov
+
+    # -- checkpoint / restart -------------------------------------------------
+    def checkpoint(self):
+        """Opaque blob (numpy uint8) from which an engine of the same configuration continues bit for bit."""
+        n = C.c_size_t()
+        self._ck(self.lib.mcgpu_checkpoint_size(self.h, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        self._ck(self.lib.mcgpu_checkpoint_save(self.h, _p(buf), n))
+        return buf
+
+    def restore(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._ck(self.lib.mcgpu_checkpoint_load(self.h, _p(blob), C.c_size_t(blob.size)))
 
     def stats(self):
         s = Stats()

@@ -474,20 +474,22 @@ def test_qriguess_matches_oracle():
         eng.qriguess(0, 4, 17, [0] * 17, [1] * 17)
 
 
-def test_host_sink_receives_the_history():
-    """mcgpu_history_attach_host: rows drained on the side stream during sampling equal a read-back."""
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_host_sink_receives_the_history(dtype):
+    """mcgpu_history_attach_host[_f32]: rows drained on the side stream during sampling equal a
+    read-back (fp32 sink: the read-back narrowed to the reference MCout's element type)."""
     eng = _engine()
     N, nsamp, thin = 4096, 120, 4
     e = eng.Engine(2, N, mode="normal", coin_group=0, pool_m=8, thin=thin, history_steps=nsamp // thin)
     e.set_likelihood("dualgaussian", [5.0]); e.set_covariance(None); e.set_state(tiled_pinit(N, 2))
     e.burnin(60)
-    sink = np.full((nsamp // thin, N, 3), np.nan)
+    sink = np.full((nsamp // thin, N, 3), np.nan, dtype=dtype)
     e.attach_host_sink(sink)
     e.sample_begin(nsamp)
     for _ in range(nsamp // 10):
         e.sample(10)
     e.synchronize()
-    assert np.array_equal(sink, e.history())
+    assert np.array_equal(sink, e.history().astype(dtype))
     e.attach_host_sink(None)
     e.close()
 
