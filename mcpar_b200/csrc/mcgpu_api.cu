@@ -1331,6 +1331,7 @@ int mcgpu_checkpoint_load(mcgpu_engine *e, const void *buf, size_t bytes)
     const unsigned long long arrived = (unsigned long long)e->M * arrivals_per_slot(e) * (unsigned long long)h.npub;
     CK(cudaMemcpyAsync(e->xchg + 3 * e->pool_bytes, &arrived, sizeof arrived, cudaMemcpyHostToDevice, e->stream));
   }
+  if (e->wide) { ++e->launches; CK(fast::launch_factor_prep(e->factor, e->factor_cm, e->d, e->diag_d, e->stream)); }   // derived copies
   CK(cudaStreamSynchronize(e->stream));
   e->burn_done = h.burn_done; e->t_main = h.t_main; e->npub = h.npub; e->nsamp = h.nsamp; e->irate = h.irate;
   e->nburn_total = h.nburn_total; e->sampling = h.sampling != 0; e->tune_pending = h.tune_pending != 0;

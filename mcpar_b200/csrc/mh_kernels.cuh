@@ -228,25 +228,28 @@ __constant__ unsigned c_stride_mask[33] = {0u,
 // lg2.approx |err| <= 2^-22 absolute on [0.5, 2] (2 ulp elsewhere); sin/cos.approx |err| <= 2^-20.9 on
 // [-pi, pi]; sqrt.approx and ex2.approx 2 ulp.
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sin_approx(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float cos_approx(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // fp32 image of the Box-Muller pair of normal_pair_t (same words, same convention).  Returns a bound on
 // the absolute error of both normals:
 //   L = -2 ln v:  |dL| <= 1.39 dlg2 + 2.4e-7 (1 + L) <= 1.6e-6, with dlg2 = 1e-6 (4x the documented bound);
-//   r = sqrt L:   |dr| <= dL / (r~ + r) + 2e-7 r, and never more than sqrt(dL) = 1.3e-3;
+//   r = sqrt L = L rsqrt(L):   |dr| <= dL / (r~ + r) + 3e-7 r, and never more than sqrt(dL) = 1.3e-3 (below
+//   r = 1.3e-3 the capped 1/r makes r~ = 770 L <= r, still within 1.3e-3 of it);
 //   angle 2 pi (a - 1/2), |a - 1/2| <= 1/2: argument error <= 8e-7, sin/cos error <= 2e-6 (the
 //   approximation's 5.1e-7 tripled, plus the argument's);  z = r trig:  |dz| <= dr + r (2e-6 + 1.2e-7)
-//   <= 1.7e-6 / (r~ + 1.3e-3) + 2.4e-6 r~   (r~ >= 1.3e-3 or not).
+//   <= 1.7e-6 min(1/r~, 770) + 2.4e-6 r~.
 __device__ __forceinline__ float normal_pair_f32(uint32_t wa, uint32_t wb, float &z0, float &z1, float &lg)
 {
   const float v = ((float)wa + 1.0f) * 2.3283064365386963e-10f;                 // (0, 1]
   lg = lg2_approx(v);                                                           // = -(z0^2 + z1^2)/2 * log2(e), in [-32, 0]
-  const float r = sqrt_approx(-1.3862943611198906f * lg);
+  const float L = -1.3862943611198906f * lg;
+  const float rs = fminf(rsqrt_approx(L), 770.0f);                              // 1/r, capped at 1/1.3e-3 (also L = 0: inf)
+  const float r = L * rs;                                                       // sqrt L (2 ulp + the cap, which only bites below r = 1.3e-3)
   const float ang = 6.283185307179586f * ((float)wb * 2.3283064365386963e-10f - 0.5f);   // 2 pi u - pi in [-pi, pi]
   z0 = -r * sin_approx(ang); z1 = -r * cos_approx(ang);                         // sin(t + pi) = -sin t, cos(t + pi) = -cos t
-  return fmaf(2.4e-6f, r, __fdividef(1.7e-6f, r + 1.3e-3f));
+  return fmaf(2.4e-6f, r, 1.7e-6f * rs);
 }
 
 // One candidate of the remote rejection loop (genRemote, mcpar.cc:331-409), decision only: draw the
@@ -298,7 +301,9 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
     }
   }
   const float theta = (1.9e-7f * (mu_max + xabs) + zerr * sgmax) * isig_max;
-  const double eps = 1.0e-4 + 1.0e-5 * (double)D + 2.0e-5 * (double)M + (double)(theta * (21.3f * sqrtf((float)D)));
+  // the comparison itself runs in fp32 as well: u rounded to fp32 and three fp32 roundings add < 3e-7 to eps
+  const float epsf = (1.01e-4f + 1.0e-5f * (float)D) + 2.0e-5f * (float)M + theta * (21.3f * sqrtf((float)D));
+  const double eps = (double)epsf;
   if constexpr (D <= 4) {
     // Exponents are taken relative to the picked component's own a_c = log2 v (>= -32 per normal pair), which
     // the Box-Muller step already has: 2^(a_s - a_c) <= 2^64 cannot overflow, so the sum needs no running
@@ -321,9 +326,9 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
       }
     }
     if (mr + ref > -14.0f && theta < 2.0e-3f && !p.exact_tests) {   // max a > -9.7: then FPEPS/qmax < 2e-10 (mcpar.cc:357-358 offsets)
-      const double Sd = (double)S, Ed = (double)ex2_approx(mr);     // R = S / E
-      if (u * (Sd * (1.0 + eps) + 3.0e-10 * Ed) < Ed) return true;  // u < r_lo
-      if (u * (Sd * (1.0 - eps)) >= Ed) return false;               // u >= r_hi
+      const float uf = (float)u, E = ex2_approx(mr);                // R = S / E
+      if (uf * fmaf(S, 1.0f + epsf, 3.0e-10f * E) < E) return true;  // u < r_lo
+      if (uf * (S * (1.0f - epsf)) >= E) return false;               // u >= r_hi
     }
   } else {
     float m = -INFINITY;                               // running max of a_s * log2(e)

@@ -66,8 +66,13 @@ def test_checkpoint_rejects_a_different_engine():
     with pytest.raises(eng.McgpuError):
         b.restore(blob)                                # likelihood first
     b.set_likelihood("rosenbrock1")
+    with pytest.raises(eng.McgpuError, match="truncated|different shape"):
+        b.restore(blob)                                # an engine of another size
+    d = eng.Engine(2, 256, pool_m=8, seed=7)
+    d.set_likelihood("rosenbrock1")
     with pytest.raises(eng.McgpuError, match="different shape"):
-        b.restore(blob)
+        d.restore(blob)                                # same size, another seed
+    d.close()
     c = eng.Engine(2, 256, pool_m=8)
     c.set_likelihood("rosenbrock1")
     with pytest.raises(eng.McgpuError):
