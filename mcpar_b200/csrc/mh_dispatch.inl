@@ -5,7 +5,7 @@
 static int step_block()
 {
   static int b = 0;
-  if (!b) { const char *e = getenv("MCGPU_BLOCK"); b = e ? atoi(e) : 64; if (b != 32 && b != 64 && b != 128) b = 64; }
+  if (!b) { const char *e = getenv("MCGPU_BLOCK"); b = e ? atoi(e) : 128; if (b != 32 && b != 64 && b != 128) b = 128; }
   return b;
 }
 

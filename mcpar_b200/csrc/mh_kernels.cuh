@@ -19,7 +19,7 @@
 #include "mcgpu_device.cuh"
 #include "../../include/mcgpu.h"
 #ifndef MCGPU_EXACT_TU
-#define MCGPU_TABLE_QUAL static __device__
+#define MCGPU_TABLE_QUAL static __device__ __align__(16)
 #include "mcgpu_tables.h"
 #else
 #define MCGPU_64_OVER_LN2 0.0
@@ -49,6 +49,19 @@ enum { RNG_PHILOX = 0, RNG_REPLAY = 1 };
 #define MC_EXP(x) mc_exp((x), T)
 #define MC_LOG(x) mc_log((x), T)
 #define MCGPU_MATH_SMEM (MCGPU_EXP_TAB + 2 * MCGPU_LOG_TAB + 2 * MCGPU_TRIG_TAB)   /* doubles */
+#endif
+
+#ifndef MCGPU_EXACT_TU
+// copy the exp / log / trig tables (3.5 KB) into shared memory, 16 bytes per access
+__device__ __forceinline__ void stage_math_tables(double *smem)
+{
+  double2 *d = reinterpret_cast<double2 *>(smem);
+  const double2 *e = reinterpret_cast<const double2 *>(MCGPU_EXP_TABLE), *l = reinterpret_cast<const double2 *>(MCGPU_LOG_TABLE),
+                *t = reinterpret_cast<const double2 *>(MCGPU_TRIG_TABLE);
+  for (int i = threadIdx.x; i < MCGPU_EXP_TAB / 2; i += blockDim.x) d[i] = e[i];
+  for (int i = threadIdx.x; i < MCGPU_LOG_TAB; i += blockDim.x) d[MCGPU_EXP_TAB / 2 + i] = l[i];
+  for (int i = threadIdx.x; i < MCGPU_TRIG_TAB; i += blockDim.x) d[MCGPU_EXP_TAB / 2 + MCGPU_LOG_TAB + i] = t[i];
+}
 #endif
 
 // Box-Muller pair, MKL BOXMULLER2 convention: z0 = r sin(2 pi u2), z1 = r cos(2 pi u2)
@@ -420,7 +433,7 @@ mh_steps_kernel(const StepParams p)
 {
   constexpr bool MAIN = PHASE != PH_BURN;
   constexpr bool CAN_REMOTE = RNGK == RNG_PHILOX && (PHASE == PH_MIXED || PHASE == PH_REMOTE);
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ unsigned char s_rank[4][32];               // per warp: lanes of the chains still in the remote loop
   __shared__ unsigned int s_stat[2];                    // remote chain-steps of this CTA and the candidates they tried
   __shared__ unsigned int s_itacc[128];                 // per chain: index of the accepted candidate of the current remote step
@@ -436,9 +449,7 @@ mh_steps_kernel(const StepParams p)
   MathTables T;
 #ifndef MCGPU_EXACT_TU
   T.exp_tab = smem; T.log_tab = smem + MCGPU_EXP_TAB; T.trig_tab = T.log_tab + 2 * MCGPU_LOG_TAB;
-  for (int i = threadIdx.x; i < MCGPU_EXP_TAB; i += blockDim.x) smem[i] = MCGPU_EXP_TABLE[i];
-  for (int i = threadIdx.x; i < 2 * MCGPU_LOG_TAB; i += blockDim.x) smem[MCGPU_EXP_TAB + i] = MCGPU_LOG_TABLE[i];
-  for (int i = threadIdx.x; i < 2 * MCGPU_TRIG_TAB; i += blockDim.x) smem[MCGPU_EXP_TAB + 2 * MCGPU_LOG_TAB + i] = MCGPU_TRIG_TABLE[i];
+  stage_math_tables(smem);
 #else
   T.exp_tab = T.log_tab = T.trig_tab = nullptr;
 #endif

@@ -188,13 +188,11 @@ mh_wide_kernel(const WideParams p)
   constexpr int L = D / 2;                      // lanes per group
   constexpr bool MAIN = PHASE != PH_BURN;
   constexpr int ABLK = (2 * L) / 4, AW = (2 * L) % 4;     // accept uniform: word 2*NP (NP = L pairs) of the local stream
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   // smem: math tables | per group of the CTA: staged points sx[D][NCH] and staged normals sz[D][NCH]
   MathTables T;
   T.exp_tab = smem; T.log_tab = smem + MCGPU_EXP_TAB; T.trig_tab = T.log_tab + 2 * MCGPU_LOG_TAB;
-  for (int i = threadIdx.x; i < MCGPU_EXP_TAB; i += blockDim.x) smem[i] = MCGPU_EXP_TABLE[i];
-  for (int i = threadIdx.x; i < 2 * MCGPU_LOG_TAB; i += blockDim.x) smem[MCGPU_EXP_TAB + i] = MCGPU_LOG_TABLE[i];
-  for (int i = threadIdx.x; i < 2 * MCGPU_TRIG_TAB; i += blockDim.x) smem[MCGPU_EXP_TAB + 2 * MCGPU_LOG_TAB + i] = MCGPU_TRIG_TABLE[i];
+  stage_math_tables(smem);
   const int gib = threadIdx.x / L;              // group within the CTA
   double *sx = smem + MCGPU_MATH_SMEM + (size_t)gib * 2 * D * NCH;
   double *sz = sx + D * NCH;

@@ -11,7 +11,7 @@ rows = list(csv.reader(out.splitlines()))
 fname = None; hdr = None; acc = []
 for r in rows:
     if not r: continue
-    if r[0] == "File Name": fname = r[1].split("/")[-1]; continue
+    if r[0] in ("File Name", "File Path"): fname = r[1].split("/")[-1]; continue
     if r[0] == "Line No": hdr = r; continue
     if r[0] == "Kernel Name": print("#", r[1][:110]); continue
     if hdr and r[0].isdigit():
