@@ -405,6 +405,7 @@ int prepare_lik(int lik, int d, const double *par, int npar, double lp[8], std::
     case MCGPU_DUALGAUSSIAN:
       if (d != 2) { err = "DualGaussian has two parameters"; return MCGPU_EINVAL; }
       lp[0] = (par && npar >= 1) ? par[0] : 5.0;
+      lp[1] = log(lp[0]);                                   // the production kernels evaluate the sum in log-sum-exp form
       return 0;
     case MCGPU_GAUSSMIX: {
       if (!par || npar < 1) { err = "GaussMix needs par = K, mu, sig2, w"; return MCGPU_EINVAL; }

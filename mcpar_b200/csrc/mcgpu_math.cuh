@@ -74,8 +74,11 @@ static const double mc_coef_host[] = {MCGPU_COEF_LIST};
 // x > 709 gives +inf; NaN propagates.
 MCGPU_HD double mc_exp(double x, const MathTables &T)
 {
-  if (x < MCK(27)) return 0.0;
-  if (x > MCK(28)) return INFINITY;
+  if (((unsigned)mc_hi(x) & 0x7fffffffu) >= 0x40862000u) {   // |x| >= 708, inf or NaN: one integer test on the fast path
+    if (x < MCK(27)) return 0.0;
+    if (x > MCK(28)) return INFINITY;
+    if (x != x) return x;
+  }
   const double nd = fma(x, MCK(0), MCK(3));
   const int n = mc_lo(nd);
   const double nf = nd - MCK(3);

@@ -116,7 +116,19 @@ template <> struct Lik<MCGPU_DUALGAUSSIAN, 2> {
     const double arg1 = 0.5 * (x[0] * x[0] + x[1] * x[1]);
     const double t2a = x[0] - 5.0, t2b = x[1] - 5.0;
     const double arg2 = 0.5 * (t2a * t2a + t2b * t2b);
+#ifdef MCGPU_EXACT_TU
     return MC_LOG(p.lp[0] * MC_EXP(-arg1) + MC_EXP(-arg2));
+#else
+    // the same value with one exponential instead of two:  log(w e^-a1 + e^-a2) = M + log(1 + e^-|t1 - t2|),
+    // t1 = log w - a1, t2 = -a2, M = max(t1, t2)  (lp[1] = log w, set on the host).  A term whose
+    // exponential the two-exp form flushes to zero (a > 708) is dropped here too, and
+    // with both dropped the result is log(0) = -inf, as in the reference.
+    const double t1 = arg1 > 708.0 ? -INFINITY : p.lp[1] - arg1;
+    const double t2 = arg2 > 708.0 ? -INFINITY : -arg2;
+    const double M = fmax(t1, t2);
+    const double r = M + MC_LOG(1.0 + MC_EXP(-fabs(t1 - t2)));    // NaN when both terms are dropped
+    return M > -INFINITY ? r : -INFINITY;
+#endif
   }
 };
 

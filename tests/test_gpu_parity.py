@@ -239,6 +239,15 @@ def test_normal_mode_matches_counter_oracle(lik, d, N, par, pool_m, pl, cg):
     # accept pattern of the main phase from the history: a row changed iff accepted
     same_state = np.all(np.isclose(h[:, :, :d], o["rows"][:, :, :d], rtol=1e-7, atol=1e-9), axis=-1)
     assert same_state.mean() > 0.999, "trajectories diverged: %.4f agree" % same_state.mean()
+    # log-likelihood column of the rows whose state agrees: the kernels' table-driven fp64 math (and the
+    # one-exponential form of DualGaussian) against the host libm evaluation of the reference's formula
+    ll, lo = h[:, :, d][same_state], o["rows"][:, :, d][same_state]
+    fin = np.isfinite(lo)
+    assert np.array_equal(np.isfinite(ll), fin)
+    assert np.allclose(ll[fin], lo[fin], rtol=1e-7, atol=1e-9)
+    tight = np.isclose(h[:, :, :d], o["rows"][:, :, :d], rtol=0, atol=0).all(axis=-1) & same_state   # bit-equal states
+    if tight.any():
+        assert _close(h[:, :, d][tight], o["rows"][:, :, d][tight], rtol=1e-12, atol=1e-13)
     assert np.allclose(st["p"], o["p"], rtol=1e-6, atol=1e-8) or same_state[-1].mean() > 0.995
     assert np.allclose(e.factor(), o["cov"]), "global burn-in tuning differs"
     s = e.stats()
