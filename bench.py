@@ -375,10 +375,13 @@ def main():
                               seed=SEED, pool_m=args.pool, thin=thin, coin_group=args.coin_group, history_steps=kept_e, device=local)
             e.set_stream(stream.cuda_stream)
             e.set_likelihood(W["lik"], W["par"]); e.set_covariance(incov_for(args.workload))
+            runner[0] = make_runner(e)                                  # construction: engines + their exchange wiring
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
             t1 = time.perf_counter()
             e.set_state(host_pin)                                       # H2D inside the timed region
             e.attach_host_sink(sink_rows)                               # D2H drains on a side stream per window
-            runner[0] = make_runner(e)
             burn(nb_e)
             e.sample_begin(ns_e)
             for _ in range(ns_e // sync):
