@@ -576,8 +576,8 @@ int mcgpu_set_likelihood(mcgpu_engine *e, int lik, const double *par, int npar)
     if (!can_wide && !fast::steps_supported(lik, e->d)) return fail(e, MCGPU_EINVAL, "no step kernel instantiated for this (likelihood, nparam)");
     if (e->have_state && can_wide != e->wide) return fail(e, MCGPU_ESTATE, "likelihood change would change the state layout: create a new engine");
     e->wide = can_wide;
-    if (!e->wide && e->cfg.pl < 1.0 && (size_t)e->M * e->d * 24 + (size_t)(e->d * e->d + e->cfg.sync) * 8 > 200 * 1024)
-      return fail(e, MCGPU_EINVAL, "remote-mixture pool does not fit in shared memory: choose pool_m with pool_m*nparam <= 8192");
+    if (!e->wide && e->cfg.pl < 1.0 && fast::steps_smem_bytes(e->d, e->cfg.sync, e->M, true) > 200 * 1024)
+      return fail(e, MCGPU_EINVAL, "remote-mixture pool does not fit in shared memory (40 bytes per slot and parameter): choose pool_m with pool_m*nparam <= 5000");
   }
   if (e->lik_dev) { cudaFree(e->lik_dev); e->lik_dev = nullptr; }
   if (!dev.empty()) {

@@ -35,9 +35,6 @@ namespace mcgpu {
 namespace MCGPU_NS {
 
 enum { RNG_PHILOX = 0, RNG_REPLAY = 1 };
-#ifndef MCGPU_EXP_NOCOUNT
-#define MCGPU_EXP_NOCOUNT 0
-#endif
 
 // transcendental calls of the step kernels: table-driven routines in the production
 // unit, CUDA libm in the exact (verification) unit
@@ -408,11 +405,8 @@ enum { PH_BURN = 0, PH_MIXED = 1, PH_LOCAL = 2, PH_REMOTE = 3 };
 // Stage the exchange pool [M][D][2] (mu, sigma^2) into shared memory as (mu, -1/(2 sigma^2)) pairs + sigma.
 // With a peer-to-peer exchange the CTA first waits until the pool has arrived from every GPU.  Out of
 // line: it runs once per launch from inside the step loop, whose register allocation it must not disturb.
-#ifndef MCGPU_STAGE_QUAL
-#define MCGPU_STAGE_QUAL __noinline__
-#endif
 template <int D>
-__device__ MCGPU_STAGE_QUAL void stage_pool(const double *pool_cur, int pool_m, const unsigned long long *arrivals,
+__device__ __noinline__ void stage_pool(const double *pool_cur, int pool_m, const unsigned long long *arrivals,
                                         unsigned long long wait_target, int *xflag, double2 *sPmh, double *sPs,
                                         float2 *sPf, float2 *sSf, float *s_scal, int Mpad)
 {
@@ -625,7 +619,7 @@ mh_steps_kernel(const StepParams p)
         for (int i = 0; i < D; ++i) xt[i] = xz[i];
       }
       if constexpr (CAN_REMOTE) {
-        if (!MCGPU_EXP_NOCOUNT && rm0) {                // statistics: remote chain-steps and the iterations the reference's
+        if (rm0) {                // statistics: remote chain-steps and the iterations the reference's
           unsigned wi = (rm0 >> lane) & 1u ? s_itacc[threadIdx.x] + 1u : 0u;   // loop (mcpar.cc:331-409) would have run for them
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) wi += __shfl_xor_sync(0xffffffffu, wi, o);

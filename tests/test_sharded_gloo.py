@@ -107,3 +107,59 @@ def test_pool_slot_rule():
     assert pool_slots(0, 64, 64, 0) == (0, 64, 64, 1)
     with pytest.raises(ValueError):
         check_even_pool(Shard(0, 3, 64), 16)
+
+
+class FakeP2PEngine(FakeEngine):
+    """The same stand-in with the peer-to-peer protocol of mcgpu_p2p_*: handles are exported and
+    attached in rank order, after which sample() may cross window boundaries and the runner must
+    not call the exchange entry points."""
+    p2p = False
+
+    def p2p_export(self):
+        return bytes([self.sh.rank]) * 64
+
+    def p2p_attach(self, world, rank, handles):
+        assert world == self.sh.world and rank == self.sh.rank and len(handles) == world
+        assert [h[0] for h in handles] == list(range(world)) and all(len(h) == 64 for h in handles)
+        self.p2p = True
+
+    def sample(self, n):
+        assert self.p2p
+        self.t += n
+
+    def exchange_begin(self):
+        raise AssertionError("the peer-to-peer exchange needs no host-side exchange call")
+
+
+def _worker_p2p(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        e = FakeP2PEngine(Shard(rank, world, 64), 16, 2, 10)
+        r = ShardedRunner(e, DistGroup(dist), lambda buf: buf.t)
+
+        def gather_bytes(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        r.enable_p2p(rank, world, gather_bytes)
+        r.burnin(60)
+        r.sample(35, 10)
+        q.put((rank, e.p2p, e.t, [t.tolist() for t in e.tuned]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_runner_p2p_wiring_over_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker_p2p, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    for rank, p2p, t, tuned in res:
+        assert p2p and t == 35
+        assert tuned == [[52 * 1 + 52 * 2, 52 * 64 * 2]]          # burn-in tuning still sums the counters over ranks
