@@ -6,7 +6,7 @@
 
 MCout::MCout(int np, std::ostream *aoutstream, MCComm)
   : maxlparams(np), maxlval(-std::numeric_limits<Real>::infinity()), mnparam(np), mncol(np + 1),
-    next(0), npset(0), maxsamps(0), nextout(0), outstream(aoutstream)
+    next(0), npset(0), maxsamps(0), nextout(0), outstream(aoutstream), mformat(TEXT), wrote_header(false)
 {
 }
 
@@ -42,7 +42,15 @@ void MCout::output()
   size_t ntot = 0;
   Real *buf = collect(&ntot);
   if (!buf) return;
-  if (outstream) {
+  if (outstream && mformat == BINARY) {
+    std::ostream &os = *outstream;
+    if (!wrote_header) {
+      const int hdr[2] = {mncol, (int)sizeof(Real)};
+      os.write("MCOUTB01", 8); os.write(reinterpret_cast<const char *>(hdr), sizeof hdr);
+      wrote_header = true;
+    }
+    os.write(reinterpret_cast<const char *>(buf), (std::streamsize)(ntot * sizeof(Real)));
+  } else if (outstream) {
     std::ostream &os = *outstream;
     const size_t nrow = ntot / (size_t)mncol;
     for (size_t r = 0; r < nrow; ++r) {

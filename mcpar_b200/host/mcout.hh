@@ -19,7 +19,14 @@ class MCout {
   size_t npset, maxsamps;
   size_t nextout;                                      // first element not yet output
   std::ostream *outstream;
+  int mformat;
+  bool wrote_header;
 public:
+  // Output formats: TEXT is the reference's ("v  v  v  \n", 6 significant digits; src/mcout.cc:37-47).
+  // BINARY is for runs whose text would not fit anywhere (10^6 chains x 10^3 steps): a 16-byte header
+  // "MCOUTB01", int32 ncol, int32 sizeof(Real), then the rows as raw reals in the same order.
+  enum Format { TEXT = 0, BINARY = 1 };
+  void set_format(Format f) { mformat = f; }
   MCout(int np, std::ostream *aoutstream = 0, MCComm acomm = 0);
   void newsamps(size_t nsamp);                         // reserve room for nsamp more parameter sets
   void add(const Real *pv, Real lval);                 // append one row, track the max-likelihood row

@@ -2,7 +2,10 @@
 // (src/mcpar-rosen1.cc): `mcpar-rosen1 [nsamp]` prints "nsamp = N" and then every sample
 // row; 4 chains per rank from the four fixed starting points.  `mpirun -np R` becomes
 // --ranks=R (all ranks live on the GPU); extra flags never disturb the positional form.
+// --binary=FILE sends the rows to FILE in MCout's binary format instead of stdout (text for 10^6 chains
+// does not fit anywhere); stdout then carries only the banner.
 #include <iostream>
+#include <fstream>
 #include <stdlib.h>
 #include <string.h>
 #include "mcpar.hh"
@@ -14,16 +17,24 @@ int main(int argc, char *argv[])
   const int nparam = 2;
   int nsamp = 100000, ranks = 1, npos = 0, ngpu = 1;
   int pool = 0, thin = 1;
+  const char *binfile = 0;
   for (int i = 1; i < argc; ++i) {
     if (!strncmp(argv[i], "--ranks=", 8)) ranks = atoi(argv[i] + 8);
     else if (!strncmp(argv[i], "--ngpu=", 7)) ngpu = atoi(argv[i] + 7);
     else if (!strncmp(argv[i], "--pool=", 7)) pool = atoi(argv[i] + 7);
     else if (!strncmp(argv[i], "--thin=", 7)) thin = atoi(argv[i] + 7);
+    else if (!strncmp(argv[i], "--binary=", 9)) binfile = argv[i] + 9;
     else if (npos++ == 0) nsamp = atoi(argv[i]);
   }
   try {
     Rosenbrock1 L(2);
-    MCout rslts(nparam, &std::cout, 0);
+    std::ofstream bin;
+    if (binfile) {
+      bin.open(binfile, std::ios::binary);
+      if (!bin) { std::cerr << "cannot open " << binfile << "\n"; return 1; }
+    }
+    MCout rslts(nparam, binfile ? static_cast<std::ostream *>(&bin) : &std::cout, 0);
+    if (binfile) rslts.set_format(MCout::BINARY);
     std::cout << "nsamp = " << nsamp << "\n";
     MCPar mcpar(nparam, 4, ranks, 0);
     mcpar.pool_m = pool; mcpar.thin = thin; mcpar.ngpu = ngpu;

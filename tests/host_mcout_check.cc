@@ -4,6 +4,7 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <string.h>
 #include "../mcpar_b200/host/mcout.hh"
 
 #define CHECK(c) do { if (!(c)) { std::cerr << "FAILED: " #c " (line " << __LINE__ << ")\n"; return 1; } } while (0)
@@ -43,6 +44,15 @@ int main()
   std::ostringstream os2; MCout o2(1, &os2, 0); o2.newsamps(1);
   const Real p[1] = {3.14159265358979}; o2.add(p, -1234567.891); o2.output();
   CHECK(os2.str() == "3.14159  -1.23457e+06  \n");
+  // binary format: header once, then raw rows in the same order, across several output() calls
+  std::ostringstream ob; MCout o3(2, &ob, 0); o3.set_format(MCout::BINARY); o3.newsamps(3);
+  o3.add(a, -3.5); o3.output(); o3.add(b, -0.75); o3.add(c, 2.0); o3.output(); o3.output();
+  const std::string bin = ob.str();
+  CHECK(bin.size() == 16 + 9 * sizeof(Real) && bin.substr(0, 8) == "MCOUTB01");
+  int hdr[2]; memcpy(hdr, bin.data() + 8, 8);
+  CHECK(hdr[0] == 3 && hdr[1] == (int)sizeof(Real));
+  Real back[9]; memcpy(back, bin.data() + 16, sizeof back);
+  CHECK(back[0] == 1.5 && back[1] == -2.25 && back[2] == -3.5 && back[3] == 0.125 && back[8] == 2.0);
   std::cout << "ok\n";
   return 0;
 }

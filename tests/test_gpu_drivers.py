@@ -104,3 +104,30 @@ def test_mcpar_rosen1_ngpu_equals_single_engine(tmp_path):
     r = subprocess.run([os.path.join(BIN, "mcpar-rosen1"), "10", "--ranks=3", "--ngpu=2"], cwd=tmp_path,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 2 and "ngpu" in r.stderr                        # ranks must split evenly, 32-chain blocks
+
+
+def test_binary_output_and_iteration_bookkeeping(tmp_path):
+    """--binary=FILE: the same rows, same order, raw fp64; and the reference analysis script's iteration
+    bookkeeping (mcparam.itercount, src/anly/mcpar-analysis.R:80-120, ported in mcpar_b200/mcout_io.py)
+    names the right iteration for every row of the driver's output."""
+    from mcpar_b200 import mcout_io, engine
+    nsamp, ranks = 100, 3
+    r = subprocess.run([os.path.join(BIN, "mcpar-rosen1"), str(nsamp), "--ranks=%d" % ranks], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    text = mcout_io.read_text(r.stdout.splitlines())
+    r = subprocess.run([os.path.join(BIN, "mcpar-rosen1"), str(nsamp), "--ranks=%d" % ranks, "--binary=out.bin"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout == "nsamp = %d\n" % nsamp
+    rows = mcout_io.read_binary(str(tmp_path / "out.bin"))
+    assert rows.shape == (nsamp * 4 * ranks, 3) and np.allclose(text, rows, rtol=2e-5, atol=1e-6)
+    # iteration of every row from the engine's own history: row (t, chain) of the history is unique
+    N = 4 * ranks
+    e = engine.Engine(2, N, mode="normal", coin_group=4, pool_m=0, history_steps=nsamp)
+    e.run(nsamp, 500, np.tile(tiled_pinit(4, 2), (ranks, 1)), "rosenbrock1")
+    h = e.history(); e.close()
+    it = mcout_io.itercount(nsamp, ranks, 4)
+    assert np.array_equal(it, mcout_io.itercount_exact(nsamp, ranks, 4))      # niter = 100: the R rule is exact
+    chain = np.tile(np.tile(np.arange(4), mcout_io.outstep_of(nsamp)), ranks * (nsamp // mcout_io.outstep_of(nsamp)))
+    rank = np.tile(np.repeat(np.arange(ranks), 4 * mcout_io.outstep_of(nsamp)), nsamp // mcout_io.outstep_of(nsamp))
+    assert np.array_equal(rows, h[it - 1, rank * 4 + chain])
