@@ -3,7 +3,7 @@
  * Plain-C restatement of the rplzzz/mcpar Metropolis-Hastings engine, in fp64,
  * operation by operation (no FMA contraction: build with -ffp-contract=off).
  * It is the CPU checker for the B200 engine; nothing in the product links it.
- * Pinned against the reference's own sources by tests/test_oracle_vs_ref.py and
+ * Pinned against the reference's own sources by tests/test_oracle.py and
  * the fixtures in tests/golden/.  Citations are file:line into /root/reference/.
  */
 #include "mh_oracle.h"
