@@ -3,7 +3,7 @@
  * Plain-C, CPU restatement of the reference MH engine (rplzzz/mcpar) used as the
  * parity checker for the B200 engine.  Every function cites the reference lines
  * it follows.  Parity of this restatement is PINNED against the reference itself:
- * tests/test_oracle_vs_ref.py runs the reference's own unmodified sources
+ * tests/test_oracle.py runs the reference's own unmodified sources
  * (oracle/_ref, built by oracle/Makefile) on the same replay streams and demands
  * bit-identical traces; tests/golden/ holds fixtures generated that way for boxes
  * where oracle/_ref is absent.  (The reference ships no tests or golden vectors of
