@@ -274,21 +274,29 @@ def test_two_sharded_engines_equal_one_engine_jobwide_coin():
     _two_vs_one(0)
 
 
-def _two_vs_one(cg):
+def test_two_sharded_engines_equal_one_engine_at_full_size():
+    """BASELINE configs[1] at its full size (DualGaussian, 2^20 chains, PLOCAL 0.9, pool 16, job-wide
+    coin, thin 10): sharding invariance is the size-independent property -- two engines of 2^19 chains
+    reproduce the 2^20-chain engine bit for bit (states, moments, kept rows, tuned factor)."""
+    _two_vs_one(0, N=1 << 20, lik="dualgaussian", par=[5.0], nburn=110, nsamp=40, pl=0.9, thin=10)
+
+
+def _two_vs_one(cg, N=512, lik="rosenbrock1", par=None, nburn=130, nsamp=60, pl=0.7, thin=1):
     import torch
     eng = _engine()
-    d, N, nburn, nsamp, M, pl = 2, 512, 130, 60, 16, 0.7
+    d, M = 2, 16
+    kept = (nsamp + thin - 1) // thin
     pin = tiled_pinit(N, d)
-    one = eng.Engine(d, N, mode="normal", pool_m=M, pl=pl, coin_group=cg, history_steps=nsamp)
-    one.run(nsamp, nburn, pin, "rosenbrock1")
+    one = eng.Engine(d, N, mode="normal", pool_m=M, pl=pl, coin_group=cg, thin=thin, history_steps=kept)
+    one.run(nsamp, nburn, pin, lik, par)
     ref_state, ref_hist, ref_factor = one.state(), one.history(), one.factor()
     one.close()
 
     half = N // 2
-    es = [eng.Engine(d, half, mode="normal", nchain_total=N, chain0=r * half, pool_m=M, pl=pl, coin_group=cg,
-                     history_steps=nsamp) for r in range(2)]
+    es = [eng.Engine(d, half, mode="normal", nchain_total=N, chain0=r * half, pool_m=M, pl=pl, coin_group=cg, thin=thin,
+                     history_steps=kept) for r in range(2)]
     for r, e in enumerate(es):
-        e.set_likelihood("rosenbrock1"); e.set_covariance(None); e.set_state(pin[r * half:(r + 1) * half])
+        e.set_likelihood(lik, par); e.set_covariance(None); e.set_state(pin[r * half:(r + 1) * half])
     dev = torch.device("cuda", 0)
     cnts = [torch.as_tensor(e.tuning_counters(), device=dev) for e in es]
     left = nburn
@@ -370,6 +378,48 @@ def test_ks_local_only_dualgaussian_marginal():
     h = e.history()[2]
     assert stats.kstest(h[:, 0], cdf).pvalue > 0.01 and stats.kstest(h[:, 1], cdf).pvalue > 0.01
     assert abs((h[:, 0] > 2.5).mean() - 1.0 / 6.0) < 0.02
+    e.close()
+
+
+@pytest.mark.parametrize("pl", [1.0, 0.9])
+def test_full_size_stationarity(pl):
+    """BASELINE configs[1] at full size (2^20 chains, pool 16, job-wide coin), chains started from exact
+    draws of the target 5/6 N(0,I) + 1/6 N((5,5),I).
+    PLOCAL 1: Metropolis steps leave the target invariant exactly; with 2^20 chains the mean is pinned to
+    +-0.01 and the mass of the small mode to +-0.002 (5 standard errors), and a KS test applies.
+    PLOCAL 0.9: the reference's remote proposal is an independence proposal from the max-mixture of the
+    pool corrected by cfac = max_i Q_i(x) / max_i Q_i(x') with UNNORMALISED Q_i = exp(-1/2 sum (x-mu)^2/sig^2)
+    (src/mcpar.cc:367-390, :412-439): the correction is exact only when all components have the same
+    widths, so the reference's own algorithm carries a small bias that 2^20 chains resolve.  The engine
+    reproduces that algorithm (it matches the oracle trajectory for trajectory at small sizes), so here
+    only coarse bounds are asserted and the deviation is printed."""
+    from scipy import stats
+    eng = _engine()
+    N = 1 << 20
+    rng = np.random.default_rng(11)
+    comp = rng.random(N) < 1.0 / 6.0
+    pin = rng.standard_normal((N, 2)) + 5.0 * comp[:, None]
+    e = eng.Engine(2, N, mode="normal", pl=pl, pool_m=16, coin_group=0, thin=100, history_steps=3)
+    e.run(300, 100, pin, "dualgaussian", [5.0])
+    s = e.stats()
+    assert (s["remote_steps"] > 20 * N) == (pl < 1.0)
+    cdf = lambda v: (5.0 * stats.norm.cdf(v) + stats.norm.cdf(v - 5.0)) / 6.0
+    var = 1.0 + 25.0 * (5.0 / 36.0)
+    for k in (1, 2):
+        h = e.history()[k]
+        dm = [h[:, i].mean() - 5.0 / 6.0 for i in (0, 1)]
+        pright = (5.0 * stats.norm.sf(2.5) + stats.norm.cdf(2.5)) / 6.0       # P(x0 > 2.5) under the mixture: 0.1708
+        df = (h[:, 0] > 2.5).mean() - pright
+        print("pl=%g kept step %d: mean - 5/6 = %+.5f %+.5f   P(x0 > 2.5) - exact = %+.5f" % (pl, k, dm[0], dm[1], df))
+        if pl >= 1.0:
+            for i in (0, 1):
+                assert abs(dm[i]) < 5.0 * np.sqrt(var / N)
+                assert abs(h[:, i].var() - var) < 0.03
+                assert stats.kstest(h[::64, i], cdf).pvalue > 1.0e-3   # four KS tests in this case: family-wise 0.4 %
+            assert abs(df) < 5.0 * np.sqrt(pright * (1.0 - pright) / N)
+        else:
+            assert max(abs(dm[0]), abs(dm[1])) < 0.25 and abs(df) < 0.05
+        assert abs(((h[:, 0] > 2.5) != (h[:, 1] > 2.5)).mean()) < 0.02      # both coordinates sit in the same mode
     e.close()
 
 
