@@ -1,0 +1,78 @@
+"""CPU model of the fp32-bounded rejection test of the production kernels (remote_candidate in
+mcpar_b200/csrc/mh_kernels.cuh): the same arithmetic in numpy float32, with every approximation the
+kernel makes pushed to the edge of its documented error (the SFU Box-Muller error bound returned by
+normal_pair_f32, 2-ulp exp2), against the exact fp64 value of
+    R = sum_s Q_s(x') / max_s Q_s(x')      (src/mcpar.cc:355-398: pacpt = qimax / qisum = 1 / R).
+The kernel decides from R32 (1 +- eps); that is sound iff the true R lies inside that interval whenever
+the kernel's guards (max a > -9.7, theta < 2e-3) let the fast path decide.  The GPU-side check of the
+same claim is tests/test_gpu_audit.py (bit-identical runs with the fp64 route forced)."""
+import numpy as np
+import pytest
+
+L2E = 1.4426950408889634
+f32 = np.float32
+
+
+def _model(rng, M, D, ncand, mu_scale, sig_lo, sig_hi, worst):
+    mu = rng.uniform(-mu_scale, mu_scale, (M, D))
+    mu[: M // 2] = mu[0] + rng.normal(0, 0.3, (M // 2, D))            # a cluster of near-coincident components
+    sig = np.exp(rng.uniform(np.log(sig_lo), np.log(sig_hi), (M, D)))
+    # staging (stage_pool): fp32 copies and the pool-wide scalars, rounded up
+    g = np.sqrt(L2E / (2.0 * sig * sig))
+    gmu32, g32, s32, mu32 = f32(g * mu), f32(g), f32(sig), f32(mu)
+    mu_max = np.nextafter(f32(np.abs(mu).max()), f32(np.inf))
+    isig_max = np.nextafter(f32((1.0 / sig).max()), f32(np.inf))
+    # candidates
+    c = rng.integers(0, M, ncand)
+    v = 1.0 - rng.random((ncand, D // 2))                              # (0, 1]
+    if worst:
+        v[: ncand // 4] = 1.0 - rng.random((ncand // 4, D // 2)) * 1e-5   # tiny radii, where the radius bound bites
+    ang = 2.0 * np.pi * rng.random((ncand, D // 2))
+    r = np.sqrt(-2.0 * np.log(v))
+    z = np.empty((ncand, D)); z[:, 0::2] = r * np.sin(ang); z[:, 1::2] = r * np.cos(ang)
+    x_true = mu[c] + sig[c] * z
+    a_true = -0.5 * (((x_true[:, None, :] - mu[None]) / sig[None]) ** 2).sum(-1)       # [ncand][M]
+    R_true = np.exp(a_true - a_true.max(1, keepdims=True)).sum(1)
+    # the kernel's fp32 path, each approximate quantity at the edge of its bound
+    r32 = f32(r)
+    zerr = f32(2.4e-6) * r32 + f32(1.7e-6) * np.minimum(f32(1.0) / np.maximum(r32, f32(1e-30)), f32(770.0))
+    zerr_pair = zerr.max(1)
+    sgn = rng.choice([-1.0, 1.0], (ncand, D))
+    zt = f32(z + sgn * np.repeat(zerr, 2, axis=1).astype(np.float64) * (0.999 if worst else 0.3))
+    xf = (s32[c] * zt + mu32[c]).astype(f32)
+    xabs = np.abs(xf).max(1)
+    sgmax = s32[c].max(1)
+    theta = (f32(1.9e-7) * (mu_max + xabs) + zerr_pair * sgmax) * isig_max
+    ref = f32((np.log2(v)).sum(1) + rng.uniform(-1e-6, 1e-6, ncand) * (D // 2))          # sum of lg2.approx(v)
+    y = (gmu32[None] - g32[None] * xf[:, None, :]).astype(f32)                            # fmaf(-g, x, g mu), two roundings here
+    acc = (-ref)[:, None].astype(f32)
+    for i in range(D):
+        acc = (acc - y[:, :, i] * y[:, :, i]).astype(f32)
+    mr = acc.max(1)
+    ex = np.exp2(acc.astype(np.float64)) * (1.0 + rng.uniform(-2.4e-7, 2.4e-7, acc.shape))  # ex2.approx: 2 ulp
+    S = f32(ex).sum(1, dtype=f32)
+    E = f32(np.exp2(mr.astype(np.float64)) * (1.0 + 2.4e-7))
+    R32 = S.astype(np.float64) / E.astype(np.float64)
+    eps = (f32(1.01e-4) + f32(1.0e-5) * f32(D)) + f32(2.0e-5) * f32(M) + theta * f32(21.3 * np.sqrt(D))
+    fast = (mr + ref > f32(-14.0)) & (theta < f32(2.0e-3))
+    return R_true, R32, eps.astype(np.float64), fast, a_true.max(1)
+
+
+@pytest.mark.parametrize("M,D,mu_scale,sig_lo,sig_hi", [
+    (16, 2, 6.0, 0.5, 2.5),          # the benchmark's regime
+    (16, 2, 6.0, 0.05, 3.0),         # widths spread over a factor 60
+    (256, 2, 10.0, 0.2, 2.0),        # config 5's pool size
+    (8, 4, 5.0, 0.3, 2.0),           # d = 4 (two normal pairs per candidate)
+    (16, 2, 300.0, 0.5, 2.0),        # far from the origin: roundings of mu and x' dominate theta
+])
+@pytest.mark.parametrize("worst", [False, True])
+def test_fast_path_interval_contains_the_true_ratio(M, D, mu_scale, sig_lo, sig_hi, worst):
+    rng = np.random.default_rng(1234 + M + D)
+    R_true, R32, eps, fast, amax = _model(rng, M, D, 200000, mu_scale, sig_lo, sig_hi, worst)
+    assert fast.mean() > 0.2, "the case must exercise the fast path"
+    rel = np.abs(R_true[fast] / R32[fast] - 1.0)
+    worst_ratio = (rel / eps[fast]).max()
+    assert worst_ratio < 1.0, "true R outside R32 (1 +- eps): %.3g of the bound" % worst_ratio
+    # whenever the fast path decides, max_s Q_s(x') > exp(-10): the reference's FPEPS offsets (mcpar.cc:357-358)
+    # then move pacpt by < 2.3e-10 relative, which the 3e-10 term of the kernel's test covers
+    assert amax[fast].min() > -10.0
