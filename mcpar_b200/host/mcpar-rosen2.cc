@@ -3,6 +3,7 @@
 // a stale copy of the 2-D demo that no longer compiles (src/mcpar-rosen2.cc:16,44); this
 // driver keeps its shape: `mcpar-rosen2 [nsamp]`, "nsamp = N", rows on stdout.
 #include <iostream>
+#include <fstream>
 #include <vector>
 #include <stdlib.h>
 #include <string.h>
@@ -14,16 +15,24 @@ int main(int argc, char *argv[])
 {
   const int nparam = 16;
   int nsamp = 10000, ranks = 1, npos = 0, pool = 0, thin = 1, ngpu = 1;
+  const char *binfile = 0;                       // --binary=FILE: rows to FILE in MCout's binary format
   for (int i = 1; i < argc; ++i) {
     if (!strncmp(argv[i], "--ranks=", 8)) ranks = atoi(argv[i] + 8);
     else if (!strncmp(argv[i], "--ngpu=", 7)) ngpu = atoi(argv[i] + 7);
     else if (!strncmp(argv[i], "--pool=", 7)) pool = atoi(argv[i] + 7);
     else if (!strncmp(argv[i], "--thin=", 7)) thin = atoi(argv[i] + 7);
+    else if (!strncmp(argv[i], "--binary=", 9)) binfile = argv[i] + 9;
     else if (npos++ == 0) nsamp = atoi(argv[i]);
   }
   try {
     Rosenbrock1 L(nparam);
-    MCout rslts(nparam, &std::cout, 0);
+    std::ofstream bin;
+    if (binfile) {
+      bin.open(binfile, std::ios::binary);
+      if (!bin) { std::cerr << "cannot open " << binfile << "\n"; return 1; }
+    }
+    MCout rslts(nparam, binfile ? static_cast<std::ostream *>(&bin) : &std::cout, 0);
+    if (binfile) rslts.set_format(MCout::BINARY);
     std::cout << "nsamp = " << nsamp << "\n";
     MCPar mcpar(nparam, 4, ranks, 0);
     mcpar.pool_m = pool; mcpar.thin = thin; mcpar.ngpu = ngpu;
