@@ -76,3 +76,19 @@ def test_fast_path_interval_contains_the_true_ratio(M, D, mu_scale, sig_lo, sig_
     # whenever the fast path decides, max_s Q_s(x') > exp(-10): the reference's FPEPS offsets (mcpar.cc:357-358)
     # then move pacpt by < 2.3e-10 relative, which the 3e-10 term of the kernel's test covers
     assert amax[fast].min() > -10.0
+
+
+def test_accept_test_interval_contains_exp_delta():
+    """accept_test (mh_kernels.cuh): u < exp(delta) cfac is decided from e32 = ex2.approx(fp32(delta) log2 e)
+    with a margin of 1e-4 either way.  Model: fp32 rounding of delta and of the product, ex2.approx at 2 ulp;
+    the true exp(delta) must lie inside e32 (1 +- 1e-4) over the clamped range |delta| <= 80."""
+    rng = np.random.default_rng(5)
+    delta = np.concatenate([rng.uniform(-80, 80, 400000), rng.normal(0, 3, 400000), -np.exp(rng.uniform(-20, 4.3, 200000))])
+    delta = delta[np.abs(delta) <= 80.0]
+    dc = f32(delta)
+    arg = (dc * f32(L2E)).astype(f32)
+    for sgn in (-1.0, 1.0):
+        e32 = f32(np.exp2(arg.astype(np.float64)) * (1.0 + sgn * 2.4e-7))
+        rel = np.abs(np.exp(delta) / e32.astype(np.float64) - 1.0)
+        assert rel.max() < 1.0e-4, rel.max()
+    assert rel.max() < 2.0e-5                      # the margin is five times what the model needs
