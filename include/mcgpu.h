@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MCGPU_ABI_VERSION 1
+#define MCGPU_ABI_VERSION 2
 
 enum {
   MCGPU_OK = 0,
@@ -83,7 +83,21 @@ typedef struct mcgpu_config {
   int32_t pool_m;           /* NORMAL: remote-mixture pool size; 0 = all chains      */
   int32_t thin;             /* keep every thin-th main step in the sample history    */
   int32_t trace;            /* VERIFY: steps of per-step accept/trial trace to keep (0 = none) */
-  int64_t history_steps;    /* kept steps the history must hold (0 = moments only)   */
+  int64_t history_steps;    /* capacity of the device history in kept steps (0 = none).  NORMAL mode keeps
+                               a RING of that many kept steps: a run may keep more (nsamp/thin >
+                               history_steps); read or drain (mcgpu_history_attach_host*) the rows
+                               before the ring overwrites them.  VERIFY holds the whole run.        */
+  int32_t remote_mode;      /* NORMAL: how a remote step proposes (replaces MCPar::genRemote, mcpar.cc:315-451)
+                               0 = the reference's algorithm: rejection-sample max_i Q_i over the pool,
+                                   cfac = max_i Q_i(x)/max_i Q_i(x') with unnormalised Q_i (default);
+                               1 = sum-mixture independence proposal: x' ~ (1/M) sum_i N(mu_i, diag sig2_i),
+                                   cfac = q(x)/q(x') with normalised components, no rejection loop
+                                   (Murray's proposal): O(M d) per remote step
+                                   and exactly invariant, but not the reference's accept/reject sequence */
+  int32_t pool_lag;         /* NORMAL: 0 = window w reads the pool published at the end of window w-1 (the
+                               reference's staleness bound, mcpar.cc:127-140); 1 = one window older, which
+                               takes the inter-GPU exchange off the critical path (remote steps start at
+                               t >= 2 sync)                                                           */
 } mcgpu_config;
 
 typedef struct mcgpu_stats {
@@ -95,8 +109,12 @@ typedef struct mcgpu_stats {
   int64_t remote_iterations;            /* VERIFY: lock-step rejection iterations;
                                            NORMAL: candidates tried by those chain-steps
                                            (iterations of the loop mcpar.cc:331-409)        */
-  int64_t history_rows;                 /* rows currently stored (kept steps * chains) */
+  int64_t history_rows;                 /* rows produced so far (kept steps * chains); the device ring
+                                           holds the last history_steps kept steps of them  */
   double  device_ms;                    /* CUDA-event time of burnin+sample calls    */
+  int64_t exchange_wait_ns;             /* peer-to-peer exchange: time the window kernels' first CTA spent
+                                           waiting for the peers' pool slots (globaltimer)   */
+  int64_t exchange_waits;               /* ... and how many launches had to wait at all      */
 } mcgpu_stats;
 
 const char *mcgpu_version(void);
@@ -140,6 +158,11 @@ int  mcgpu_burnin(mcgpu_engine *e, int nburn);
  * is [own_offset, own_offset+own_bytes)), then exchange_end. */
 int  mcgpu_sample_begin(mcgpu_engine *e, int nsamp);
 int  mcgpu_sample(mcgpu_engine *e, int nsteps);
+/* The same for `world` peer-to-peer engines driven by ONE host thread (mcgpu_p2p_attach_local): the
+ * windows of all engines are enqueued in turn, one exchange window at a time.  A window kernel that waits
+ * for its peers' publications is then never queued in front of the launches that make them; engines
+ * attached with attach_local refuse an mcgpu_sample call that would cross a multiple of `sync`. */
+int  mcgpu_sample_group(mcgpu_engine *const *engines, int world, int nsteps);
 int  mcgpu_exchange_begin(mcgpu_engine *e, void **dev_buffer, size_t *total_bytes,
                           size_t *own_offset, size_t *own_bytes);
 int  mcgpu_exchange_end(mcgpu_engine *e);
@@ -217,7 +240,9 @@ int  mcgpu_history_moments(mcgpu_engine *e, double *mean, double *cov);
  * running moments, the tuned proposal factor, the counters, the exchange pools and the schedule;
  * an engine created with the same configuration and likelihood continues the run bit for bit after
  * load (with a peer-to-peer exchange, all peers restore the same checkpoint).  The sample history
- * is not part of it: rows kept before the checkpoint must have been read or drained. */
+ * is not part of it: rows kept before the checkpoint must have been read or drained (after a load,
+ * history_read / maxlike / moments see only rows produced since).  With a peer-to-peer exchange every
+ * peer must have finished its load (a barrier) before any peer samples again. */
 int  mcgpu_checkpoint_size(mcgpu_engine *e, size_t *bytes);
 int  mcgpu_checkpoint_save(mcgpu_engine *e, void *buf, size_t bytes);
 int  mcgpu_checkpoint_load(mcgpu_engine *e, const void *buf, size_t bytes);
@@ -237,6 +262,11 @@ int  mcgpu_loglik(int device, int lik, int nparam, const double *par, int npar, 
  * rank skip-ahead; pout is npset*nparam chain-major on the host. */
 int  mcgpu_qriguess(int device, int rank, int npset, int nparam, const double *plo,
                     const double *phi, double *pout);
+/* qriguess straight into the engine (no host round trip): chain g of the job starts at Sobol point
+ * `first_point + g` of the nparam-dimensional sequence scaled into the box [plo, phi] -- what
+ * qriguess(rank, npset, ...) gives rank = chain0 / npset (mcutil.cc:16-31; first_point = 0).  Replaces
+ * mcgpu_set_state for runs of >= 1M chains without a hand-made pinit; nparam <= 64. */
+int  mcgpu_set_state_sobol(mcgpu_engine *e, const double *plo, const double *phi, uint64_t first_point);
 
 /* FP64 DFMA micro-benchmark used for the roofline denominator: returns the measured
  * TFLOP/s (2 flops per DFMA) of `iters` dependent-chain DFMAs per thread. */

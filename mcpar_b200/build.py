@@ -72,7 +72,7 @@ def build(force=False, verbose=False):
 
 HOST = os.path.join(HERE, "host")
 BIN = os.path.join(HERE, "bin")
-DRIVERS = ["mcpar-rosen1", "mcpar-dgauss", "mcpar-rosen2"]
+DRIVERS = ["mcpar-rosen1", "mcpar-dgauss", "mcpar-rosen2", "mcpar-gmix", "mcpar-bench"]
 
 
 def build_host():

@@ -7,6 +7,7 @@
 // MCGPU_ENODEVICE / MCGPU_ECUDA when no device is usable.
 #include "../../include/mcgpu.h"
 #include "mh_launch.h"
+#include "mcgpu_sobol.h"
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -15,6 +16,7 @@
 #include <time.h>
 #include <string>
 #include <vector>
+#include <deque>
 #include <algorithm>
 
 using namespace mcgpu;
@@ -42,13 +44,15 @@ struct mcgpu_engine {
   // NORMAL / REPLAY_LOCAL state (SoA) or VERIFY state (AoS per rank)
   double *x = nullptr, *ly = nullptr, *mu = nullptr, *ps = nullptr;
   double *factor = nullptr;
-  unsigned long long *counts = nullptr;   // [0,1] window, [2,3] cumulative, [4,5] main-phase stats, [6,7] remote chain-steps / candidate iterations
-  // exchange region (one allocation, IPC-exportable): 3 pool buffers [M][d][2] + the arrival counter
+  unsigned long long *counts = nullptr;   // [0,1] window, [2,3] cumulative, [4,5] main-phase stats, [6,7] remote chain-steps / candidate iterations, [8,9] exchange wait ns / waits
+  // exchange region (one allocation, IPC-exportable): NPOOL pool buffers [M][d][2] + the arrival counter
   char *xchg = nullptr; size_t pool_bytes = 0, xchg_bytes = 0;
-  double *pool[3] = {nullptr, nullptr, nullptr}; int M = 0; long long stride = 1; bool pool_in_smem = true;
-  long long npub = 0;                      // publications completed since create: the pool read now is pool[npub % nbuf]
-  bool p2p = false; int p2p_world = 0; char **peers_d = nullptr; std::vector<void*> peer_opened; int *xflag_d = nullptr;
-  double *hist = nullptr; long long hist_cap = 0, hist_kept = 0;
+  double *pool[4] = {nullptr, nullptr, nullptr, nullptr}; int M = 0; long long stride = 1; bool pool_in_smem = true;
+  long long npub = 0;                      // publications completed since create: publication k lives in pool[k % nbuf]
+  int lag = 0, remote_mode = 0;            // cfg.pool_lag, cfg.remote_mode
+  bool p2p = false, p2p_local = false; int p2p_world = 0; char **peers_d = nullptr; std::vector<void*> peer_opened; int *xflag_d = nullptr;
+  // sample history: a ring of hist_cap kept steps; kept step k lives in ring row k % hist_cap
+  double *hist = nullptr; long long hist_cap = 0, hist_kept = 0, hist_valid_from = 0;
   int *overrun = nullptr;
   double *Zd = nullptr, *Ud = nullptr; int *Id = nullptr; long long nz = 0, nu = 0, ni = 0;
 
@@ -72,7 +76,7 @@ struct mcgpu_engine {
   bool have_state = false, have_factor = false, sampling = false, exchange_pending = false, tune_pending = false;
   long long burn_done = 0, t_main = 0; int nsamp = 0; int irate = 50; int nburn_total = 0;
   long long launches = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers; double ms_accum = 0.0;
+  std::deque<std::pair<cudaEvent_t, cudaEvent_t>> timers; std::vector<cudaEvent_t> ev_free; double ms_accum = 0.0;
 
   // pinned staging for history reads
   double *pin[2] = {nullptr, nullptr}; size_t pin_bytes = 0; cudaEvent_t pin_ev[2] = {nullptr, nullptr};
@@ -81,6 +85,7 @@ struct mcgpu_engine {
   double *sink = nullptr; size_t sink_rows_cap = 0; long long sink_sent = 0; bool sink_registered = false;
   bool sink_f32 = false; float *hist_f32 = nullptr;       // fp32 sink (the reference's MCout element type): device mirror of the history
   cudaEvent_t sink_ev = nullptr;
+  std::deque<std::pair<long long, cudaEvent_t>> drains;   // (kept steps drained once the event completes, event on the side stream)
 };
 
 namespace {
@@ -111,24 +116,35 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// device time of the burnin / sample calls: event pairs, harvested without blocking as they complete and recycled
+cudaEvent_t event_get(mcgpu_engine *e, unsigned flags = cudaEventDefault)
+{
+  cudaEvent_t ev = nullptr;
+  if (flags == cudaEventDefault && !e->ev_free.empty()) { ev = e->ev_free.back(); e->ev_free.pop_back(); return ev; }
+  cudaEventCreateWithFlags(&ev, flags);
+  return ev;
+}
+void timers_harvest(mcgpu_engine *e, bool block)
+{
+  while (!e->timers.empty()) {
+    auto &t = e->timers.front();
+    if (block) cudaEventSynchronize(t.second);
+    else if (cudaEventQuery(t.second) != cudaSuccess) { cudaGetLastError(); break; }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, t.first, t.second) == cudaSuccess) e->ms_accum += ms; else cudaGetLastError();
+    e->ev_free.push_back(t.first); e->ev_free.push_back(t.second);
+    e->timers.pop_front();
+  }
+}
 void timer_begin(mcgpu_engine *e)
 {
-  cudaEvent_t a, b;
-  cudaEventCreate(&a); cudaEventCreate(&b);
+  timers_harvest(e, false);
+  cudaEvent_t a = event_get(e), b = event_get(e);
   cudaEventRecord(a, e->stream);
   e->timers.emplace_back(a, b);
 }
 void timer_end(mcgpu_engine *e) { cudaEventRecord(e->timers.back().second, e->stream); }
-void timers_resolve(mcgpu_engine *e)
-{
-  for (auto &t : e->timers) {
-    float ms = 0;
-    cudaEventSynchronize(t.second);
-    if (cudaEventElapsedTime(&ms, t.first, t.second) == cudaSuccess) e->ms_accum += ms;
-    cudaEventDestroy(t.first); cudaEventDestroy(t.second);
-  }
-  e->timers.clear();
-}
+void timers_resolve(mcgpu_engine *e) { timers_harvest(e, true); }
 
 // lower Cholesky factor of a row-major SPD matrix in place (replaces spotrf('U') on the
 // column-major view, mcpar.cc:475-480); the strict upper triangle keeps its input
@@ -149,8 +165,12 @@ int cholesky_lower(int d, double *a)
 // publication P may write publication P+1 into its peers while their last CTAs of the window that
 // produced P still read pool P-1 -- so P+1 must not alias P-1.  (Every main-phase launch waits for the
 // arrivals of the pool it is entitled to read, so no GPU is ever more than one publication ahead.)
-int pool_nbuf(const mcgpu_engine *e) { return e->p2p ? 3 : 2; }
-double *pool_cur(const mcgpu_engine *e) { return e->pool[e->npub % pool_nbuf(e)]; }
+// With pool_lag = 1 a window reads the publication BEFORE the newest one, so one more buffer stays live.
+enum { NPOOL = 4 };
+int pool_nbuf(const mcgpu_engine *e) { return (e->p2p ? 3 : 2) + e->lag; }
+long long pool_read_index(const mcgpu_engine *e) { return std::max<long long>(e->npub - e->lag, 0); }
+double *pool_cur(const mcgpu_engine *e) { return e->pool[pool_read_index(e) % pool_nbuf(e)]; }       // what this window reads
+double *pool_newest(const mcgpu_engine *e) { return e->pool[e->npub % pool_nbuf(e)]; }                 // the latest publication
 double *pool_next(const mcgpu_engine *e) { return e->pool[(e->npub + 1) % pool_nbuf(e)]; }
 int arrivals_per_slot(const mcgpu_engine *e) { return e->wide ? e->d / 2 : 1; }   // the wide kernel's lanes arrive one by one
 
@@ -159,9 +179,11 @@ void fill_p2p(const mcgpu_engine *e, StepParams &p)
 {
   if (!e->p2p) return;
   p.peers = e->peers_d; p.npeers = e->p2p_world;
-  p.next_off = (long long)(((e->npub + 1) % 3) * e->pool_bytes); p.arr_off = (long long)(3 * e->pool_bytes);
-  p.arrivals = reinterpret_cast<const unsigned long long*>(e->xchg + 3 * e->pool_bytes);
-  p.wait_target = (unsigned long long)e->M * arrivals_per_slot(e) * (unsigned long long)e->npub;
+  p.next_off = (long long)(((e->npub + 1) % pool_nbuf(e)) * e->pool_bytes); p.arr_off = (long long)(NPOOL * e->pool_bytes);
+  p.arrivals = reinterpret_cast<const unsigned long long*>(e->xchg + NPOOL * e->pool_bytes);
+  const unsigned long long per_pub = (unsigned long long)e->M * arrivals_per_slot(e);
+  p.wait_target = per_pub * (unsigned long long)pool_read_index(e);     // readers: the publication this window reads
+  p.pub_wait_target = per_pub * (unsigned long long)e->npub;            // publishers: never more than one publication ahead
   p.xflag = e->xflag_d;
 }
 
@@ -174,6 +196,8 @@ void fill_step_params(mcgpu_engine *e, StepParams &p)
   p.key0 = (uint32_t)e->cfg.seed; p.key1 = (uint32_t)(e->cfg.seed >> 32);
   for (int r = 0; r < 10; ++r) { p.rk[2 * r] = p.key0 + (uint32_t)r * 0x9E3779B9u; p.rk[2 * r + 1] = p.key1 + (uint32_t)r * 0xBB67AE85u; }
   p.sync = e->cfg.sync; p.coin_group = e->cfg.coin_group; p.pl = e->cfg.pl;
+  p.first_remote_t = e->cfg.sync * (1 + e->lag);
+  p.hist_cap = (int)std::max<long long>(e->hist_cap, 1);
   p.pool_m = e->M; p.pool_stride = e->stride; p.pool_in_smem = e->pool_in_smem;
   p.thin = e->cfg.thin;
   static const int exact_tests = getenv("MCGPU_EXACT_TESTS") ? atoi(getenv("MCGPU_EXACT_TESTS")) : 0;
@@ -194,13 +218,16 @@ cudaError_t launch_steps_any(mcgpu_engine *e, int phase, const StepParams &p)
     w.pmh = reinterpret_cast<const double2*>(e->pprep); w.psd = e->pprep + (size_t)2 * e->d * e->mpad;
     w.pool_m = e->M; w.mpad = e->mpad; w.pool_next = p.pool_next; w.pool_stride = p.pool_stride;
     w.peers = p.peers; w.npeers = p.npeers; w.next_off = p.next_off; w.arr_off = p.arr_off;
-    w.arrivals = p.arrivals; w.wait_target = p.wait_target; w.xflag = p.xflag;   // readers wait in pool_prep, publishers in the kernel
-    w.hist = p.hist; w.thin = p.thin; w.hist_step0 = p.hist_step0;
+    w.arrivals = p.arrivals; w.wait_target = p.wait_target; w.pub_wait_target = p.pub_wait_target; w.xflag = p.xflag;   // readers wait in pool_prep, publishers in the kernel
+    w.xstat = p.xstat;
+    w.hist = p.hist; w.thin = p.thin; w.hist_cap = p.hist_cap; w.hist_ring0 = p.hist_ring0;
+    w.pnb = e->pprep + (size_t)3 * e->d * e->mpad; w.summix = e->remote_mode;
     w.gm2 = reinterpret_cast<const double2*>(e->gm_t);
     w.gm_lw = e->gm_t ? e->gm_t + (size_t)2 * e->d * e->kpad : nullptr; w.kpad = e->kpad;
-    return fast::launch_wide(e->lik, e->d, phase, w, e->stream);
+    return fast::launch_wide(e->lik, e->d, phase == PH_REMOTE && e->remote_mode == 1 ? PH_REMOTE_SUM : phase, w, e->stream);
   }
   if (e->replay_local) return exact::launch_steps(e->lik, e->d, 1, phase == PH_BURN ? PH_BURN : PH_LOCAL, p, e->stream);
+  if (e->remote_mode == 1) phase = phase == PH_MIXED ? PH_MIXED_SUM : (phase == PH_REMOTE ? PH_REMOTE_SUM : phase);
   return fast::launch_steps(e->lik, e->d, 0, phase, p, e->stream);
 }
 
@@ -288,6 +315,11 @@ __global__ void narrow_rows_kernel(const double *src, float *dst, size_t n)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (float)src[i];
 }
 
+__global__ void fill_kernel(double *dst, size_t n, double v)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+
 __global__ void argmax_rows_kernel(const double *rows, long long nrows, int ncol, double *best_val, long long *best_row)
 {
   __shared__ double sv[256]; __shared__ long long sr[256];
@@ -327,19 +359,23 @@ __global__ void moments_kernel(const double *rows, long long nrows, int d, doubl
   if (threadIdx.x == 0) atomicAdd(out + q, ssum[0]);
 }
 
-__global__ void sobol_box_kernel(const uint32_t *dirs, int d, unsigned long long first_scalar, int ntot,
-                                 const double *plo, const double *phi, double *pout)
+// Scalar q of the output is scalar first_scalar + q of the point-major Sobol stream (what vslSkipAheadStream +
+// vsRngUniform deliver, mcutil.cc:22-25) scaled into the box of OUTPUT column q % d (mcutil.cc:28-32).
+// ld = 0: chain-major output pout[q] (the host layout); ld > 0: the engine's SoA state pout[(q % d) * ld + q / d].
+__global__ void sobol_box_kernel(const uint32_t *dirs, int d, unsigned long long first_scalar, size_t ntot,
+                                 const double *plo, const double *phi, double *pout, long long ld)
 {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= ntot) return;
-  const unsigned long long sc = first_scalar + (unsigned long long)q;
-  const unsigned long long n = sc / (unsigned long long)d; const int k = (int)(sc % (unsigned long long)d);
-  unsigned long long gray = n ^ (n >> 1);
-  uint32_t xv = 0;
-  for (int b = 0; gray; ++b, gray >>= 1) if (gray & 1ull) xv ^= dirs[k * 32 + b];
-  const double u = (double)xv * (1.0 / 4294967296.0);
-  const int i = q % d;
-  pout[q] = __dadd_rn(plo[i], __dmul_rn(u, __dsub_rn(phi[i], plo[i])));   // mcutil.cc:31, no contraction
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < ntot; q += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long sc = first_scalar + (unsigned long long)q;
+    const unsigned long long n = sc / (unsigned long long)d; const int k = (int)(sc % (unsigned long long)d);
+    unsigned long long gray = n ^ (n >> 1);
+    uint32_t xv = 0;
+    for (int b = 0; gray && b < 32; ++b, gray >>= 1) if (gray & 1ull) xv ^= dirs[k * 32 + b];
+    const double u = (double)xv * (1.0 / 4294967296.0);
+    const int i = (int)(q % (size_t)d);
+    const double v = __dadd_rn(plo[i], __dmul_rn(u, __dsub_rn(phi[i], plo[i])));   // mcutil.cc:31, no contraction
+    if (ld > 0) pout[(size_t)i * ld + q / (size_t)d] = v; else pout[q] = v;
+  }
 }
 
 __global__ void dfma_peak_kernel(double *out, int iters, double a, double b)
@@ -366,18 +402,11 @@ __global__ void transpose_soa_to_aos(const double *soa, double *aos, long long C
   for (int i = 0; i < d; ++i) aos[j * d + i] = soa[i * ld + j] * scale;
 }
 
-// Sobol direction numbers, Joe & Kuo (2008), dimensions 1..16
-struct jk_t { int s; uint32_t a; uint32_t m[7]; };
-const jk_t JK[16] = {
-  {0,0,{0}}, {1,0,{1}}, {2,1,{1,3}}, {3,1,{1,3,1}}, {3,2,{1,1,1}}, {4,1,{1,1,3,3}},
-  {4,4,{1,3,5,13}}, {5,2,{1,1,5,5,17}}, {5,4,{1,1,5,5,5}}, {5,7,{1,1,7,11,19}},
-  {5,11,{1,1,5,1,1}}, {5,13,{1,1,1,3,11}}, {5,14,{1,3,5,5,31}}, {6,1,{1,3,3,9,7,49}},
-  {6,13,{1,1,1,15,21,21}}, {6,16,{1,3,1,13,27,49}},
-};
+// Sobol direction numbers, Joe & Kuo (2008), dimensions 1..64 (mcgpu_sobol.h, generated by tools/gen_sobol_table.py)
 void sobol_dirs(int dim, uint32_t *v)
 {
   if (dim == 0) { for (int i = 0; i < 32; ++i) v[i] = 1u << (31 - i); return; }
-  const jk_t &p = JK[dim]; const int s = p.s;
+  const sobol_jk_t &p = SOBOL_JK[dim]; const int s = p.s;
   for (int i = 0; i < 32; ++i) {
     if (i < s) v[i] = p.m[i] << (31 - i);
     else {
@@ -467,6 +496,10 @@ int mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out)
     if (cfg->mode != MCGPU_MODE_NORMAL && cfg->mode != MCGPU_MODE_REPLAY_LOCAL) return bail(MCGPU_EINVAL, "unknown mode");
     if (cfg->coin_group < 0 || cfg->coin_group > 32 || (cfg->coin_group & (cfg->coin_group - 1))) return bail(MCGPU_EINVAL, "coin_group must be 0 (job-wide coin) or a power of two in 1..32");
     if (cfg->chain0 % 32) return bail(MCGPU_EINVAL, "chain0 must be a multiple of 32");
+    if (cfg->remote_mode != 0 && cfg->remote_mode != 1) return bail(MCGPU_EINVAL, "remote_mode must be 0 (reference max-mixture rejection loop) or 1 (sum-mixture proposal)");
+    if (cfg->pool_lag != 0 && cfg->pool_lag != 1) return bail(MCGPU_EINVAL, "pool_lag must be 0 or 1");
+    if (e->replay_local && (cfg->remote_mode || cfg->pool_lag)) return bail(MCGPU_EINVAL, "REPLAY_LOCAL takes local steps only: remote_mode / pool_lag do not apply");
+    e->remote_mode = cfg->remote_mode; e->lag = cfg->pool_lag;
     if (e->replay_local && e->sharded) return bail(MCGPU_EINVAL, "REPLAY_LOCAL hosts the whole rank");
     e->ld = (e->C + 31) / 32 * 32;
     const bool never_remote = cfg->pl >= 1.0;              // the coin is < 1: rndlocal <= PLOCAL always (mcpar.cc:152)
@@ -477,16 +510,17 @@ int mcgpu_create(const mcgpu_config *cfg, mcgpu_engine **out)
     e->pool_in_smem = true;
     TRY(dalloc(e, &e->x, (size_t)d * e->ld)); TRY(dalloc(e, &e->ly, (size_t)e->ld));
     TRY(dalloc(e, &e->mu, (size_t)d * e->ld)); TRY(dalloc(e, &e->ps, (size_t)d * e->ld));
-    TRY(dalloc(e, &e->factor, (size_t)d * d)); TRY(dalloc(e, &e->counts, 8));
+    TRY(dalloc(e, &e->factor, (size_t)d * d)); TRY(dalloc(e, &e->counts, 12));
     e->pool_bytes = ((size_t)e->M * d * 16 + 255) / 256 * 256;
-    e->xchg_bytes = 3 * e->pool_bytes + 256;
+    e->xchg_bytes = NPOOL * e->pool_bytes + 256;
     TRY(dalloc(e, &e->xchg, e->xchg_bytes));
-    for (int b = 0; b < 3; ++b) e->pool[b] = reinterpret_cast<double*>(e->xchg + (size_t)b * e->pool_bytes);
+    for (int b = 0; b < NPOOL; ++b) e->pool[b] = reinterpret_cast<double*>(e->xchg + (size_t)b * e->pool_bytes);
     TRY(dalloc(e, &e->xflag_d, 1));
     e->hist_cap = cfg->history_steps;
     if (e->hist_cap > 0) TRY(dalloc(e, &e->hist, (size_t)e->hist_cap * e->C * (d + 1), false));
     e->host_streams.resize(1);
   } else {
+    if (cfg->remote_mode || cfg->pool_lag) return bail(MCGPU_EINVAL, "VERIFY runs the reference's own remote proposal: remote_mode / pool_lag must be 0");
     e->Cr = cfg->chains_per_rank;
     if (e->Cr < 1 || e->Cr > 1024) return bail(MCGPU_EINVAL, "VERIFY: chains_per_rank must be 1..1024");
     if (e->C % e->Cr || e->N % e->Cr || cfg->chain0 % e->Cr) return bail(MCGPU_EINVAL, "VERIFY: chain counts must be multiples of chains_per_rank");
@@ -533,7 +567,7 @@ int mcgpu_destroy(mcgpu_engine *e)
     const unsigned long long want = (unsigned long long)e->M * arrivals_per_slot(e) * (unsigned long long)e->npub;
     for (int i = 0; i < 10000; ++i) {
       unsigned long long got = 0;
-      if (cudaMemcpy(&got, e->xchg + 3 * e->pool_bytes, sizeof got, cudaMemcpyDeviceToHost) != cudaSuccess || got >= want) break;
+      if (cudaMemcpy(&got, e->xchg + NPOOL * e->pool_bytes, sizeof got, cudaMemcpyDeviceToHost) != cudaSuccess || got >= want) break;
       struct timespec ts = {0, 1000000}; nanosleep(&ts, nullptr);
     }
   }
@@ -548,6 +582,8 @@ int mcgpu_destroy(mcgpu_engine *e)
   if (e->side) cudaStreamSynchronize(e->side);
   if (e->sink && e->sink_registered) cudaHostUnregister(e->sink);
   if (e->sink_ev) cudaEventDestroy(e->sink_ev);
+  for (auto &dr : e->drains) cudaEventDestroy(dr.second);
+  for (cudaEvent_t ev : e->ev_free) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->side) cudaStreamDestroy(e->side);
   delete e;
@@ -577,7 +613,7 @@ int mcgpu_set_likelihood(mcgpu_engine *e, int lik, const double *par, int npar)
     if (e->have_state && can_wide != e->wide) return fail(e, MCGPU_ESTATE, "likelihood change would change the state layout: create a new engine");
     e->wide = can_wide;
     if (!e->wide && e->cfg.pl < 1.0 && fast::steps_smem_bytes(e->d, e->cfg.sync, e->M, true) > 200 * 1024)
-      return fail(e, MCGPU_EINVAL, "remote-mixture pool does not fit in shared memory (40 bytes per slot and parameter): choose pool_m with pool_m*nparam <= 5000");
+      return fail(e, MCGPU_EINVAL, "remote-mixture pool does not fit in shared memory (40 bytes per slot and parameter + 16 per slot): choose pool_m with pool_m*nparam <= 4800");
   }
   if (e->lik_dev) { cudaFree(e->lik_dev); e->lik_dev = nullptr; }
   if (!dev.empty()) {
@@ -590,7 +626,7 @@ int mcgpu_set_likelihood(mcgpu_engine *e, int lik, const double *par, int npar)
     const int d = e->d, L = d / 2;
     if (!e->factor_cm) { CK(cudaMalloc((void**)&e->factor_cm, (size_t)d * d * 8)); CK(cudaMalloc((void**)&e->diag_d, sizeof(int))); }
     e->mpad = (e->M + L - 1) / L * L;
-    if (!e->pprep) CK(cudaMalloc((void**)&e->pprep, (size_t)3 * d * e->mpad * 8));
+    if (!e->pprep) CK(cudaMalloc((void**)&e->pprep, ((size_t)3 * d + 1) * e->mpad * 8));   // (mu, h) pairs, sigma, n_s
     if (e->gm_t) { cudaFree(e->gm_t); e->gm_t = nullptr; }
     if (lik == MCGPU_GAUSSMIX) {                        // [d][Kpad] (mu, 1/s2) pairs, then [Kpad] log w; padding has weight 0
       e->kpad = (K + 2 * L - 1) / (2 * L) * (2 * L);
@@ -627,6 +663,15 @@ int mcgpu_set_covariance(mcgpu_engine *e, const double *incov)
   return MCGPU_OK;
 }
 
+// a fresh run starts here: schedule, tuning counters (window and cumulative) and the pending-boundary flag
+static int state_installed(mcgpu_engine *e)
+{
+  if (!e->verify) CK(cudaMemsetAsync(e->counts, 0, 4 * sizeof(unsigned long long), e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->have_state = true; e->burn_done = 0; e->t_main = 0; e->sampling = false; e->irate = 50; e->tune_pending = false;
+  return MCGPU_OK;
+}
+
 int mcgpu_set_state(mcgpu_engine *e, const double *pinit)
 {
   if (!e || !pinit) return MCGPU_EINVAL;
@@ -657,9 +702,7 @@ int mcgpu_set_state(mcgpu_engine *e, const double *pinit)
     e->launches += 2;
     CK((e->replay_local ? exact::launch_init_loglik : fast::launch_init_loglik)(e->lik, d, p, e->stream));
   }
-  CK(cudaStreamSynchronize(e->stream));
-  e->have_state = true; e->burn_done = 0; e->t_main = 0; e->sampling = false; e->irate = 50;
-  return MCGPU_OK;
+  return state_installed(e);
 }
 
 int mcgpu_set_streams(mcgpu_engine *e, int local_rank, const double *Z, size_t nz, const double *U, size_t nu,
@@ -759,18 +802,65 @@ int mcgpu_sample_begin(mcgpu_engine *e, int nsamp)
   DeviceGuard g(e->dev);
   int rc = ready_to_step(e); if (rc) return rc;
   const int d = e->d;
+  CK(cudaStreamSynchronize(e->side));
   e->nsamp = nsamp; e->t_main = 0; e->sampling = true; e->exchange_pending = false; e->hist_kept = 0; e->sink_sent = 0;
+  e->hist_valid_from = 0;
+  for (auto &dr : e->drains) e->ev_free.push_back(dr.second);
+  e->drains.clear();
   e->nburn_total = (int)e->burn_done;
   const long long need = (nsamp + e->cfg.thin - 1) / e->cfg.thin;
-  if (e->hist && need > e->hist_cap) return fail(e, MCGPU_EINVAL, "history_steps too small for nsamp/thin");
+  if (e->verify && e->hist && need > e->hist_cap) return fail(e, MCGPU_EINVAL, "history_steps too small for nsamp (VERIFY holds the whole run)");
   // mu = 0, psum2 = FPEPS (mcpar.cc:100-103)
   const size_t n = e->verify ? (size_t)e->C * d : (size_t)d * e->ld;
-  std::vector<double> eps(n, MCGPU_FPEPS);
   CK(cudaMemsetAsync(e->mu, 0, n * 8, e->stream));
-  CK(cudaMemcpyAsync(e->ps, eps.data(), n * 8, cudaMemcpyHostToDevice, e->stream));
-  if (!e->verify) CK(cudaMemsetAsync(e->counts + 4, 0, 32, e->stream));
+  fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, e->stream>>>(e->ps, n, MCGPU_FPEPS);
+  CK(cudaGetLastError());
+  if (!e->verify) CK(cudaMemsetAsync(e->counts + 4, 0, 64, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return MCGPU_OK;
+}
+
+// The device history is a ring: before a launch overwrites kept steps that a host sink has not received yet,
+// the engine's stream waits for their drain (an event on the side stream).
+static int ring_guard(mcgpu_engine *e, long long k_hi)
+{
+  const long long need = k_hi - e->hist_cap;               // kept steps < need are about to be overwritten
+  if (need <= 0 || !e->hist) return 0;
+  if (e->sink && e->sink_sent < need) return fail(e, MCGPU_EINVAL, "history_steps is smaller than one exchange window's kept steps: the ring would overwrite rows before they drain");
+  while (!e->drains.empty() && e->drains.front().first < need) { e->ev_free.push_back(e->drains.front().second); e->drains.pop_front(); }
+  if (!e->drains.empty()) {                                // the first drain that covers `need` (drains complete in order)
+    CK(cudaStreamWaitEvent(e->stream, e->drains.front().second, 0));
+    e->ev_free.push_back(e->drains.front().second); e->drains.pop_front();
+  }
+  return 0;
+}
+
+// MCout drain: the kept steps [sink_sent, hist_kept) go to the host sink with asynchronous copies on the side
+// stream (fp32 sink: narrowed on the device first), ring segment by ring segment.
+static int drain_to_sink(mcgpu_engine *e)
+{
+  if (!e->sink || e->hist_kept <= e->sink_sent) return 0;
+  if ((size_t)e->hist_kept > e->sink_rows_cap) return fail(e, MCGPU_EINVAL, "host sink is full: capacity_steps must hold every kept step of the run");
+  const size_t row_elems = (size_t)(e->d + 1) * e->C;
+  CK(cudaEventRecord(e->sink_ev, e->stream));
+  CK(cudaStreamWaitEvent(e->side, e->sink_ev, 0));
+  long long k = e->sink_sent;
+  while (k < e->hist_kept) {
+    const long long ring = k % e->hist_cap, cnt = std::min<long long>(e->hist_kept - k, e->hist_cap - ring);
+    const size_t n0 = (size_t)ring * row_elems, n = (size_t)cnt * row_elems;
+    if (e->sink_f32) {                                       // narrow on the device, then move half the bytes
+      narrow_rows_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, e->side>>>(e->hist + n0, e->hist_f32 + n0, n);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync((float*)(void*)e->sink + (size_t)k * row_elems, e->hist_f32 + n0, n * sizeof(float), cudaMemcpyDeviceToHost, e->side));
+    } else
+      CK(cudaMemcpyAsync(e->sink + (size_t)k * row_elems, e->hist + n0, n * 8, cudaMemcpyDeviceToHost, e->side));
+    k += cnt;
+  }
+  cudaEvent_t ev = event_get(e);
+  CK(cudaEventRecord(ev, e->side));
+  e->drains.emplace_back(e->hist_kept, ev);
+  e->sink_sent = e->hist_kept;
+  return 0;
 }
 
 int mcgpu_sample(mcgpu_engine *e, int nsteps)
@@ -780,12 +870,15 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
   if (e->t_main + nsteps > e->nsamp) return fail(e, MCGPU_EINVAL, "more steps than sample_begin announced");
   DeviceGuard g(e->dev);
   const int sync = e->cfg.sync;
+  if (e->p2p_local && nsteps > sync - (e->t_main % sync))
+    return fail(e, MCGPU_ESTATE, "engines attached with mcgpu_p2p_attach_local advance one exchange window at a time, in turn: use mcgpu_sample_group");
   timer_begin(e);
   int left = nsteps;
   while (left > 0) {
     if (e->exchange_pending) return fail(e, MCGPU_ESTATE, "exchange pending: call mcgpu_exchange_begin/end at every multiple of sync");
     const long long to_boundary = sync - (e->t_main % sync);
     const int n = (int)std::min<long long>(left, to_boundary);
+    if (!e->verify) { int rc = ring_guard(e, (e->t_main + n + e->cfg.thin - 1) / e->cfg.thin); if (rc) return rc; }
     if (e->verify) {
       VerifyParams p; fill_verify_params(e, p);
       p.phase = 1; p.s0 = (int)e->t_main; p.nsteps = n; p.trace_base = (int)(e->nburn_total + e->t_main);
@@ -796,10 +889,10 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
       CK(exact::launch_verify(p, e->Rl, e->stream));
     } else {
       StepParams p; fill_step_params(e, p);
-      p.counts = e->counts + 4;
+      p.counts = e->counts + 4; p.xstat = e->counts + 8;
       p.pool_cur = pool_cur(e);
       fill_p2p(e, p);
-      p.hist = e->hist; p.hist_step0 = 0;
+      p.hist = e->hist; p.hist_ring0 = e->hist ? (int)((e->t_main / e->cfg.thin) % e->hist_cap) : 0;
       // publish (mu, sigma^2) into the next pool only from the launch that ends the window
       double *const publish = ((e->t_main + n) % sync == 0) ? pool_next(e) : nullptr;
       if (e->cfg.coin_group > 0 || e->replay_local) {       // per-group coins: one mixed launch per window
@@ -814,10 +907,11 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
         auto pool_prep = [&]() -> cudaError_t {
           prepped = true; ++e->launches;
           return fast::launch_pool_prep(pool_cur(e), e->M, e->mpad, e->d, reinterpret_cast<double2*>(e->pprep),
-                                        e->pprep + (size_t)2 * e->d * e->mpad, p.arrivals, p.wait_target, p.xflag, e->stream);
+                                        e->pprep + (size_t)2 * e->d * e->mpad, e->pprep + (size_t)3 * e->d * e->mpad,
+                                        p.arrivals, p.wait_target, p.xflag, p.xstat, e->stream);
         };
         auto is_remote = [&](long long tt) {
-          return tt >= sync && !(host_coin(e, (uint32_t)(e->nburn_total + tt)) <= e->cfg.pl);   // mcpar.cc:142-152
+          return tt >= (long long)sync * (1 + e->lag) && !(host_coin(e, (uint32_t)(e->nburn_total + tt)) <= e->cfg.pl);   // mcpar.cc:142-152
         };
         static const int plan = getenv("MCGPU_PLAN") ? atoi(getenv("MCGPU_PLAN")) : 1;
         uint32_t mask = 0;
@@ -847,20 +941,7 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
     }
     e->t_main += n; left -= n;
     e->hist_kept = (e->t_main + e->cfg.thin - 1) / e->cfg.thin;
-    if (e->sink && e->hist_kept > e->sink_sent) {          // MCout drain: async D2H on the side stream
-      const size_t row_bytes = (size_t)(e->d + 1) * 8 * e->C;
-      CK(cudaEventRecord(e->sink_ev, e->stream));
-      CK(cudaStreamWaitEvent(e->side, e->sink_ev, 0));
-      if (e->sink_f32) {                                     // narrow on the device, then move half the bytes
-        const size_t n0 = (size_t)e->sink_sent * e->C * (e->d + 1), n = (size_t)(e->hist_kept - e->sink_sent) * e->C * (e->d + 1);
-        narrow_rows_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, e->side>>>(e->hist + n0, e->hist_f32 + n0, n);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync((float*)(void*)e->sink + n0, e->hist_f32 + n0, n * sizeof(float), cudaMemcpyDeviceToHost, e->side));
-      } else
-      CK(cudaMemcpyAsync((char*)e->sink + (size_t)e->sink_sent * row_bytes, (const char*)e->hist + (size_t)e->sink_sent * row_bytes,
-                         (size_t)(e->hist_kept - e->sink_sent) * row_bytes, cudaMemcpyDeviceToHost, e->side));
-      e->sink_sent = e->hist_kept;
-    }
+    if (e->hist) { int rc = drain_to_sink(e); if (rc) return rc; }
     if (e->t_main % sync == 0) {
       if (e->sharded && !e->p2p) e->exchange_pending = true;   // caller all-gathers the published slices
       else if (e->verify) e->snap_cur ^= 1;
@@ -978,6 +1059,28 @@ int mcgpu_p2p_attach_local(mcgpu_engine *const *engines, int world)
     }
     CK(cudaStreamSynchronize(e->stream));
     int rc = p2p_finish(e, world, bases); if (rc) return rc;
+    e->p2p_local = true;
+  }
+  return MCGPU_OK;
+}
+
+// One host thread drives `world` peer-to-peer engines: their windows are enqueued in turn, one exchange window at
+// a time, so that a window kernel waiting for its peers' publications is never queued in front of the launches
+// that make them (the launch queue is finite, and engines may share a device).
+int mcgpu_sample_group(mcgpu_engine *const *engines, int world, int nsteps)
+{
+  if (!engines || world < 1 || nsteps < 0) return MCGPU_EINVAL;
+  for (int r = 0; r < world; ++r) {
+    if (!engines[r]) return MCGPU_EINVAL;
+    if (engines[r]->t_main != engines[0]->t_main || engines[r]->cfg.sync != engines[0]->cfg.sync)
+      return fail(engines[r], MCGPU_ESTATE, "engines of a group are out of step");
+  }
+  const int sync = engines[0]->cfg.sync;
+  int left = nsteps;
+  while (left > 0) {
+    const int n = (int)std::min<long long>(left, sync - (engines[0]->t_main % sync));
+    for (int r = 0; r < world; ++r) { int rc = mcgpu_sample(engines[r], n); if (rc) return rc; }
+    left -= n;
   }
   return MCGPU_OK;
 }
@@ -1057,7 +1160,8 @@ static int attach_host_sink(mcgpu_engine *e, void *rows_v, size_t capacity_steps
   e->sink = nullptr; e->sink_rows_cap = 0; e->sink_f32 = false;
   if (!rows) return MCGPU_OK;
   if (!e->hist) return fail(e, MCGPU_ESTATE, "engine was created with history_steps = 0");
-  if ((long long)capacity_steps < e->hist_cap) return fail(e, MCGPU_EINVAL, "host sink smaller than history_steps");
+  if (capacity_steps < 1) return fail(e, MCGPU_EINVAL, "host sink holds no kept step");
+  if (e->hist_cap * e->cfg.thin < e->cfg.sync && !e->verify) return fail(e, MCGPU_EINVAL, "history_steps must hold at least one exchange window's kept steps to drain into a host sink");
   cudaPointerAttributes at;
   const bool pinned = cudaPointerGetAttributes(&at, rows) == cudaSuccess && at.type == cudaMemoryTypeHost;
   cudaGetLastError();
@@ -1133,7 +1237,7 @@ int mcgpu_get_musig(mcgpu_engine *e, int local_rank, double *musig)
     const size_t nm = (size_t)2 * e->N * e->d;
     CK(cudaMemcpyAsync(musig, e->musig + (size_t)local_rank * nm, nm * 8, cudaMemcpyDeviceToHost, e->stream));
   } else {
-    CK(cudaMemcpyAsync(musig, pool_cur(e), (size_t)e->M * e->d * 16, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(musig, pool_newest(e), (size_t)e->M * e->d * 16, cudaMemcpyDeviceToHost, e->stream));
   }
   CK(cudaStreamSynchronize(e->stream));
   return MCGPU_OK;
@@ -1164,10 +1268,17 @@ int mcgpu_history_read(mcgpu_engine *e, int64_t first_step, int64_t count, doubl
   if (!e || !rows || first_step < 0 || count < 0) return MCGPU_EINVAL;
   if (!e->hist) return fail(e, MCGPU_ESTATE, "engine was created with history_steps = 0");
   if (first_step + count > e->hist_kept) return fail(e, MCGPU_EINVAL, "history range not yet produced");
+  if (count > 0 && first_step < std::max(e->hist_valid_from, e->hist_kept - e->hist_cap))
+    return fail(e, MCGPU_EINVAL, "history range no longer on the device (the ring holds the last history_steps kept steps; rows before a checkpoint load are not restored)");
   DeviceGuard g(e->dev);
   const size_t row_bytes = (size_t)(e->d + 1) * 8;
+  if (count > 0 && first_step % e->hist_cap + count > e->hist_cap) {   // the range wraps around the ring: two reads
+    const int64_t c1 = e->hist_cap - first_step % e->hist_cap;
+    int rc = mcgpu_history_read(e, first_step, c1, rows); if (rc) return rc;
+    return mcgpu_history_read(e, first_step + c1, count - c1, rows + (size_t)c1 * e->C * (e->d + 1));
+  }
   const size_t total = (size_t)count * e->C * row_bytes;
-  const char *src = (const char*)e->hist + (size_t)first_step * e->C * row_bytes;
+  const char *src = (const char*)e->hist + (size_t)(first_step % e->hist_cap) * e->C * row_bytes;
   if (total == 0) return MCGPU_OK;
   {
     cudaPointerAttributes at;
@@ -1207,27 +1318,47 @@ int mcgpu_history_read(mcgpu_engine *e, int64_t first_step, int64_t count, doubl
   return MCGPU_OK;
 }
 
+// the kept steps the device still holds, [max(valid_from, kept - cap), kept), as at most two contiguous ring ranges
+namespace {
+struct HistSeg { long long ring0, kept0, count; };
+int hist_segments(const mcgpu_engine *e, HistSeg seg[2])
+{
+  const long long lo = std::max(e->hist_valid_from, e->hist_kept - e->hist_cap), hi = e->hist_kept;
+  if (hi <= lo) return 0;
+  const long long r0 = lo % e->hist_cap, c0 = std::min(hi - lo, e->hist_cap - r0);
+  seg[0] = {r0, lo, c0};
+  if (c0 == hi - lo) return 1;
+  seg[1] = {0, lo + c0, hi - lo - c0};
+  return 2;
+}
+}  // namespace
+
 int mcgpu_history_maxlike(mcgpu_engine *e, double *out)
 {
   if (!e || !out) return MCGPU_EINVAL;
   if (!e->hist) return fail(e, MCGPU_ESTATE, "engine was created with history_steps = 0");
   DeviceGuard g(e->dev);
-  const long long nrows = e->hist_kept * e->C;
-  if (nrows == 0) return fail(e, MCGPU_ESTATE, "history is empty");
+  HistSeg seg[2]; const int nseg = hist_segments(e, seg);
+  if (nseg == 0) return fail(e, MCGPU_ESTATE, "history is empty");
   const int nb = 296;
   double *bv = nullptr; long long *br = nullptr;
   CK(cudaMallocAsync((void**)&bv, nb * 8, e->stream)); CK(cudaMallocAsync((void**)&br, nb * 8, e->stream));
-  ++e->launches;
-  argmax_rows_kernel<<<nb, 256, 0, e->stream>>>(e->hist, nrows, e->d + 1, bv, br);
-  CK(cudaGetLastError());
   std::vector<double> hv(nb); std::vector<long long> hr(nb);
-  CK(cudaMemcpyAsync(hv.data(), bv, nb * 8, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaMemcpyAsync(hr.data(), br, nb * 8, cudaMemcpyDeviceToHost, e->stream));
+  long long best = -1, best_abs = -1; double val = -INFINITY;   // best_abs: row index in kept-step order (first occurrence wins, mcout.cc:138)
+  for (int sg = 0; sg < nseg; ++sg) {
+    ++e->launches;
+    argmax_rows_kernel<<<nb, 256, 0, e->stream>>>(e->hist + (size_t)seg[sg].ring0 * e->C * (e->d + 1), seg[sg].count * e->C, e->d + 1, bv, br);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hv.data(), bv, nb * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(hr.data(), br, nb * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < nb; ++i) {
+      if (hr[i] < 0) continue;
+      const long long abs_row = seg[sg].kept0 * e->C + hr[i];
+      if (best < 0 || hv[i] > val || (hv[i] == val && abs_row < best_abs)) { best = seg[sg].ring0 * e->C + hr[i]; best_abs = abs_row; val = hv[i]; }
+    }
+  }
   CK(cudaFreeAsync(bv, e->stream)); CK(cudaFreeAsync(br, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  long long best = -1; double val = -INFINITY;
-  for (int i = 0; i < nb; ++i)
-    if (hr[i] >= 0 && (best < 0 || hv[i] > val || (hv[i] == val && hr[i] < best))) { best = hr[i]; val = hv[i]; }
   if (best < 0) return fail(e, MCGPU_ESTATE, "history holds no finite log-likelihood");
   CK(cudaMemcpy(out, e->hist + (size_t)best * (e->d + 1), (size_t)(e->d + 1) * 8, cudaMemcpyDeviceToHost));
   return MCGPU_OK;
@@ -1239,14 +1370,18 @@ int mcgpu_history_moments(mcgpu_engine *e, double *mean, double *cov)
   if (!e->hist) return fail(e, MCGPU_ESTATE, "engine was created with history_steps = 0");
   DeviceGuard g(e->dev);
   const int d = e->d; const int nq = d + d * (d + 1) / 2;
-  const long long nrows = e->hist_kept * e->C;
-  if (nrows == 0) return fail(e, MCGPU_ESTATE, "history is empty");
+  HistSeg seg[2]; const int nseg = hist_segments(e, seg);
+  if (nseg == 0) return fail(e, MCGPU_ESTATE, "history is empty");
+  long long nrows = 0;
   double *acc = nullptr;
   CK(cudaMallocAsync((void**)&acc, nq * 8, e->stream));
   CK(cudaMemsetAsync(acc, 0, nq * 8, e->stream));
-  ++e->launches;
-  moments_kernel<<<dim3(592, nq), 256, 0, e->stream>>>(e->hist, nrows, d, acc);
-  CK(cudaGetLastError());
+  for (int sg = 0; sg < nseg; ++sg) {
+    ++e->launches;
+    moments_kernel<<<dim3(592, nq), 256, 0, e->stream>>>(e->hist + (size_t)seg[sg].ring0 * e->C * (d + 1), seg[sg].count * e->C, d, acc);
+    CK(cudaGetLastError());
+    nrows += seg[sg].count * e->C;
+  }
   std::vector<double> h(nq);
   CK(cudaMemcpyAsync(h.data(), acc, nq * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaFreeAsync(acc, e->stream));
@@ -1266,12 +1401,12 @@ int mcgpu_history_moments(mcgpu_engine *e, double *mean, double *cov)
 namespace {
 struct CkptHeader {
   char magic[8]; int32_t abi, d, lik, wide, M, sync, thin, coin_group; int64_t C, N, chain0, ld;
-  int64_t burn_done, t_main, npub; int32_t nsamp, irate, nburn_total, sampling, tune_pending, have_factor;
+  int64_t burn_done, t_main, npub; int32_t nsamp, irate, nburn_total, sampling, tune_pending, have_factor, remote_mode, pool_lag;
   uint64_t seed; double pl;
 };
 size_t ckpt_bytes(const mcgpu_engine *e)
 {
-  return sizeof(CkptHeader) + ((size_t)3 * e->d * e->ld + e->ld + (size_t)e->d * e->d) * 8 + 8 * 8 + 3 * e->pool_bytes;
+  return sizeof(CkptHeader) + ((size_t)3 * e->d * e->ld + e->ld + (size_t)e->d * e->d) * 8 + 12 * 8 + NPOOL * e->pool_bytes;
 }
 }  // namespace
 
@@ -1292,17 +1427,17 @@ int mcgpu_checkpoint_save(mcgpu_engine *e, void *buf, size_t bytes)
   if (e->exchange_pending) return fail(e, MCGPU_ESTATE, "finish the pending exchange first");
   DeviceGuard g(e->dev);
   CkptHeader h; memset(&h, 0, sizeof h);
-  memcpy(h.magic, "MCGPUCK1", 8);
+  memcpy(h.magic, "MCGPUCK2", 8);
   h.abi = MCGPU_ABI_VERSION; h.d = e->d; h.lik = e->lik; h.wide = e->wide; h.M = e->M; h.sync = e->cfg.sync; h.thin = e->cfg.thin;
   h.coin_group = e->cfg.coin_group; h.C = e->C; h.N = e->N; h.chain0 = e->cfg.chain0; h.ld = e->ld;
   h.burn_done = e->burn_done; h.t_main = e->t_main; h.npub = e->npub; h.nsamp = e->nsamp; h.irate = e->irate;
   h.nburn_total = e->nburn_total; h.sampling = e->sampling; h.tune_pending = e->tune_pending; h.have_factor = e->have_factor;
-  h.seed = e->cfg.seed; h.pl = e->cfg.pl;
+  h.seed = e->cfg.seed; h.pl = e->cfg.pl; h.remote_mode = e->remote_mode; h.pool_lag = e->lag;
   char *q = static_cast<char*>(buf);
   memcpy(q, &h, sizeof h); q += sizeof h;
   const size_t ns = (size_t)e->d * e->ld * 8;
   struct { const void *src; size_t n; } parts[] = {{e->x, ns}, {e->mu, ns}, {e->ps, ns}, {e->ly, (size_t)e->ld * 8},
-                                                   {e->factor, (size_t)e->d * e->d * 8}, {e->counts, 64}, {e->xchg, 3 * e->pool_bytes}};
+                                                   {e->factor, (size_t)e->d * e->d * 8}, {e->counts, 96}, {e->xchg, NPOOL * e->pool_bytes}};
   for (auto &pt : parts) { CK(cudaMemcpyAsync(q, pt.src, pt.n, cudaMemcpyDeviceToHost, e->stream)); q += pt.n; }
   CK(cudaStreamSynchronize(e->stream));
   return MCGPU_OK;
@@ -1315,22 +1450,21 @@ int mcgpu_checkpoint_load(mcgpu_engine *e, const void *buf, size_t bytes)
   if (e->lik < 0) return fail(e, MCGPU_ESTATE, "set_likelihood first (the likelihood is not part of a checkpoint)");
   if (bytes < ckpt_bytes(e)) return fail(e, MCGPU_EINVAL, "checkpoint truncated");
   CkptHeader h; memcpy(&h, buf, sizeof h);
-  if (memcmp(h.magic, "MCGPUCK1", 8) || h.abi != MCGPU_ABI_VERSION) return fail(e, MCGPU_EINVAL, "not a checkpoint of this ABI");
+  if (memcmp(h.magic, "MCGPUCK2", 8) || h.abi != MCGPU_ABI_VERSION) return fail(e, MCGPU_EINVAL, "not a checkpoint of this ABI");
   if (h.d != e->d || h.C != e->C || h.N != e->N || h.chain0 != e->cfg.chain0 || h.ld != e->ld || h.M != e->M || h.lik != e->lik ||
       h.wide != (int)e->wide || h.sync != e->cfg.sync || h.thin != e->cfg.thin || h.coin_group != e->cfg.coin_group ||
-      h.seed != e->cfg.seed || h.pl != e->cfg.pl)
+      h.seed != e->cfg.seed || h.pl != e->cfg.pl || h.remote_mode != e->remote_mode || h.pool_lag != e->lag)
     return fail(e, MCGPU_EINVAL, "checkpoint was taken by an engine of a different shape / likelihood / seed");
-  const long long need = ((long long)h.nsamp + e->cfg.thin - 1) / e->cfg.thin;
-  if (h.sampling && e->hist && need > e->hist_cap) return fail(e, MCGPU_EINVAL, "history_steps too small for the checkpointed run");
   DeviceGuard g(e->dev);
+  CK(cudaStreamSynchronize(e->side));
   const char *q = static_cast<const char*>(buf) + sizeof h;
   const size_t ns = (size_t)e->d * e->ld * 8;
   struct { void *dst; size_t n; } parts[] = {{e->x, ns}, {e->mu, ns}, {e->ps, ns}, {e->ly, (size_t)e->ld * 8},
-                                             {e->factor, (size_t)e->d * e->d * 8}, {e->counts, 64}, {e->xchg, 3 * e->pool_bytes}};
+                                             {e->factor, (size_t)e->d * e->d * 8}, {e->counts, 96}, {e->xchg, NPOOL * e->pool_bytes}};
   for (auto &pt : parts) { CK(cudaMemcpyAsync(pt.dst, q, pt.n, cudaMemcpyHostToDevice, e->stream)); q += pt.n; }
   if (e->p2p) {   // peers restore the same epoch: every publication up to npub counts as arrived
     const unsigned long long arrived = (unsigned long long)e->M * arrivals_per_slot(e) * (unsigned long long)h.npub;
-    CK(cudaMemcpyAsync(e->xchg + 3 * e->pool_bytes, &arrived, sizeof arrived, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->xchg + NPOOL * e->pool_bytes, &arrived, sizeof arrived, cudaMemcpyHostToDevice, e->stream));
   }
   if (e->wide) { ++e->launches; CK(fast::launch_factor_prep(e->factor, e->factor_cm, e->d, e->diag_d, e->stream)); }   // derived copies
   CK(cudaStreamSynchronize(e->stream));
@@ -1338,6 +1472,9 @@ int mcgpu_checkpoint_load(mcgpu_engine *e, const void *buf, size_t bytes)
   e->nburn_total = h.nburn_total; e->sampling = h.sampling != 0; e->tune_pending = h.tune_pending != 0;
   e->have_factor = h.have_factor != 0; e->have_state = true; e->exchange_pending = false;
   e->hist_kept = (e->t_main + e->cfg.thin - 1) / e->cfg.thin; e->sink_sent = e->hist_kept;
+  e->hist_valid_from = e->hist_kept;                       // the history is not part of the blob: earlier rows are not on this device
+  for (auto &dr : e->drains) e->ev_free.push_back(dr.second);
+  e->drains.clear();
   return MCGPU_OK;
 }
 
@@ -1350,15 +1487,16 @@ int mcgpu_get_stats(mcgpu_engine *e, mcgpu_stats *out)
   memset(out, 0, sizeof *out);
   out->burn_steps = e->burn_done; out->main_steps = e->t_main; out->kernel_launches = e->launches;
   out->history_rows = e->hist_kept * e->C; out->device_ms = e->ms_accum;
-  unsigned long long h[8] = {0};
+  unsigned long long h[12] = {0};
   if (e->verify) {
     CK(cudaMemcpy(h, e->rstats, 32, cudaMemcpyDeviceToHost));
     out->remote_steps = (int64_t)h[0]; out->remote_iterations = (int64_t)h[1];
     out->accepted = (int64_t)h[2]; out->tried = (int64_t)h[3];
   } else {
-    CK(cudaMemcpy(h, e->counts, 64, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h, e->counts, 96, cudaMemcpyDeviceToHost));
     out->accepted = (int64_t)h[4]; out->tried = (int64_t)h[5];
     out->remote_steps = (int64_t)h[6]; out->remote_iterations = (int64_t)h[7];
+    out->exchange_wait_ns = (int64_t)h[8]; out->exchange_waits = (int64_t)h[9];
   }
   return MCGPU_OK;
 }
@@ -1374,7 +1512,7 @@ int mcgpu_device_ptr(mcgpu_engine *e, int which, void **ptr, size_t *bytes)
     case 2: *ptr = e->mu; nb = st; break;
     case 3: *ptr = e->ps; nb = st; break;
     case 4: *ptr = e->hist; nb = (size_t)e->hist_cap * e->C * (e->d + 1) * 8; break;
-    case 5: *ptr = e->verify ? e->snap[e->snap_cur] : pool_cur(e); nb = e->verify ? (size_t)2 * e->N * e->d * 8 : (size_t)e->M * e->d * 16; break;
+    case 5: *ptr = e->verify ? e->snap[e->snap_cur] : pool_newest(e); nb = e->verify ? (size_t)2 * e->N * e->d * 8 : (size_t)e->M * e->d * 16; break;
     default: return fail(e, MCGPU_EINVAL, "unknown buffer id");
   }
   if (bytes) *bytes = nb;
@@ -1409,24 +1547,57 @@ int mcgpu_loglik(int device, int lik, int nparam, const double *par, int npar, i
 int mcgpu_qriguess(int device, int rank, int npset, int nparam, const double *plo, const double *phi, double *pout)
 {
   if (!plo || !phi || !pout || npset < 0 || rank < 0) return fail(nullptr, MCGPU_EINVAL, "bad argument");
-  if (nparam < 1 || nparam > 16) return fail(nullptr, MCGPU_EINVAL, "Sobol table covers 1..16 dimensions");
+  if (nparam < 1 || nparam > SOBOL_JK_NDIM) return fail(nullptr, MCGPU_EINVAL, "Sobol table covers 1..64 dimensions");
   if (mcgpu_device_count() <= device || device < 0) return fail(nullptr, MCGPU_ENODEVICE, "no usable CUDA device (this engine has no CPU path)");
-  const int ntot = npset * nparam;                                  // mcutil.cc:19
+  const size_t ntot = (size_t)npset * (size_t)nparam;               // mcutil.cc:19 (an int there)
   if (ntot == 0) return MCGPU_OK;
   DeviceGuard g(device);
   std::vector<uint32_t> dirs((size_t)nparam * 32);
   for (int k = 0; k < nparam; ++k) sobol_dirs(k, &dirs[(size_t)k * 32]);
   uint32_t *dd = nullptr; double *dlo = nullptr, *dhi = nullptr, *dout = nullptr;
   CK0(cudaMalloc((void**)&dd, dirs.size() * 4)); CK0(cudaMalloc((void**)&dlo, nparam * 8));
-  CK0(cudaMalloc((void**)&dhi, nparam * 8)); CK0(cudaMalloc((void**)&dout, (size_t)ntot * 8));
+  CK0(cudaMalloc((void**)&dhi, nparam * 8)); CK0(cudaMalloc((void**)&dout, ntot * 8));
   CK0(cudaMemcpy(dd, dirs.data(), dirs.size() * 4, cudaMemcpyHostToDevice));
   CK0(cudaMemcpy(dlo, plo, nparam * 8, cudaMemcpyHostToDevice)); CK0(cudaMemcpy(dhi, phi, nparam * 8, cudaMemcpyHostToDevice));
   const unsigned long long first = rank > 0 ? (unsigned long long)rank * (unsigned long long)ntot : 0ull;   // :22-23
-  sobol_box_kernel<<<(ntot + 255) / 256, 256>>>(dd, nparam, first, ntot, dlo, dhi, dout);
+  sobol_box_kernel<<<(unsigned)std::min<size_t>((ntot + 255) / 256, 148 * 32), 256>>>(dd, nparam, first, ntot, dlo, dhi, dout, 0);
   CK0(cudaGetLastError());
-  CK0(cudaMemcpy(pout, dout, (size_t)ntot * 8, cudaMemcpyDeviceToHost));
+  CK0(cudaMemcpy(pout, dout, ntot * 8, cudaMemcpyDeviceToHost));
   cudaFree(dd); cudaFree(dlo); cudaFree(dhi); cudaFree(dout);
   return MCGPU_OK;
+}
+
+// qriguess straight into the engine's state: chain g = chain0 + j starts at Sobol point first_point + g.
+int mcgpu_set_state_sobol(mcgpu_engine *e, const double *plo, const double *phi, uint64_t first_point)
+{
+  if (!e || !plo || !phi) return MCGPU_EINVAL;
+  if (e->lik < 0) return fail(e, MCGPU_ESTATE, "set_likelihood first");
+  if (e->verify) return fail(e, MCGPU_ESTATE, "VERIFY mode takes its initial points from the host (mcgpu_set_state)");
+  DeviceGuard g(e->dev);
+  const int d = e->d;
+  std::vector<uint32_t> dirs((size_t)d * 32);
+  for (int k = 0; k < d; ++k) sobol_dirs(k, &dirs[(size_t)k * 32]);
+  std::vector<double> box(plo, plo + d); box.insert(box.end(), phi, phi + d);
+  uint32_t *dd = nullptr; double *dbox = nullptr;
+  CK(cudaMallocAsync((void**)&dd, dirs.size() * 4, e->stream)); CK(cudaMallocAsync((void**)&dbox, box.size() * 8, e->stream));
+  CK(cudaMemcpyAsync(dd, dirs.data(), dirs.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(dbox, box.data(), box.size() * 8, cudaMemcpyHostToDevice, e->stream));
+  const size_t ntot = (size_t)e->C * d;
+  const unsigned long long first = ((unsigned long long)first_point + (unsigned long long)e->cfg.chain0) * (unsigned long long)d;
+  ++e->launches;
+  sobol_box_kernel<<<(unsigned)std::min<size_t>((ntot + 255) / 256, 148 * 32), 256, 0, e->stream>>>(dd, d, first, ntot, dbox, dbox + d, e->x, e->wide ? 0 : e->ld);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));                    // dirs / box are host temporaries
+  CK(cudaFreeAsync(dd, e->stream)); CK(cudaFreeAsync(dbox, e->stream));
+  ++e->launches;
+  if (e->wide) {
+    LikSpec L; L.lik = e->lik; L.d = d; L.k = e->lik_k; memcpy(L.lp, e->lp, sizeof L.lp); L.dev = e->lik_dev;
+    CK(exact::launch_loglik_aos(L, e->x, e->ly, (int)e->C, e->stream));   // L(nchain, pvals, lylast), mcpar.cc:53
+  } else {
+    StepParams p; fill_step_params(e, p);
+    CK((e->replay_local ? exact::launch_init_loglik : fast::launch_init_loglik)(e->lik, d, p, e->stream));
+  }
+  return state_installed(e);
 }
 
 int mcgpu_measure_fp64_peak(int device, double *tflops)

@@ -92,6 +92,7 @@ struct StepParams {
   int t0;                          // main-phase index of the first step (main kernels)
   int nburn_total;                 // replay offsets: burn-in length of the run
   int sync, coin_group;
+  int first_remote_t;              // main steps before this one are local: sync * (1 + pool_lag)  (mcpar.cc:142-146 with lag 0)
   double pl;
   uint32_t plan_mask; int plan_valid;   // PH_MIXED with a job-wide coin: bit k = step k of this launch is remote
   // remote-proposal pool: [pool_m][d][2] (mu, sigma^2); slot s is global chain s*pool_stride
@@ -100,12 +101,16 @@ struct StepParams {
   // straight into every peer's next pool buffer over NVLink, then bump the peer's arrival counter
   char *const *peers; int npeers; long long next_off, arr_off;
   // consumer side: wait until `arrivals` (this GPU's counter) reaches wait_target before reading the pool
-  const unsigned long long *arrivals; unsigned long long wait_target; int *xflag;
+  // (wait_target: all slots of the publication this launch READS; pub_wait_target: all slots of the
+  // publication before the one it WRITES -- equal without pool lag)
+  const unsigned long long *arrivals; unsigned long long wait_target, pub_wait_target; int *xflag;
+  unsigned long long *xstat;       // {ns CTA 0 spent waiting for arrivals, launches that waited}
   int pool_m; long long pool_stride;
   int pool_in_smem;
   int exact_tests;                 // audit mode: accept / rejection tests always in fp64 (MCGPU_EXACT_TESTS=1)
   // sample history: rows (p..., logL), kept step major, then hosted chain
-  double *hist; int thin; long long hist_step0;   // kept-step index base of the history buffer
+  // (a ring of hist_cap kept steps; the first kept step of this launch goes to ring row hist_ring0)
+  double *hist; int thin; int hist_cap, hist_ring0;
   // replay-local streams
   const double *Z, *U; long long nz, nu; int *overrun;
   // likelihood parameters
@@ -131,8 +136,11 @@ struct WideParams {
   // straight into every peer's next pool buffer over NVLink, then bump the peer's arrival counter
   char *const *peers; int npeers; long long next_off, arr_off;
   // consumer side: wait until `arrivals` (this GPU's counter) reaches wait_target before reading the pool
-  const unsigned long long *arrivals; unsigned long long wait_target; int *xflag;
-  double *hist; int thin; long long hist_step0;
+  const unsigned long long *arrivals; unsigned long long wait_target, pub_wait_target; int *xflag;
+  unsigned long long *xstat;
+  double *hist; int thin; int hist_cap, hist_ring0;
+  const double *pnb;               // [Mpad] n_s = -1/2 sum_i log sig2_si (remote mode 1: normalised components)
+  int summix;                      // remote mode 1
   // likelihood: GaussMix parameters, component fastest: gm2 [D][Kpad] = (mu, 1/s2) pairs, gm_lw [Kpad] = log w
   const double2 *gm2; const double *gm_lw; int kpad;
 };
@@ -187,10 +195,16 @@ __device__ __forceinline__ void wait_arrivals_thread(const unsigned long long *a
   }
 }
 // one thread per CTA waits (bounded: 10 s, then the engine reports MCGPU_EPEER) until all pool slots of
-// the exchange have arrived in this GPU's memory; callers follow with __syncthreads()
-__device__ __forceinline__ void wait_arrivals(const unsigned long long *arrivals, unsigned long long target, int *xflag)
+// the exchange have arrived in this GPU's memory; callers follow with __syncthreads().  CTA 0 -- the first
+// one dispatched -- accounts the time it waited in xstat (the exchange time of mcgpu_stats / the log file).
+__device__ __forceinline__ void wait_arrivals(const unsigned long long *arrivals, unsigned long long target, int *xflag,
+                                              unsigned long long *xstat = nullptr)
 {
-  if (threadIdx.x == 0) wait_arrivals_thread(arrivals, target, xflag);
+  if (threadIdx.x != 0) return;
+  if (!target || ld_acquire_sys(arrivals) >= target) return;
+  const unsigned long long t0 = global_ns();
+  wait_arrivals_thread(arrivals, target, xflag);
+  if (xstat && blockIdx.x == 0) { atomicAdd(xstat, global_ns() - t0); atomicAdd(xstat + 1, 1ull); }
 }
 
 }  // namespace mcgpu

@@ -95,10 +95,13 @@ MCGPU_HD double mc_exp(double x, const MathTables &T)
 
 // log(x) for normal positive x.  0 and subnormals give -inf (their logs, below -708, only
 // ever mark proposals that are rejected anyway), negative x gives NaN, +inf and NaN pass through.
-MCGPU_HD double mc_log(double x, const MathTables &T)
+// CHECKED = false: the caller guarantees a normal, positive, finite x (the Box-Muller argument
+// (w+1) 2^-32 in (0, 1]; 1 + e^-t in [1, 2]) and the special-case test disappears.
+template <bool CHECKED>
+MCGPU_HD double mc_log_t(double x, const MathTables &T)
 {
   const int hi = mc_hi(x);
-  if (hi < 0x00100000 || hi >= 0x7ff00000)             // <= 0, subnormal, inf, NaN
+  if (CHECKED && (hi < 0x00100000 || hi >= 0x7ff00000))   // <= 0, subnormal, inf, NaN
     return hi < 0 && x < 0.0 ? NAN : (hi >= 0x7ff00000 && hi > 0 ? x : -INFINITY);
   const int idx = (hi >> 13) & 127;
   const int big = idx >= 53;                           // m >= 1.4140625: use m/2, exponent + 1
@@ -115,6 +118,31 @@ MCGPU_HD double mc_log(double x, const MathTables &T)
   double res = fma(ef, MCK(15), l);                    // exact-ish: LN2_HI has 26 trailing zero bits
   res += lg;
   return fma(ef, MCK(16), res);
+}
+MCGPU_HD double mc_log(double x, const MathTables &T) { return mc_log_t<true>(x, T); }
+MCGPU_HD double mc_log_pos(double x, const MathTables &T) { return mc_log_t<false>(x, T); }
+
+// sqrt(L) for 0 <= L < 2^100 (the Box-Muller radius: L = -2 ln v <= 44.4).  CUDA's double sqrt is
+// 27 issue slots (MUFU.RSQ64H, a Newton chain and a special-case branch); here the SFU's fp32
+// reciprocal square root y0 = (1 + d) / sqrt(L), |d| <= 2^-21 (twice the documented bound), seeds two
+// Newton corrections r <- r + (L - r^2) y0 / 2 of r = L y0, each with an exact fma residual: the
+// relative error e of r becomes -e^2/2 - e d, i.e. 2^-21 -> 2^-41 -> 2^-62, and the last fma rounds once:
+// <= 0.51 ulp in 2 DMUL + 4 DFMA.  L = 0 gives 0.  `seed_err` perturbs the host stand-in of the SFU seed
+// so that the accuracy test covers the worst case.
+MCGPU_HD double mc_sqrt_pos(double L, double seed_err = 0.0)
+{
+#ifdef __CUDA_ARCH__
+  float y0f;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0f) : "f"(fmaxf((float)L, 1.0e-30f)));
+  const double y0 = (double)y0f;
+#else
+  const float lf = (float)L > 1.0e-30f ? (float)L : 1.0e-30f;
+  const double y0 = (double)(float)((1.0 / sqrt((double)lf)) * (1.0 + seed_err));
+#endif
+  const double h = 0.5 * y0;
+  double r = L * y0;
+  r = fma(fma(-r, r, L), h, r);
+  return fma(fma(-r, r, L), h, r);
 }
 
 // (sin, cos)(2 pi u) for u in [0, 1]

@@ -28,6 +28,8 @@ static cudaError_t launch_lik_d(int rngk, int phase, const StepParams &p, size_t
   else if (rngk == RNG_PHILOX && phase == PH_MIXED) MCGPU_GO(RNG_PHILOX, PH_MIXED);
   else if (rngk == RNG_PHILOX && phase == PH_LOCAL) MCGPU_GO(RNG_PHILOX, PH_LOCAL);
   else if (rngk == RNG_PHILOX && phase == PH_REMOTE) MCGPU_GO(RNG_PHILOX, PH_REMOTE);
+  else if (rngk == RNG_PHILOX && phase == PH_MIXED_SUM) MCGPU_GO(RNG_PHILOX, PH_MIXED_SUM);
+  else if (rngk == RNG_PHILOX && phase == PH_REMOTE_SUM) MCGPU_GO(RNG_PHILOX, PH_REMOTE_SUM);
 #endif
   else return cudaErrorInvalidValue;
 #undef MCGPU_GO
@@ -53,14 +55,17 @@ bool steps_supported(int lik, int d)
   return false;
 }
 
-size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem)
+// pool (only the phases that can take a remote step stage it): (mu, h) + sigma in fp64, (g mu, g) + (sigma, mu)
+// in fp32 = 40 bytes per slot and parameter, + n_s (fp64) and nb_s (fp32) per slot
+size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool with_pool)
 {
-  return sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)d * d + (size_t)((nsteps + 1) & ~1) + (pool_in_smem ? (size_t)((pool_m + 7) & ~7) * d * 5 : 0));   // pool: (mu, h) + sigma in fp64; (g mu, g) + (sigma, mu) in fp32
+  const size_t mpad = (size_t)((pool_m + 7) & ~7);
+  return sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)d * d + (size_t)((nsteps + 1) & ~1) + (with_pool ? mpad * d * 5 + mpad * 2 : 0));
 }
 
 cudaError_t launch_steps(int lik, int d, int rngk, int phase, const StepParams &p, cudaStream_t st)
 {
-  const size_t smem = steps_smem_bytes(d, p.nsteps, p.pool_m, p.pool_in_smem != 0);
+  const size_t smem = steps_smem_bytes(d, p.nsteps, p.pool_m, phase != PH_BURN && phase != PH_LOCAL);
   switch (lik) {
     case MCGPU_ROSENBROCK1:  return launch_lik<MCGPU_ROSENBROCK1>(d, rngk, phase, p, smem, st);
     case MCGPU_GAUSSMIX:     return launch_lik<MCGPU_GAUSSMIX>(d, rngk, phase, p, smem, st);

@@ -29,6 +29,7 @@ static cudaError_t launch_wide_d(int phase, const WideParams &p, cudaStream_t st
     case PH_BURN:   mh_wide_kernel<LIK, D, NCH, PH_BURN><<<grid, block, smem, st>>>(p); break;
     case PH_LOCAL:  mh_wide_kernel<LIK, D, NCH, PH_LOCAL><<<grid, block, smem, st>>>(p); break;
     case PH_REMOTE: mh_wide_kernel<LIK, D, NCH, PH_REMOTE><<<grid, block, smem, st>>>(p); break;
+    case PH_REMOTE_SUM: mh_wide_kernel<LIK, D, NCH, PH_REMOTE_SUM><<<grid, block, smem, st>>>(p); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -53,10 +54,11 @@ cudaError_t launch_wide(int lik, int d, int phase, const WideParams &p, cudaStre
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd,
-                             const unsigned long long *arrivals, unsigned long long wait_target, int *xflag, cudaStream_t st)
+cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd, double *pnb,
+                             const unsigned long long *arrivals, unsigned long long wait_target, int *xflag,
+                             unsigned long long *xstat, cudaStream_t st)
 {
-  pool_prep_kernel<<<(D * mpad + 127) / 128, 128, 0, st>>>(pool, M, mpad, D, pmh, psd, arrivals, wait_target, xflag);
+  pool_prep_kernel<<<(D * mpad + 127) / 128, 128, 0, st>>>(pool, M, mpad, D, pmh, psd, pnb, arrivals, wait_target, xflag, xstat);
   return cudaGetLastError();
 }
 

@@ -67,7 +67,9 @@ __device__ __forceinline__ void normal_pair_t(uint32_t wa, uint32_t wb, double &
 #ifdef MCGPU_EXACT_TU
   normal_pair(wa, wb, z0, z1);
 #else
-  const double r = sqrt(fmax(-2.0 * mc_log(u32_pos(wa), T), 0.0));
+  // v = (w+1) 2^-32 in (0, 1] is normal and positive, so the unchecked log applies and ln v <= 0 (exactly 0 at
+  // v = 1: table entry 0 is (1, 0)): L = -2 ln v >= 0 needs no clamp
+  const double r = mc_sqrt_pos(-2.0 * mc_log_pos(u32_pos(wa), T));
   double s, c;
   mc_sincos2pi(u32_half(wb), s, c, T);
   z0 = r * s; z1 = r * c;
@@ -120,11 +122,14 @@ template <> struct Lik<MCGPU_DUALGAUSSIAN, 2> {
     // t1 = log w - a1, t2 = -a2, M = max(t1, t2)  (lp[1] = log w, set on the host).  A term whose
     // exponential the two-exp form flushes to zero (a > 708) is dropped here too, and
     // with both dropped the result is log(0) = -inf, as in the reference.
-    const double t1 = arg1 > 708.0 ? -INFINITY : p.lp[1] - arg1;
-    const double t2 = arg2 > 708.0 ? -INFINITY : -arg2;
-    const double M = fmax(t1, t2);
-    const double r = M + MC_LOG(1.0 + MC_EXP(-fabs(t1 - t2)));    // NaN when both terms are dropped
-    return M > -INFINITY ? r : -INFINITY;
+    // The comparisons run on the integer pipe (high words): arg >= 0, so arg >= 708 <=> hi(arg) >= hi(708);
+    // the sign of t1 - t2 picks the maximum (-inf - -inf = NaN picks either: both are -inf).
+    const double t1 = __double2hiint(arg1) >= 0x40862000 ? -INFINITY : p.lp[1] - arg1;
+    const double t2 = __double2hiint(arg2) >= 0x40862000 ? -INFINITY : -arg2;
+    const double dt = t1 - t2;
+    const double M = __double2hiint(dt) < 0 ? t2 : t1;
+    const double r = M + mc_log_pos(1.0 + MC_EXP(-fabs(dt)), T);   // argument in [1, 2]; NaN when both terms are dropped
+    return __double2hiint(M) != (int)0xfff00000 ? r : -INFINITY;
 #endif
   }
 };
@@ -171,7 +176,9 @@ __device__ __forceinline__ Words philox_d(uint32_t c0, uint32_t c1, uint32_t c2,
 template <int D>
 __device__ __forceinline__ double factor_at(const double *sT, int idx)
 {
+#ifdef MCGPU_FACTOR_HOIST
   if (D <= 4) return sT[idx];
+#endif
   return *reinterpret_cast<const volatile double *>(sT + idx);
 }
 
@@ -184,6 +191,12 @@ __device__ __forceinline__ float ex2_approx(float x)
   return y;
 }
 
+// the exact evaluation behind every bounded accept test: rare (~1e-4 of the steps), so one out-of-line copy
+__device__ __noinline__ bool accept_exact(double u, double delta, double cfac, const MathTables T)
+{
+  return u < MC_EXP(delta) * cfac;
+}
+
 // The accept test  u < exp(delta) * cfac  (mcpar.cc:67-69 / :167-169).  Only the
 // decision is needed, so it is settled by rigorous fp32 bounds on exp(delta) and
 // computed exactly (fp64 exp) only when u falls between the bounds (~1e-4 of cases).
@@ -192,14 +205,33 @@ __device__ __forceinline__ bool accept_test(double u, double delta, double cfac,
 #ifdef MCGPU_EXACT_TU
   return u < exp(delta) * cfac;
 #else
-  if (exact_tests) return u < mc_exp(delta, T) * cfac;   // audit mode (MCGPU_EXACT_TESTS): no fp32 short cut
+  if (exact_tests) return accept_exact(u, delta, cfac, T);   // audit mode (MCGPU_EXACT_TESTS): no fp32 short cut
   const float dc = fminf(fmaxf((float)delta, -80.0f), 80.0f);
   const double e = (double)ex2_approx(dc * 1.4426950408889634f);
   const double lo = (delta >= -80.0) ? e * cfac * (1.0 - 1.0e-4) : 0.0;   // valid lower bound (clamped above 80)
   const double hi = (delta <= 80.0) ? e * cfac * (1.0 + 1.0e-4) : INFINITY;
   if (u < lo) return true;
   if (u >= hi) return false;
-  return u < mc_exp(delta, T) * cfac;                 // also the NaN path: comparisons above are false
+  return accept_exact(u, delta, cfac, T);             // also the NaN path: comparisons above are false
+#endif
+}
+
+// The same for steps without a Hastings factor (local proposals, burn-in): u < exp(delta).  exp(80) > 1 > u and
+// exp(-80) < 2^-33 <= u settle |delta| >= 80 outright; in between the comparison runs in fp32 -- u rounded to
+// fp32 (relative 2^-24) against exp2.approx with the same 1e-4 margin -- so the FP64 pipe sees no compare at all.
+__device__ __forceinline__ bool accept_test_local(double u, double delta, const MathTables &T, int exact_tests)
+{
+#ifdef MCGPU_EXACT_TU
+  return u < exp(delta);
+#else
+  const float df = (float)delta;
+  if (exact_tests || df != df) return accept_exact(u, delta, 1.0, T);   // audit mode; NaN (-inf - -inf): the comparison is false
+  if (df >= 80.0f) return true;
+  if (df <= -80.0f) return false;
+  const float e = ex2_approx(df * 1.4426950408889634f), uf = (float)u;
+  if (uf < e * (1.0f - 1.0e-4f)) return true;
+  if (uf >= e * (1.0f + 1.0e-4f)) return false;
+  return accept_exact(u, delta, 1.0, T);
 #endif
 }
 
@@ -330,8 +362,15 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
     // Exponents are taken relative to the picked component's own a_c = log2 v (>= -32 per normal pair), which
     // the Box-Muller step already has: 2^(a_s - a_c) <= 2^64 cannot overflow, so the sum needs no running
     // maximum and no rescaling -- the accumulator simply starts at -a_c.
+    // Early reject: Q_s <= 1, so max_s Q_s / sum_s Q_s <= 1 / (Q_c S) with S any partial sum of 2^(a_s - a_c):
+    // the candidate is rejected as soon as u S (1 - eps) >= 2^(-a_c), without the rest of the pool (at the
+    // plateau max/sum ~ 1/M, so most candidates leave after the first chunks; the FPEPS offsets of
+    // mcpar.cc:357-358 only lower the ratio further).
+    const bool fastok = theta < 2.0e-3f && !p.exact_tests;
+    const float uf_lo = (float)u * (1.0f - epsf) * (1.0f - 2.0e-7f), ebound = ex2_approx(-ref) * (1.0f + 1.0e-6f);
     float mr = -INFINITY, S = 0.0f;                    // max_s and sum_s of 2^(a_s - a_c)
     for (int s0 = 0; s0 < Mpad; s0 += CH) {
+      if (fastok && uf_lo * S >= ebound) return false;
 #pragma unroll
       for (int q = 0; q < CH; ++q) {
         float acc = -ref;
@@ -347,7 +386,7 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
         S += ex2_approx(acc);
       }
     }
-    if (mr + ref > -14.0f && theta < 2.0e-3f && !p.exact_tests) {   // max a > -9.7: then FPEPS/qmax < 2e-10 (mcpar.cc:357-358 offsets)
+    if (mr + ref > -14.0f && fastok) {                 // max a > -9.7: then FPEPS/qmax < 2e-10 (mcpar.cc:357-358 offsets)
       const float uf = (float)u, E = ex2_approx(mr);                // R = S / E
       if (uf * fmaf(S, 1.0f + epsf, 3.0e-10f * E) < E) return true;  // u < r_lo
       if (uf * (S * (1.0f - epsf)) >= E) return false;               // u >= r_hi
@@ -400,19 +439,134 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
 // job) the host knows each step's kind in advance -- the coin is a counter-based draw -- and
 // launches lean PH_LOCAL kernels (no remote code, few registers, full occupancy) and dedicated
 // PH_REMOTE kernels instead of the mixed one.
-enum { PH_BURN = 0, PH_MIXED = 1, PH_LOCAL = 2, PH_REMOTE = 3 };
+//   PH_MIXED_SUM / PH_REMOTE_SUM  the same two with remote mode 1: the sum-mixture proposal below
+enum { PH_BURN = 0, PH_MIXED = 1, PH_LOCAL = 2, PH_REMOTE = 3, PH_MIXED_SUM = 4, PH_REMOTE_SUM = 5 };
+
+// ---- remote mode 1: sum-mixture independence proposal ----------------------------------------------
+// (Murray's mixture proposal in place of the reference's rejection loop,
+// mcpar.cc:333-443.)  x' is drawn from the uniform mixture of the pool's diagonal Gaussians -- one pick,
+// one set of normals, no loop -- and the Metropolis ratio carries the exact Hastings factor
+//     cfac = q(x) / q(x'),   q(y) = sum_s N(y; mu_s, diag sig2_s)    (NORMALISED components),
+// so the chain leaves the target invariant whatever the widths in the pool (the reference's
+// max_i Q_i / max_i Q_i correction with unnormalised Q_i does not: DESIGN.md section 4).  Cost: two
+// passes over the pool, O(M d), instead of ~M candidates x O(M d).
+//
+// Only the accept decision is needed, so cfac is first BOUNDED in fp32: with A_s(y) = nb_s - sum_i
+// (g_si mu_si - g_si y_i)^2 the log2 of component s at y (nb_s = -1/2 sum_i log2 sig2_si, g as in
+// stage_pool) and ref = A_c(x') of the picked component, So = sum_s 2^(A_s(x) - ref) and Sn = sum_s
+// 2^(A_s(x') - ref) give cfac = So / Sn; Sn >= 1 (its term c) and neither sum needs a running maximum.
+// Error bound of one sum at point y.  y_i - mu_si is off by at most (roundings of g mu, g, y and the
+// fma) 2.55 u24 (|mu|max + |y|max) / sigma =: theta' sigma-units, so A_s moves by at most
+//     dA = 2 theta' sqrt(D E) + (4 + D) u24 E + 4 u24 |nb|max + D theta'^2,    E = nb_s - A_s(y).
+// Terms within 2^-30 of the largest carry the sum (the others add < M 2^-30 whatever their error); for
+// those E <= |nb|max - (ref + log2(S / M)) + 30 =: Erel, everything on the right known after the loop.
+// ex2.approx (2^-22), the 8 partial sums + tree ((M/8 + 3) u24) and the margin make
+//     eps = 0.75 dA(Erel) + 1e-5 + 1e-8 M.
+// Sums that overflowed, theta' >= 1e-3 (pools with sigma ~ 1e-7: the first windows) or eps >= 0.02 send
+// the step to the exact fp64 evaluation (summix_lse_exact), as does a uniform that falls between the
+// bounds (~3e-4 of the steps).  Terms flushed to zero (ftz) are covered by the absolute term M 2e-38 of
+// the upper bound.  tests/test_bounds_model.py replays this arithmetic in numpy with every approximation
+// pushed to the edge of its bound; MCGPU_EXACT_TESTS=1 forces the fp64 route (tests/test_gpu_audit.py).
+template <int D> struct PointD { double v[D]; };
+
+template <int D>
+__device__ __noinline__ double summix_lse_exact(const PointD<D> x, const double2 *sPmh, const double *sPn, int M, const MathTables &T)
+{
+  double m = -INFINITY, s = 0.0;
+  for (int k = 0; k < M; ++k) {
+    double a = sPn[k];
+#pragma unroll
+    for (int i = 0; i < D; ++i) { const double2 mh = sPmh[k * D + i]; const double xm = mh.x - x.v[i]; a += xm * xm * mh.y; }
+    if (a > m) { s = s * mc_exp(m - a, T) + 1.0; m = a; }
+    else if (a > -INFINITY) s += mc_exp(a - m, T);
+  }
+  return m + mc_log(s, T);                             // no finite term: -inf + log 0 = -inf
+}
+
+template <int D>
+__device__ __forceinline__ bool summix_bounds(const double (&xo)[D], const double (&xn)[D], int c, int M,
+                                              const float2 *sPf, const float *sNb, const float *s_scal,
+                                              float &cf_lo, float &cf_hi)
+{
+  constexpr int CH = 8;
+  const int Mpad = (M + CH - 1) & ~(CH - 1);
+  float xof[D], xnf[D], xabs_o = 0.0f, xabs_n = 0.0f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    xof[i] = (float)xo[i]; xnf[i] = (float)xn[i];
+    xabs_o = fmaxf(xabs_o, fabsf(xof[i])); xabs_n = fmaxf(xabs_n, fabsf(xnf[i]));
+  }
+  float ref = sNb[c];                                  // A_c(x'): the level both sums are taken relative to
+#pragma unroll
+  for (int i = 0; i < D; ++i) { const float2 f = sPf[c * D + i]; const float y = fmaf(-f.y, xnf[i], f.x); ref = fmaf(-y, y, ref); }
+  float Sn[4] = {0.0f, 0.0f, 0.0f, 0.0f}, So[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int s0 = 0; s0 < Mpad; s0 += CH) {
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      const float base = sNb[s0 + q] - ref;
+      float an = base, ao = base;
+      if constexpr (D == 2) {                          // one 16-byte shared-memory load per slot
+        const float4 f = reinterpret_cast<const float4 *>(sPf)[s0 + q];
+        const float yn0 = fmaf(-f.y, xnf[0], f.x), yn1 = fmaf(-f.w, xnf[1], f.z);
+        const float yo0 = fmaf(-f.y, xof[0], f.x), yo1 = fmaf(-f.w, xof[1], f.z);
+        an = fmaf(-yn0, yn0, an); an = fmaf(-yn1, yn1, an);
+        ao = fmaf(-yo0, yo0, ao); ao = fmaf(-yo1, yo1, ao);
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const float2 f = sPf[(s0 + q) * D + i];
+          const float yn = fmaf(-f.y, xnf[i], f.x), yo = fmaf(-f.y, xof[i], f.x);
+          an = fmaf(-yn, yn, an); ao = fmaf(-yo, yo, ao);
+        }
+      }
+      Sn[q & 3] += ex2_approx(an); So[q & 3] += ex2_approx(ao);
+    }
+  }
+  const float sn = (Sn[0] + Sn[1]) + (Sn[2] + Sn[3]), so = (So[0] + So[1]) + (So[2] + So[3]);
+  if (!(sn < 1.0e30f) || !(so < 1.0e30f) || !(sn > 0.5f)) return false;      // overflow / NaN: exact path
+  const float mumax = s_scal[0], isig = s_scal[1], nbmax = s_scal[2];
+  const float th_n = 1.6e-7f * (mumax + xabs_n) * isig, th_o = 1.6e-7f * (mumax + xabs_o) * isig;
+  const float lvl = nbmax - ref + lg2_approx((float)M) + 30.0f;
+  const float En = fmaxf(lvl - lg2_approx(sn), 30.0f), Eo = fmaxf(lvl - lg2_approx(fmaxf(so, 1.0e-37f)), 30.0f);
+  const float cD = (float)D, cu = (4.0f + cD) * 6.0e-8f, cn = 2.4e-7f * nbmax + 1.0e-5f + 1.0e-8f * (float)M;
+  const float eps_n = 0.75f * (2.0f * th_n * sqrtf(cD * En) + cu * En + cD * th_n * th_n) + cn;
+  const float eps_o = 0.75f * (2.0f * th_o * sqrtf(cD * Eo) + cu * Eo + cD * th_o * th_o) + cn;
+  if (!(th_n < 1.0e-3f && th_o < 1.0e-3f && eps_n < 0.02f && eps_o < 0.02f)) return false;
+  cf_lo = __fdividef(so * (1.0f - eps_o), sn * (1.0f + eps_n)) * (1.0f - 1.0e-6f);
+  cf_hi = __fdividef(fmaf(so, 1.0f + eps_o, 2.0e-38f * (float)M), sn * (1.0f - eps_n)) * (1.0f + 1.0e-6f);
+  return true;
+}
+
+// u < exp(delta) cfac with cfac in [cf_lo, cf_hi]:  1 accept, 0 reject, -1 the bounds straddle u.
+// Relative error of the fp32 exponential: (float)delta and the product with log2(e) 1.2e-5 at |delta| <= 80,
+// ex2.approx 2.4e-7.
+__device__ __forceinline__ int accept_test_bounded(double u, double delta, float cf_lo, float cf_hi)
+{
+  const float dc = fminf(fmaxf((float)delta, -80.0f), 80.0f);
+  const double e = (double)ex2_approx(dc * 1.4426950408889634f);
+  const double lo = (delta >= -80.0) ? e * (double)cf_lo * (1.0 - 2.0e-5) : 0.0;
+  const double hi = (delta <= 80.0) ? e * (double)cf_hi * (1.0 + 2.0e-5) : INFINITY;
+  if (u < lo) return 1;
+  if (u >= hi) return 0;
+  return -1;                                           // also the NaN path: both comparisons are false
+}
 
 // Stage the exchange pool [M][D][2] (mu, sigma^2) into shared memory as (mu, -1/(2 sigma^2)) pairs + sigma.
 // With a peer-to-peer exchange the CTA first waits until the pool has arrived from every GPU.  Out of
 // line: it runs once per launch from inside the step loop, whose register allocation it must not disturb.
+// Returns false when a peer-to-peer wait has timed out (now or in an earlier launch): the caller stops stepping
+// instead of sampling from an incomplete pool; the host reports MCGPU_EPEER at the next synchronize.
 template <int D>
-__device__ __noinline__ void stage_pool(const double *pool_cur, int pool_m, const unsigned long long *arrivals,
-                                        unsigned long long wait_target, int *xflag, double2 *sPmh, double *sPs,
-                                        float2 *sPf, float2 *sSf, float *s_scal, int Mpad)
+__device__ __noinline__ bool stage_pool(const double *pool_cur, int pool_m, const unsigned long long *arrivals,
+                                        unsigned long long wait_target, int *xflag, unsigned long long *xstat,
+                                        double2 *sPmh, double *sPs, float2 *sPf, float2 *sSf, double *sPn, float *sNb,
+                                        float *s_scal, int Mpad, const MathTables T)
 {
-  if (wait_target) wait_arrivals(arrivals, wait_target, xflag);
-  if (threadIdx.x < 2) s_scal[threadIdx.x] = 0.0f;
+  if (wait_target) wait_arrivals(arrivals, wait_target, xflag, xstat);
+  if (threadIdx.x < 3) s_scal[threadIdx.x] = 0.0f;
+  if (threadIdx.x == 0) s_scal[3] = (wait_target && *reinterpret_cast<volatile int *>(xflag)) ? 1.0f : 0.0f;
   __syncthreads();
+  if (s_scal[3] != 0.0f) return false;
   float mumax = 0.0f, isig = 0.0f;
   for (int i = threadIdx.x; i < Mpad * D; i += blockDim.x) {
     if (i < pool_m * D) {
@@ -426,11 +580,24 @@ __device__ __noinline__ void stage_pool(const double *pool_cur, int pool_m, cons
       sPmh[i] = make_double2(1.0e300, -1.0); sPf[i] = make_float2(1.0e18f, 0.0f); sSf[i] = make_float2(0.0f, 0.0f);
     }
   }
+  // normalisation of the components (remote mode 1): n_s = -1/2 sum_i log sig2_si, and nb_s = n_s log2(e) in fp32
+  float nbabs = 0.0f;
+  for (int k = threadIdx.x; k < Mpad; k += blockDim.x) {
+    double n = 0.0;
+    if (k < pool_m) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) n -= 0.5 * MC_LOG(pool_cur[(k * D + i) * 2 + 1]);
+    }
+    sPn[k] = n; sNb[k] = (float)(n * 1.4426950408889634);
+    nbabs = fmaxf(nbabs, __double2float_ru(fabs(n * 1.4426950408889634)));
+  }
   // max over the CTA (non-negative floats order like their bit patterns; NaN/inf sort above every
   // number, which makes theta fail its test and sends every candidate to the exact path)
   atomicMax(reinterpret_cast<int *>(&s_scal[0]), __float_as_int(mumax));
   atomicMax(reinterpret_cast<int *>(&s_scal[1]), __float_as_int(isig));
+  atomicMax(reinterpret_cast<int *>(&s_scal[2]), __float_as_int(nbabs));
   __syncthreads();
+  return true;
 }
 
 template <int LIK, int D, int RNGK, int PHASE>
@@ -438,7 +605,10 @@ __global__ void __launch_bounds__(128, (D <= 2 ? ((PHASE == PH_BURN || PHASE == 
 mh_steps_kernel(const StepParams p)
 {
   constexpr bool MAIN = PHASE != PH_BURN;
-  constexpr bool CAN_REMOTE = RNGK == RNG_PHILOX && (PHASE == PH_MIXED || PHASE == PH_REMOTE);
+  constexpr bool SUMMIX = PHASE == PH_MIXED_SUM || PHASE == PH_REMOTE_SUM;       // remote mode 1
+  constexpr bool MIXED = PHASE == PH_MIXED || PHASE == PH_MIXED_SUM;
+  constexpr bool ALLREMOTE = PHASE == PH_REMOTE || PHASE == PH_REMOTE_SUM;
+  constexpr bool CAN_REMOTE = RNGK == RNG_PHILOX && (MIXED || ALLREMOTE);
   extern __shared__ __align__(16) double smem[];
   __shared__ unsigned char s_rank[4][32];               // per warp: lanes of the chains still in the remote loop
   __shared__ unsigned int s_stat[2];                    // remote chain-steps of this CTA and the candidates they tried
@@ -451,7 +621,9 @@ mh_steps_kernel(const StepParams p)
   double *sPs = reinterpret_cast<double*>(sPmh + Mpad * D);
   float2 *sPf = reinterpret_cast<float2*>(sPs + Mpad * D);                    // fp32 copy: (g mu, g), g = sqrt(log2(e)/(2 sig^2))
   float2 *sSf = sPf + Mpad * D;                                               //            (sigma, mu)
-  __shared__ float s_scal[2];                           // pool-wide max |mu| and max 1/sigma (error bound of pool_test)
+  double *sPn = reinterpret_cast<double*>(sSf + Mpad * D);                    // n_s = -1/2 sum_i log sig2_si (remote mode 1)
+  float *sNb = reinterpret_cast<float*>(sPn + Mpad);                          // n_s log2(e)
+  __shared__ float s_scal[4];                           // pool-wide max |mu|, max 1/sigma, max |nb| (error bounds of the fp32 pool tests)
   MathTables T;
 #ifndef MCGPU_EXACT_TU
   T.exp_tab = smem; T.log_tab = smem + MCGPU_EXP_TAB; T.trig_tab = T.log_tab + 2 * MCGPU_LOG_TAB;
@@ -482,23 +654,23 @@ mh_steps_kernel(const StepParams p)
 #pragma unroll
     for (int i = 0; i < D; ++i) { mu[i] = p.mu[i * p.ld + jc]; ps[i] = p.ps[i * p.ld + jc]; }
   }
-  unsigned int nacc = 0;
-  int tmod = MAIN ? p.t0 % p.thin : 0;                // t % thin and t / thin without per-step divisions
-  long long tkeep = MAIN ? (long long)(p.t0 / p.thin) - p.hist_step0 : 0;
+  unsigned int nacc = 0, nrem = 0;
+  int tmod = MAIN ? p.t0 % p.thin : 0;                // t % thin without per-step divisions
+  int tring = p.hist_ring0;                           // ring row of the next kept step
 
   // Stage the exchange pool into shared memory before the first step (with a peer-to-peer exchange this is
   // where the CTA waits for the peers' publications).  Measured alternatives that defer the staging to the
   // window's first remote step -- a barrier inside the step loop, or the loop split in two segments -- cost
   // 3-9 % of the kernel's throughput on every GPU and bought 3 % at 8 GPUs: profiles/r01_history.md.
   if constexpr (CAN_REMOTE) {
-    if (p.t0 + p.nsteps > p.sync)
-      stage_pool<D>(p.pool_cur, p.pool_m, p.arrivals, p.wait_target, p.xflag, sPmh, sPs, sPf, sSf, s_scal, Mpad);
+    if (p.t0 + p.nsteps > p.first_remote_t)
+      if (!stage_pool<D>(p.pool_cur, p.pool_m, p.arrivals, p.wait_target, p.xflag, p.xstat, sPmh, sPs, sPf, sSf, sPn, sNb, s_scal, Mpad, T)) return;
   }
   for (int k = 0; k < p.nsteps; ++k) {
     const uint32_t step = p.step0 + (uint32_t)k;
     const int t = p.t0 + k;
     double u_acc;
-    bool remote = PHASE == PH_REMOTE;
+    bool remote = ALLREMOTE;
     long long zoff = 0;
     constexpr int NP = (D + 1) / 2;                   // normal pairs per proposal
     constexpr int ABLK = (2 * NP) / 4, AW = (2 * NP) % 4;   // accept uniform: word 2*NP of the local stream
@@ -506,9 +678,9 @@ mh_steps_kernel(const StepParams p)
     if (RNGK == RNG_PHILOX) {
       wacc = philox_d<D, true>(glo, ghi, step, (uint32_t)ABLK, p);
       u_acc = u32_mid(word_of(wacc, AW));
-      if (PHASE == PH_MIXED) {
+      if (MIXED) {
         if (p.plan_valid) remote = (p.plan_mask >> k) & 1u;   // job-wide coin, drawn by the host (launch-uniform)
-        else if (t >= p.sync) {                        // one coin per group: the leader's word 2*NP+1
+        else if (t >= p.first_remote_t) {              // one coin per group: the leader's word 2*NP+1
           const uint32_t cw = __shfl_sync(0xffffffffu, word_of(wacc, AW + 1), leader);
           remote = !(u32_half(cw) <= p.pl);            // mcpar.cc:152
         }
@@ -541,9 +713,9 @@ mh_steps_kernel(const StepParams p)
       // keeps the INDEX of its first accepted candidate in iteration order -- the sequential
       // loop's outcome, without lock-step divergence.  Only decisions are needed here, so the
       // candidates are evaluated in fp32 under rigorous bounds (remote_candidate).
-      unsigned rm = CAN_REMOTE ? __ballot_sync(0xffffffffu, remote && live) : 0u;
+      unsigned rm = (CAN_REMOTE && !SUMMIX) ? __ballot_sync(0xffffffffu, remote && live) : 0u;
       const unsigned rm0 = rm;                          // the chains of this warp that take a remote step
-      if constexpr (CAN_REMOTE) {
+      if constexpr (CAN_REMOTE && !SUMMIX) {
         bool pending = remote && live;
         uint32_t it_next = 0;
         if (rm) s_itacc[threadIdx.x] = 0u;
@@ -585,8 +757,8 @@ mh_steps_kernel(const StepParams p)
         const bool rem = CAN_REMOTE && remote;
         uint32_t slot = 0;
         Words blk;
-        if (rem) {
-          slot = MCGPU_SLOT_REMOTE | (s_itacc[threadIdx.x] << 6);
+        if (rem) {                                      // remote mode 1 draws candidate 0 of the remote stream, once
+          slot = SUMMIX ? MCGPU_SLOT_REMOTE : (MCGPU_SLOT_REMOTE | (s_itacc[threadIdx.x] << 6));
           blk = philox_d<D, true>(glo, ghi, step, slot, p);
           cpick = (int)__umulhi(blk.w0, (uint32_t)p.pool_m);
         } else if (ABLK == 0) blk = wacc;               // d = 2: the accept block also carries pair 0
@@ -618,7 +790,7 @@ mh_steps_kernel(const StepParams p)
 #pragma unroll
         for (int i = 0; i < D; ++i) xt[i] = xz[i];
       }
-      if constexpr (CAN_REMOTE) {
+      if constexpr (CAN_REMOTE && !SUMMIX) {
         if (rm0) {                // statistics: remote chain-steps and the iterations the reference's
           unsigned wi = (rm0 >> lane) & 1u ? s_itacc[threadIdx.x] + 1u : 0u;   // loop (mcpar.cc:331-409) would have run for them
 #pragma unroll
@@ -658,7 +830,32 @@ mh_steps_kernel(const StepParams p)
     }
 
     const double lyt = Lik<LIK, D>::eval(xt, p, T);
-    const bool a = accept_test(u_acc, lyt - ly, MAIN ? cfac : 1.0, T, p.exact_tests);   // mcpar.cc:67-69 / :167-169
+    bool a;
+    if constexpr (SUMMIX) {
+      if (remote) {
+        // remote mode 1:  u < exp(lyt - ly + log q(x) - log q(x')), decided from fp32 bounds on q(x)/q(x')
+        // whenever they settle it
+        float cf_lo = 0.0f, cf_hi = 0.0f;
+        int dec = -1;
+        if (!p.exact_tests && summix_bounds<D>(x, xt, cpick, p.pool_m, sPf, sNb, s_scal, cf_lo, cf_hi))
+          dec = accept_test_bounded(u_acc, lyt - ly, cf_lo, cf_hi);
+        if (dec < 0) {
+          PointD<D> po, pn;
+#pragma unroll
+          for (int i = 0; i < D; ++i) { po.v[i] = x[i]; pn.v[i] = xt[i]; }
+          const double lcf = summix_lse_exact<D>(po, sPmh, sPn, p.pool_m, T) - summix_lse_exact<D>(pn, sPmh, sPn, p.pool_m, T);
+          dec = accept_exact(u_acc, (lyt - ly) + lcf, 1.0, T) ? 1 : 0;
+        }
+        a = dec != 0;
+        nrem += live ? 1u : 0u;
+      } else
+        a = accept_test_local(u_acc, lyt - ly, T, p.exact_tests);             // mcpar.cc:167-169 with cfac = 1
+    } else if constexpr (!CAN_REMOTE) {
+      a = accept_test_local(u_acc, lyt - ly, T, p.exact_tests);               // mcpar.cc:67-69 / :167-169 with cfac = 1
+    } else {
+      a = remote ? accept_test(u_acc, lyt - ly, cfac, T, p.exact_tests)       // mcpar.cc:167-169
+                 : accept_test_local(u_acc, lyt - ly, T, p.exact_tests);
+    }
     if (a) {
       ly = lyt;
 #pragma unroll
@@ -667,13 +864,13 @@ mh_steps_kernel(const StepParams p)
     nacc += a ? 1u : 0u;
 
     if (MAIN) {
-      if (p.hist && live && tmod == 0) {               // MCout::add, mcout.cc:129-145
-        double *row = p.hist + (tkeep * p.C + j) * (D + 1);
+      if (p.hist && live && tmod == 0) {               // MCout::add, mcout.cc:129-145 (a ring of hist_cap kept steps)
+        double *row = p.hist + ((long long)tring * p.C + j) * (D + 1);
 #pragma unroll
         for (int i = 0; i < D; ++i) row[i] = x[i];
         row[D] = ly;
       }
-      if (++tmod == p.thin) { tmod = 0; ++tkeep; }
+      if (++tmod == p.thin) { tmod = 0; if (++tring == p.hist_cap) tring = 0; }
       const double pwgt = (double)(t + 1), winv = sW[k];
       const bool adopt = CAN_REMOTE && remote && a;    // mcpar.cc:190-197
 #pragma unroll
@@ -705,7 +902,7 @@ mh_steps_kernel(const StepParams p)
         if (p.npeers > 0) {                            // sharded: store into every GPU's next pool over NVLink
           // A GPU may not publish P+1 before all of P has reached it: its peers' last CTAs of the
           // previous window may still read pool P-1, which P+2 will overwrite (three buffers).
-          wait_arrivals_thread(p.arrivals, p.wait_target, p.xflag);
+          wait_arrivals_thread(p.arrivals, p.pub_wait_target, p.xflag);
           for (int r = 0; r < p.npeers; ++r) {
             double *dst = reinterpret_cast<double *>(p.peers[r] + p.next_off);
 #pragma unroll
@@ -732,6 +929,12 @@ mh_steps_kernel(const StepParams p)
   if (lane == 0) {
     atomicAdd(p.counts, (unsigned long long)wacc);
     atomicAdd(p.counts + 1, (unsigned long long)nlive * (unsigned long long)p.nsteps);
+  }
+  if constexpr (SUMMIX) {                              // one candidate per remote chain-step
+    unsigned int wr = nrem;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wr += __shfl_xor_sync(0xffffffffu, wr, o);
+    if (lane == 0 && wr) { atomicAdd(&s_stat[0], wr); atomicAdd(&s_stat[1], wr); }
   }
   if constexpr (CAN_REMOTE) {                          // main-phase statistics: counts[2] remote chain-steps, [3] candidates
     __syncthreads();

@@ -2,15 +2,16 @@
 #pragma once
 #include "mcgpu_device.cuh"
 namespace mcgpu {
-enum { PH_BURN = 0, PH_MIXED = 1, PH_LOCAL = 2, PH_REMOTE = 3 };   // kernel phases, see mh_kernels.cuh
+enum { PH_BURN = 0, PH_MIXED = 1, PH_LOCAL = 2, PH_REMOTE = 3, PH_MIXED_SUM = 4, PH_REMOTE_SUM = 5 };   // kernel phases, see mh_kernels.cuh
 namespace fast {
 bool wide_supported(int lik, int d);
 cudaError_t launch_wide(int lik, int d, int phase, const WideParams &p, cudaStream_t st);
-cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd,
-                             const unsigned long long *arrivals, unsigned long long wait_target, int *xflag, cudaStream_t st);
+cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd, double *pnb,
+                             const unsigned long long *arrivals, unsigned long long wait_target, int *xflag,
+                             unsigned long long *xstat, cudaStream_t st);
 cudaError_t launch_factor_prep(const double *rm, double *cm, int D, int *diag, cudaStream_t st);
 bool steps_supported(int lik, int d);
-size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem);
+size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool with_pool);
 cudaError_t launch_steps(int lik, int d, int rngk, int phase, const StepParams &p, cudaStream_t st);
 cudaError_t launch_init_loglik(int lik, int d, const StepParams &p, cudaStream_t st);
 cudaError_t launch_tune(unsigned long long *counts, unsigned long long *cum, double *factor, int dd,
@@ -18,7 +19,7 @@ cudaError_t launch_tune(unsigned long long *counts, unsigned long long *cum, dou
 }
 namespace exact {
 bool steps_supported(int lik, int d);
-size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool pool_in_smem);
+size_t steps_smem_bytes(int d, int nsteps, int pool_m, bool with_pool);
 cudaError_t launch_steps(int lik, int d, int rngk, int phase, const StepParams &p, cudaStream_t st);
 cudaError_t launch_init_loglik(int lik, int d, const StepParams &p, cudaStream_t st);
 cudaError_t launch_tune(unsigned long long *counts, unsigned long long *cum, double *factor, int dd,

@@ -119,7 +119,8 @@ __device__ __forceinline__ void wide_loglik(const double (&x0)[NCH], const doubl
 
 // For the NCH points staged in sx: amax[c] = max_s log Q_s (exact fp64) and S[c] = fp32 bound
 // material sum_s exp(log Q_s - amax[c]).  Lane r evaluates pool slots r, r+L, ...
-template <int D, int NCH>
+// NORM: the components are normalised, log Q_s = n_s - 1/2 sum_i (mu - x)^2 / sig2 (remote mode 1).
+template <int D, int NCH, bool NORM>
 __device__ __forceinline__ void wide_pool_eval(const double *sx, int r, const WideParams &p, double (&amax)[NCH], float (&S)[NCH])
 {
   constexpr int L = D / 2;
@@ -129,8 +130,9 @@ __device__ __forceinline__ void wide_pool_eval(const double *sx, int r, const Wi
   for (int c = 0; c < NCH; ++c) { m[c] = -INFINITY; sl[c] = 0.0f; }
   for (int s = r; s < p.mpad; s += L) {
     double a[NCH];
+    const double n0 = NORM ? __ldg(p.pnb + s) : 0.0;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) a[c] = 0.0;
+    for (int c = 0; c < NCH; ++c) a[c] = n0;
     const double2 *g = p.pmh + s;
 #pragma unroll 4
     for (int i = 0; i < D; ++i) {
@@ -144,7 +146,9 @@ __device__ __forceinline__ void wide_pool_eval(const double *sx, int r, const Wi
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const bool gt = a[c] > m[c];
-      const float e = ex2_approx(-fabsf((float)(a[c] - m[c])) * L2E);
+      // a = -inf (a padding slot, or a point hopelessly far away) contributes 0; without the guard the first
+      // such slot of a lane (m still -inf) would make a - m NaN and poison the group's sum
+      const float e = a[c] == -INFINITY ? 0.0f : ex2_approx(-fabsf((float)(a[c] - m[c])) * L2E);
       sl[c] = gt ? fmaf(sl[c], e, 1.0f) : sl[c] + e;
       m[c] = gt ? a[c] : m[c];
     }
@@ -152,8 +156,31 @@ __device__ __forceinline__ void wide_pool_eval(const double *sx, int r, const Wi
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     amax[c] = group_max<L>(m[c]);
-    S[c] = group_sumf<L>(sl[c] * ex2_approx((float)(m[c] - amax[c]) * L2E));      // m = -inf (no slot): 0
+    S[c] = group_sumf<L>(m[c] == -INFINITY ? 0.0f : sl[c] * ex2_approx((float)(m[c] - amax[c]) * L2E));   // a lane that saw no live slot adds 0
   }
+}
+
+// exact log of the normalised sum-mixture at chain c's staged point (remote mode 1, rare path)
+template <int D, int NCH>
+__device__ __noinline__ double wide_pool_lse_exact(const double *sx, int c, int r, const WideParams &p, const MathTables &T)
+{
+  constexpr int L = D / 2;
+  double m = -INFINITY, sm = 0.0;
+  for (int s = r; s < p.pool_m; s += L) {
+    double a = __ldg(p.pnb + s);
+    const double2 *g = p.pmh + s;
+    for (int i = 0; i < D; ++i) {
+      const double2 mh = __ldg(g);
+      g += p.mpad;
+      const double xm = mh.x - sx[i * NCH + c];
+      a += xm * xm * mh.y;
+    }
+    if (a > m) { sm = sm * mc_exp(m - a, T) + 1.0; m = a; }
+    else if (a > -INFINITY) sm += mc_exp(a - m, T);
+  }
+  const double gm = group_max<L>(m);
+  const double tot = group_sum<L>(m == -INFINITY ? 0.0 : sm * mc_exp(m - gm, T));
+  return gm + mc_log(tot, T);
 }
 
 // exact pacpt material for chain c of the staged points (rare path)
@@ -187,6 +214,8 @@ mh_wide_kernel(const WideParams p)
 {
   constexpr int L = D / 2;                      // lanes per group
   constexpr bool MAIN = PHASE != PH_BURN;
+  constexpr bool SUMMIX = PHASE == PH_REMOTE_SUM;                         // remote mode 1 (mh_kernels.cuh)
+  constexpr bool REMOTE = PHASE == PH_REMOTE || PHASE == PH_REMOTE_SUM;
   constexpr int ABLK = (2 * L) / 4, AW = (2 * L) % 4;     // accept uniform: word 2*NP (NP = L pairs) of the local stream
   extern __shared__ __align__(16) double smem[];
   // smem: math tables | per group of the CTA: staged points sx[D][NCH] and staged normals sz[D][NCH]
@@ -219,13 +248,14 @@ mh_wide_kernel(const WideParams p)
   const double tdiag0 = p.factor_rm[i0 * D + i0], tdiag1 = p.factor_rm[(i0 + 1) * D + i0 + 1];
   const bool diag = *p.diagonal != 0;
   int tmod = MAIN ? p.t0 % p.thin : 0;
-  long long tkeep = MAIN ? (long long)(p.t0 / p.thin) - p.hist_step0 : 0;
+  int tring = p.hist_ring0;                     // ring row of the next kept step
 
   for (int k = 0; k < p.nsteps; ++k) {
     const uint32_t step = p.step0 + (uint32_t)k;
     const int t = p.t0 + k;
     double u_acc[NCH], xt0[NCH], xt1[NCH], cfac[NCH];
     int cpick[NCH];
+    double lcf_m[NCH]; float so_[NCH], sn_[NCH];    // remote mode 1: log q(x) - log q(x') = lcf_m + log(so / sn)
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const Words wacc = philox4x32_10_rk(glo[c], ghi[c], step, (uint32_t)ABLK, p.rk);
@@ -233,7 +263,7 @@ mh_wide_kernel(const WideParams p)
       cfac[c] = 1.0; cpick[c] = 0; xt0[c] = x0[c]; xt1[c] = x1[c];
     }
 
-    if (PHASE != PH_REMOTE) {
+    if (!REMOTE) {
       // genLocal: lane r's Box-Muller pair = words (2r, 2r+1) of the chain's local stream
       double za[NCH], zb[NCH];
 #pragma unroll
@@ -261,6 +291,33 @@ mh_wide_kernel(const WideParams p)
         for (int c = 0; c < NCH; ++c) { xt0[c] = a0[c]; xt1[c] = a1[c] + tl * zb[c]; }
         __syncwarp();
       }
+    } else if (SUMMIX) {
+      // remote mode 1 (sum-mixture proposal, no rejection loop): candidate 0 of the remote stream is THE
+      // proposal; lane r tests pool slots r, r+L, ... against x' and against x for all NCH chains
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const Words w0 = philox4x32_10_rk(glo[c], ghi[c], step, MCGPU_SLOT_REMOTE, p.rk);
+        cpick[c] = (int)__umulhi(w0.w0, (uint32_t)p.pool_m);
+        const int qq = r + 1;                       // lane r's pair = words (2+2r, 3+2r)
+        Words b = w0;
+        if ((qq >> 1) != 0) b = philox4x32_10_rk(glo[c], ghi[c], step, MCGPU_SLOT_REMOTE + (uint32_t)(qq >> 1), p.rk);
+        double za, zb;
+        normal_pair_t((qq & 1) ? b.w2 : b.w0, (qq & 1) ? b.w3 : b.w1, za, zb, T);
+        xt0[c] = __ldg(p.pmh + (size_t)i0 * p.mpad + cpick[c]).x + __ldg(p.psd + (size_t)i0 * p.mpad + cpick[c]) * za;
+        xt1[c] = __ldg(p.pmh + (size_t)(i0 + 1) * p.mpad + cpick[c]).x + __ldg(p.psd + (size_t)(i0 + 1) * p.mpad + cpick[c]) * zb;
+        sx[i0 * NCH + c] = xt0[c]; sx[(i0 + 1) * NCH + c] = xt1[c];
+      }
+      __syncwarp();
+      double am_n[NCH], am_o[NCH];
+      wide_pool_eval<D, NCH, true>(sx, r, p, am_n, sn_);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) { sx[i0 * NCH + c] = x0[c]; sx[(i0 + 1) * NCH + c] = x1[c]; }
+      __syncwarp();
+      wide_pool_eval<D, NCH, true>(sx, r, p, am_o, so_);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) { lcf_m[c] = am_o[c] - am_n[c]; nit += live[c] ? 1u : 0u; }
     } else {
       // genRemote: the group's chains run the reference's rejection loop in step: candidate
       // iteration `it` of every chain is evaluated together (lane r tests pool slots r, r+L, ...
@@ -290,7 +347,7 @@ mh_wide_kernel(const WideParams p)
         }
         __syncwarp();
         double am[NCH]; float S[NCH];
-        wide_pool_eval<D, NCH>(sx, r, p, am, S);
+        wide_pool_eval<D, NCH, false>(sx, r, p, am, S);
         bool acc[NCH], decided[NCH], alldec = true;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -325,7 +382,7 @@ mh_wide_kernel(const WideParams p)
       for (int c = 0; c < NCH; ++c) { sx[i0 * NCH + c] = x0[c]; sx[(i0 + 1) * NCH + c] = x1[c]; }
       __syncwarp();
       double aold[NCH]; float dummy[NCH];
-      wide_pool_eval<D, NCH>(sx, r, p, aold, dummy);
+      wide_pool_eval<D, NCH, false>(sx, r, p, aold, dummy);
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -345,18 +402,51 @@ mh_wide_kernel(const WideParams p)
     if (LIK != MCGPU_ROSENBROCK1) __syncwarp();
 
     const double pwgt = (double)(t + 1), winv = 1.0 / pwgt;
+    int dec[NCH];
+    if (SUMMIX) {
+      // u < exp(lyt - ly + log q(x) - log q(x')): the fp64 maxima go into the exponent, the fp32 sums (each
+      // right to eps: float conversion of the exponents, ex2.approx, <= M/L rescales) bound the rest
+      const float eps = 1.0e-4f + 1.0e-6f * (float)p.pool_m;
+      bool alldec = true;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        dec[c] = -1;
+        if (sn_[c] > 0.5f && sn_[c] < 1.0e30f && so_[c] > 0.5f && so_[c] < 1.0e30f)      // each sum holds its maximum's term: >= 1
+          dec[c] = accept_test_bounded(u_acc[c], (lyt[c] - ly[c]) + lcf_m[c], __fdividef(so_[c] * (1.0f - eps), sn_[c] * (1.0f + eps)) * (1.0f - 1.0e-6f),
+                                       __fdividef(so_[c] * (1.0f + eps), sn_[c] * (1.0f - eps)) * (1.0f + 1.0e-6f));
+        alldec = alldec && dec[c] >= 0;
+      }
+      if (!__all_sync(0xffffffffu, alldec)) {          // rare: exact log q(x) - log q(x'), warp-wide
+        double lo_[NCH], ln_[NCH];
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) { sx[i0 * NCH + c] = xt0[c]; sx[(i0 + 1) * NCH + c] = xt1[c]; }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) ln_[c] = wide_pool_lse_exact<D, NCH>(sx, c, r, p, T);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) { sx[i0 * NCH + c] = x0[c]; sx[(i0 + 1) * NCH + c] = x1[c]; }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) lo_[c] = wide_pool_lse_exact<D, NCH>(sx, c, r, p, T);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) if (dec[c] < 0) dec[c] = u_acc[c] < mc_exp((lyt[c] - ly[c]) + (lo_[c] - ln_[c]), T) ? 1 : 0;
+      }
+    }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const bool a = accept_test(u_acc[c], lyt[c] - ly[c], MAIN ? cfac[c] : 1.0, T, 0);   // same inputs in every lane of the group
+      const bool a = SUMMIX ? dec[c] != 0 : accept_test(u_acc[c], lyt[c] - ly[c], MAIN ? cfac[c] : 1.0, T, 0);   // same inputs in every lane of the group
       if (a) { ly[c] = lyt[c]; x0[c] = xt0[c]; x1[c] = xt1[c]; }
       nacc[c] += a ? 1u : 0u;
       if (MAIN) {
         if (p.hist && live[c] && tmod == 0) {          // MCout::add: one row per chain, coalesced over the lanes
-          double *row = p.hist + (tkeep * p.C + jb + c) * (D + 1);
+          double *row = p.hist + ((long long)tring * p.C + jb + c) * (D + 1);
           row[i0] = x0[c]; row[i0 + 1] = x1[c];
           if (r == 0) row[D] = ly[c];
         }
-        if (PHASE == PH_REMOTE && a) {                 // adopt the component's moments, mcpar.cc:190-197
+        if (REMOTE && a) {                             // adopt the component's moments, mcpar.cc:190-197
           const double sd0 = __ldg(p.psd + (size_t)i0 * p.mpad + cpick[c]), sd1 = __ldg(p.psd + (size_t)(i0 + 1) * p.mpad + cpick[c]);
           mu0[c] = __ldg(p.pmh + (size_t)i0 * p.mpad + cpick[c]).x; mu1[c] = __ldg(p.pmh + (size_t)(i0 + 1) * p.mpad + cpick[c]).x;
           ps0[c] = (sd0 * sd0) * (pwgt - 1.0); ps1[c] = (sd1 * sd1) * (pwgt - 1.0);
@@ -365,7 +455,7 @@ mh_wide_kernel(const WideParams p)
         dl = x1[c] - mu1[c]; mu1[c] += dl * winv; ps1[c] += dl * (x1[c] - mu1[c]);
       }
     }
-    if (MAIN) { if (++tmod == p.thin) { tmod = 0; ++tkeep; } }
+    if (MAIN) { if (++tmod == p.thin) { tmod = 0; if (++tring == p.hist_cap) tring = 0; } }
   }
 
   unsigned int wacc = 0, nlive = 0;
@@ -382,7 +472,7 @@ mh_wide_kernel(const WideParams p)
           const long long s = gg / p.pool_stride;
           const double wi = 1.0 / (double)(p.t0 + p.nsteps);
           if (p.npeers > 0) {                          // sharded: store into every GPU's next pool over NVLink
-            wait_arrivals_thread(p.arrivals, p.wait_target, p.xflag);   // never more than one publication ahead (mh_kernels.cuh)
+            wait_arrivals_thread(p.arrivals, p.pub_wait_target, p.xflag);   // never more than one publication ahead (mh_kernels.cuh)
             for (int q = 0; q < p.npeers; ++q) {
               double *dst = reinterpret_cast<double *>(p.peers[q] + p.next_off);
               dst[(s * D + i0) * 2] = mu0[c];     dst[(s * D + i0) * 2 + 1] = ps0[c] * wi;
@@ -407,7 +497,7 @@ mh_wide_kernel(const WideParams p)
     atomicAdd(p.counts, (unsigned long long)wacc);
     atomicAdd(p.counts + 1, (unsigned long long)nlive * (unsigned long long)p.nsteps);
   }
-  if (PHASE == PH_REMOTE) {                     // main-phase statistics: counts[2] remote chain-steps, [3] candidates
+  if (REMOTE) {                                 // main-phase statistics: counts[2] remote chain-steps, [3] candidates
     unsigned int wi = r == 0 ? nit : 0u;        // every lane of a group counted the same
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wi += __shfl_xor_sync(0xffffffffu, wi, o);
@@ -419,11 +509,17 @@ mh_wide_kernel(const WideParams p)
 }
 
 // pool [M][D][2] (mu, sigma^2) -> pmh [D][Mpad] (mu, -1/(2 sigma^2)), psd [D][Mpad] sigma; padding slots get Q = 0
-static __global__ void pool_prep_kernel(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd,
-                                        const unsigned long long *arrivals, unsigned long long wait_target, int *xflag)
+static __global__ void pool_prep_kernel(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd, double *pnb,
+                                        const unsigned long long *arrivals, unsigned long long wait_target, int *xflag,
+                                        unsigned long long *xstat)
 {
-  if (wait_target) { wait_arrivals(arrivals, wait_target, xflag); __syncthreads(); }   // peer-to-peer exchange: all slots in?
+  if (wait_target) { wait_arrivals(arrivals, wait_target, xflag, xstat); __syncthreads(); }   // peer-to-peer exchange: all slots in?
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < mpad) {                                   // n_s = -1/2 sum_i log sig2_si (remote mode 1); padding 0
+    double n = 0.0;
+    if (idx < M) for (int i = 0; i < D; ++i) n -= 0.5 * log(pool[((size_t)idx * D + i) * 2 + 1]);
+    pnb[idx] = n;
+  }
   if (idx >= D * mpad) return;
   const int i = idx / mpad, s = idx % mpad;
   if (s < M) {

@@ -21,7 +21,8 @@ P2P_HANDLE_BYTES = 64
 EXPORTS = [
     "mcgpu_version", "mcgpu_device_count", "mcgpu_last_error", "mcgpu_create", "mcgpu_destroy",
     "mcgpu_set_stream", "mcgpu_set_likelihood", "mcgpu_set_covariance", "mcgpu_set_state",
-    "mcgpu_set_streams", "mcgpu_burnin", "mcgpu_sample_begin", "mcgpu_sample",
+    "mcgpu_set_streams", "mcgpu_burnin", "mcgpu_sample_begin", "mcgpu_sample", "mcgpu_sample_group",
+    "mcgpu_set_state_sobol",
     "mcgpu_exchange_begin", "mcgpu_exchange_end", "mcgpu_p2p_export", "mcgpu_p2p_attach",
     "mcgpu_p2p_attach_local", "mcgpu_burnin_group", "mcgpu_tuning_counters", "mcgpu_burnin_some",
     "mcgpu_tune", "mcgpu_synchronize", "mcgpu_get_state", "mcgpu_get_factor", "mcgpu_get_musig",
@@ -44,14 +45,17 @@ class Config(C.Structure):
                 ("pl", C.c_double), ("armin", C.c_double), ("armax", C.c_double),
                 ("dfac", C.c_double), ("ifac", C.c_double), ("seed", C.c_uint64),
                 ("coin_group", C.c_int32), ("pool_m", C.c_int32), ("thin", C.c_int32),
-                ("trace", C.c_int32), ("history_steps", C.c_int64)]
+                ("trace", C.c_int32), ("history_steps", C.c_int64),
+                ("remote_mode", C.c_int32), ("pool_lag", C.c_int32)]
+
+REMOTE_MODE = {"reference": 0, "maxmix": 0, "summix": 1, "murray": 1, 0: 0, 1: 1}
 
 
 class Stats(C.Structure):
     _fields_ = [("burn_steps", C.c_int64), ("main_steps", C.c_int64), ("accepted", C.c_int64),
                 ("tried", C.c_int64), ("kernel_launches", C.c_int64), ("remote_steps", C.c_int64),
                 ("remote_iterations", C.c_int64), ("history_rows", C.c_int64),
-                ("device_ms", C.c_double)]
+                ("device_ms", C.c_double), ("exchange_wait_ns", C.c_int64), ("exchange_waits", C.c_int64)]
 
 
 _lib = None
@@ -129,6 +133,12 @@ def p2p_attach_local(engines):
         e.p2p = True
 
 
+def sample_group(engines, nsteps):
+    """mcgpu_sample on several peer-to-peer engines of ONE process, one exchange window at a time, in turn."""
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    _check(load().mcgpu_sample_group(arr, len(engines), nsteps), engines[0].h)
+
+
 def burnin_group(engines, nburn):
     """Burn-in of several sharded engines of ONE process with job-wide tuning counters."""
     arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
@@ -145,10 +155,10 @@ class Engine:
     def __init__(self, nparam, nchain, *, mode="normal", nchain_total=None, chain0=0,
                  chains_per_rank=0, pl=0.9, armin=0.2, armax=0.5, dfac=0.2, ifac=1.5, sync=10,
                  seed=8675309, coin_group=32, pool_m=0, thin=1, trace=0, history_steps=0,
-                 device=0):
+                 device=0, remote_mode=0, pool_lag=0):
         self.lib = load()
         cfg = Config()
-        cfg.abi_version = 1
+        cfg.abi_version = 2
         cfg.device, cfg.mode, cfg.nparam = device, MODE[mode], nparam
         cfg.nchain, cfg.chain0 = nchain, chain0
         cfg.nchain_total = nchain if nchain_total is None else nchain_total
@@ -156,6 +166,7 @@ class Engine:
         cfg.pl, cfg.armin, cfg.armax, cfg.dfac, cfg.ifac = pl, armin, armax, dfac, ifac
         cfg.seed, cfg.coin_group, cfg.pool_m, cfg.thin = seed, coin_group, pool_m, thin
         cfg.trace, cfg.history_steps = int(trace), history_steps
+        cfg.remote_mode, cfg.pool_lag = REMOTE_MODE[remote_mode], int(pool_lag)
         self.cfg = cfg
         self.d, self.C, self.mode = nparam, nchain, mode
         self.p2p = False
@@ -201,6 +212,12 @@ class Engine:
         pinit = np.ascontiguousarray(pinit, dtype=np.float64)
         assert pinit.size == self.C * self.d, "pinit must hold nchain*nparam values"
         self._ck(self.lib.mcgpu_set_state(self.h, _p(pinit)))
+
+    def set_state_sobol(self, plo, phi, first_point=0):
+        """mcutil::qriguess straight into the engine: chain g starts at Sobol point first_point + g in [plo, phi]."""
+        plo = np.ascontiguousarray(plo, dtype=np.float64); phi = np.ascontiguousarray(phi, dtype=np.float64)
+        assert plo.size == self.d and phi.size == self.d
+        self._ck(self.lib.mcgpu_set_state_sobol(self.h, _p(plo), _p(phi), C.c_uint64(first_point)))
 
     def set_streams(self, local_rank, Z, U, I=None):
         Z = np.ascontiguousarray(Z, dtype=np.float64).ravel()
@@ -303,6 +320,8 @@ class Engine:
         st = self.stats()
         kept = st["history_rows"] // self.C
         if count is None:
+            if first == 0 and self.cfg.history_steps and kept > self.cfg.history_steps:
+                first = kept - self.cfg.history_steps          # the ring holds the last history_steps kept steps
             count = kept - first
         rows = out if out is not None else np.empty((count, self.C, self.d + 1))
         self._ck(self.lib.mcgpu_history_read(self.h, C.c_int64(first), C.c_int64(count), _p(rows)))

@@ -10,22 +10,20 @@
 #include "mcpar.hh"
 #include "rosenbrock.hh"
 #include "mcout.hh"
+#include "driver_opts.hh"
 
 int main(int argc, char *argv[])
 {
   const int nparam = 2;
-  int ngpu = 1;
-  int ranks = 1, nsamp = 8;
-  for (int i = 1; i < argc; ++i) {
-    if (!strncmp(argv[i], "--ranks=", 8)) ranks = atoi(argv[i] + 8);
-    else if (!strncmp(argv[i], "--ngpu=", 7)) ngpu = atoi(argv[i] + 7);
-    else if (!strncmp(argv[i], "--nsamp=", 8)) nsamp = atoi(argv[i] + 8);
-  }
+  DriverOpts o(8);
+  o.parse(argc, argv);
+  for (int i = 1; i < argc; ++i) if (!strncmp(argv[i], "--nsamp=", 8)) o.nsamp = atoi(argv[i] + 8);
+  const int nsamp = o.nsamp, ranks = o.ranks;
   try {
     DualGaussian L(5.0);
     MCout rslts(nparam, &std::cout, 0);
     MCPar mcpar(nparam, 4, ranks, 0);
-    mcpar.ngpu = ngpu;
+    o.apply(mcpar);
     Real pinit[8] = {0.0, 0.0, 2.0, 2.0, 0.0, 1.5, 0.0, -2.0};
     if (mcpar.run(nsamp, 500, pinit, L, rslts) != MCPar::OK) return 2;
 

@@ -11,21 +11,15 @@
 #include "mcpar.hh"
 #include "rosenbrock.hh"
 #include "mcout.hh"
+#include "driver_opts.hh"
 
 int main(int argc, char *argv[])
 {
   const int nparam = 2;
-  int nsamp = 100000, ranks = 1, npos = 0, ngpu = 1;
-  int pool = 0, thin = 1;
-  const char *binfile = 0;
-  for (int i = 1; i < argc; ++i) {
-    if (!strncmp(argv[i], "--ranks=", 8)) ranks = atoi(argv[i] + 8);
-    else if (!strncmp(argv[i], "--ngpu=", 7)) ngpu = atoi(argv[i] + 7);
-    else if (!strncmp(argv[i], "--pool=", 7)) pool = atoi(argv[i] + 7);
-    else if (!strncmp(argv[i], "--thin=", 7)) thin = atoi(argv[i] + 7);
-    else if (!strncmp(argv[i], "--binary=", 9)) binfile = argv[i] + 9;
-    else if (npos++ == 0) nsamp = atoi(argv[i]);
-  }
+  DriverOpts o(100000);
+  o.parse(argc, argv);
+  const int nsamp = o.nsamp, ranks = o.ranks;
+  const char *binfile = o.binfile;
   try {
     Rosenbrock1 L(2);
     std::ofstream bin;
@@ -37,7 +31,7 @@ int main(int argc, char *argv[])
     if (binfile) rslts.set_format(MCout::BINARY);
     std::cout << "nsamp = " << nsamp << "\n";
     MCPar mcpar(nparam, 4, ranks, 0);
-    mcpar.pool_m = pool; mcpar.thin = thin; mcpar.ngpu = ngpu;
+    o.apply(mcpar);
     Real pinit[8] = {0.0, 0.0, 2.0, 2.0, 0.0, 1.5, 0.0, -2.0};
     if (mcpar.run(nsamp, 500, pinit, L, rslts) != MCPar::OK) return 2;
     rslts.output();

@@ -10,20 +10,15 @@
 #include "mcpar.hh"
 #include "rosenbrock.hh"
 #include "mcout.hh"
+#include "driver_opts.hh"
 
 int main(int argc, char *argv[])
 {
   const int nparam = 16;
-  int nsamp = 10000, ranks = 1, npos = 0, pool = 0, thin = 1, ngpu = 1;
-  const char *binfile = 0;                       // --binary=FILE: rows to FILE in MCout's binary format
-  for (int i = 1; i < argc; ++i) {
-    if (!strncmp(argv[i], "--ranks=", 8)) ranks = atoi(argv[i] + 8);
-    else if (!strncmp(argv[i], "--ngpu=", 7)) ngpu = atoi(argv[i] + 7);
-    else if (!strncmp(argv[i], "--pool=", 7)) pool = atoi(argv[i] + 7);
-    else if (!strncmp(argv[i], "--thin=", 7)) thin = atoi(argv[i] + 7);
-    else if (!strncmp(argv[i], "--binary=", 9)) binfile = argv[i] + 9;
-    else if (npos++ == 0) nsamp = atoi(argv[i]);
-  }
+  DriverOpts o(10000);
+  o.parse(argc, argv);
+  const int nsamp = o.nsamp, ranks = o.ranks;
+  const char *binfile = o.binfile;
   try {
     Rosenbrock1 L(nparam);
     std::ofstream bin;
@@ -35,7 +30,7 @@ int main(int argc, char *argv[])
     if (binfile) rslts.set_format(MCout::BINARY);
     std::cout << "nsamp = " << nsamp << "\n";
     MCPar mcpar(nparam, 4, ranks, 0);
-    mcpar.pool_m = pool; mcpar.thin = thin; mcpar.ngpu = ngpu;
+    o.apply(mcpar);
     // the 2-D demo's four starting points, repeated over the 8 coordinate pairs
     const Real p4[8] = {0.0, 0.0, 2.0, 2.0, 0.0, 1.5, 0.0, -2.0};
     std::vector<Real> pinit(4 * nparam);

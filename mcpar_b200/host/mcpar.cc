@@ -27,8 +27,9 @@ void die(mcgpu_engine *e, const char *what, int rc)
 
 MCPar::MCPar(int np, int nc, int mpisiz, int mpirank, Real pl, Real armin, Real armax, Real dfac, Real ifac, int sync)
   : TGT_ARATE_MIN(armin), TGT_ARATE_MAX(armax), SCALE_DEC(dfac), SCALE_INC(ifac), PLOCAL(pl), SYNCSTEP(sync),
-    logging(false), logstep(1000), device(0), ngpu(1), pool_m(0), thin(1), seed(8675309ull),
-    nparam(np), nchain(nc), size(mpisiz < 1 ? 1 : mpisiz), rank(mpirank), mdevice_ms(0), maccept(0)
+    logging(false), logstep(1000), device(0), ngpu(1), pool_m(0), thin(1), coin_group(-1), remote_mode(0), pool_lag(0),
+    history_bytes(1ll << 30), seed(8675309ull),
+    nparam(np), nchain(nc), size(mpisiz < 1 ? 1 : mpisiz), rank(mpirank), mdevice_ms(0), maccept(0), mxwait_ms(0)
 {
   tchains = size * nchain;
   if (rank != 0) {
@@ -76,7 +77,16 @@ int MCPar::run(int nsamp, int nburn, const Real *pinit, VLFunc &L, MCout &outsam
   const int rpg = size / G;                                           // ranks per engine
   // one local/remote coin per rank-sized group of chains (mcpar.cc:106-109,142-159)
   int cg = 1; while (cg * 2 <= nchain && cg < 32) cg *= 2;
+  if (coin_group == 0) cg = 0;                                        // one coin per step for the whole job
   mcgpu_engine *eng = 0;                                              // the engine CHECK reports on
+  // The device history is a ring of `ring` kept steps, read back into MCout piece by piece: at least one
+  // exchange window's worth, at most the whole run, otherwise what fits the byte budget.
+  const int outstep = nsamp > 50 ? nsamp / 10 : 5;       // mcpar.cc:110
+  const long long kept_total = (nsamp + thin - 1) / thin;
+  const long long row_bytes = (long long)cg_chains * (nparam + 1) * (long long)sizeof(Real);
+  long long ring = std::max<long long>(history_bytes / std::max<long long>(row_bytes, 1), (SYNCSTEP + thin - 1) / thin + 1);
+  ring = std::max<long long>(1, std::min(ring, kept_total));
+  const int piece = (int)std::max<long long>(SYNCSTEP, (ring * thin) / SYNCSTEP * SYNCSTEP);   // steps sampled between two reads
   for (int g = 0; g < G; ++g) {
     mcgpu_config cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -85,8 +95,8 @@ int MCPar::run(int nsamp, int nburn, const Real *pinit, VLFunc &L, MCout &outsam
     cfg.sync = SYNCSTEP; cfg.pl = PLOCAL; cfg.armin = TGT_ARATE_MIN; cfg.armax = TGT_ARATE_MAX;
     cfg.dfac = SCALE_DEC; cfg.ifac = SCALE_INC; cfg.seed = seed;
     cfg.coin_group = cg;
-    cfg.pool_m = pool_m; cfg.thin = thin;
-    cfg.history_steps = (nsamp + thin - 1) / thin;
+    cfg.pool_m = pool_m; cfg.thin = thin; cfg.remote_mode = remote_mode; cfg.pool_lag = pool_lag;
+    cfg.history_steps = ring;
     mcgpu_engine *e = 0;
     const int rc = mcgpu_create(&cfg, &e);
     if (rc != MCGPU_OK) die(0, "mcgpu_create", rc);
@@ -112,7 +122,6 @@ int MCPar::run(int nsamp, int nburn, const Real *pinit, VLFunc &L, MCout &outsam
   if (G > 1) CHECK(mcgpu_burnin_group(&engs[0], G, nburn));            // tuning counters summed over the engines
   else CHECK(mcgpu_burnin(eng, nburn));
 
-  const int outstep = nsamp > 50 ? nsamp / 10 : 5;       // mcpar.cc:110
   logfile << "Starting main sample loop:  nsamp = " << nsamp << std::endl;
   logfile << "Output after each " << outstep << " steps." << std::endl;
   for (int g = 0; g < G; ++g) { eng = engs[g]; CHECK(mcgpu_sample_begin(eng, nsamp)); }
@@ -121,44 +130,43 @@ int MCPar::run(int nsamp, int nburn, const Real *pinit, VLFunc &L, MCout &outsam
   // rank-major blocks; inside a rank block step-major, then chain (mcout.cc:52-94 gathers
   // rank blocks; src/anly/mcpar-analysis.R:80-120 relies on it).
   const int ncol = nparam + 1;
-  std::vector<std::vector<Real> > block(G);
+  std::vector<std::vector<Real> > block(G);                // the rows of the current output batch, per engine, kept-step major
+  long long batch_kept = 0;                                // kept steps gathered in `block` so far
   int done = 0;
+  int next_out = outstep;                                  // outsamples.output() before step outstep, 2 outstep, ... (mcpar.cc:115-119)
   while (done < nsamp) {
-    const int n = (nsamp - done < outstep) ? nsamp - done : outstep;
-    if (done > 0) {
+    if (done > 0 && done == next_out) {
       logfile << "Beginning output at step " << done << std::endl;
       outsamples.output();
       logfile << "Output finished\n" << std::endl;
+      next_out += outstep;
     }
+    const int n = std::min(std::min(nsamp - done, next_out - done), piece);   // up to the next output, at most one ring
     if (logging && done % logstep == 0)
       logfile << "sample step " << done << ":\toutsamples size= " << outsamples.size() << "  maxsize = "
               << outsamples.maxsize() << "  ncol= " << outsamples.ncol() << std::endl;
     if (G == 1) CHECK(mcgpu_sample(eng, n));
-    else {
-      // engines are fed one exchange window at a time, in turn: a window kernel that waits for its peers'
-      // publications is then never queued in front of the kernels that make them (engines may share a device)
-      for (int k = 0; k < n;) {
-        const int m = std::min(n - k, SYNCSTEP - (done + k) % SYNCSTEP);
-        for (int g = 0; g < G; ++g) { eng = engs[g]; CHECK(mcgpu_sample(eng, m)); }
-        k += m;
-      }
-    }
-    const long long k0 = (done + thin - 1) / thin, k1 = (done + n + thin - 1) / thin;   // kept steps of this batch
+    else CHECK(mcgpu_sample_group(&engs[0], G, n));      // one exchange window at a time, engine after engine
+    const long long k0 = (done + thin - 1) / thin, k1 = (done + n + thin - 1) / thin;   // kept steps of this piece
     if (k1 > k0) {
       for (int g = 0; g < G; ++g) {
         eng = engs[g];
-        block[g].resize((size_t)(k1 - k0) * cg_chains * ncol);
-        CHECK(mcgpu_history_read(eng, k0, k1 - k0, &block[g][0]));
+        block[g].resize((size_t)(batch_kept + k1 - k0) * cg_chains * ncol);
+        CHECK(mcgpu_history_read(eng, k0, k1 - k0, &block[g][(size_t)batch_kept * cg_chains * ncol]));
       }
-      for (int r = 0; r < size; ++r)
-        for (long long k = 0; k < k1 - k0; ++k)
-          outsamples.addrows(&block[r / rpg][((size_t)k * cg_chains + (size_t)(r % rpg) * nchain) * ncol], (size_t)nchain);
+      batch_kept += k1 - k0;
     }
     done += n;
+    if ((done == next_out || done == nsamp) && batch_kept > 0) {   // the batch is complete: hand it to MCout rank by rank
+      for (int r = 0; r < size; ++r)
+        for (long long k = 0; k < batch_kept; ++k)
+          outsamples.addrows(&block[r / rpg][((size_t)k * cg_chains + (size_t)(r % rpg) * nchain) * ncol], (size_t)nchain);
+      batch_kept = 0;
+    }
   }
   outsamples.output();                                   // remaining samples (mcpar.cc:212)
 
-  long long acc = 0, tried = 0;
+  long long acc = 0, tried = 0, xwait = 0, xwaits = 0;
   mdevice_ms = 0;
   for (int g = 0; g < G; ++g) {
     eng = engs[g];
@@ -167,9 +175,15 @@ int MCPar::run(int nsamp, int nburn, const Real *pinit, VLFunc &L, MCout &outsam
     CHECK(mcgpu_get_stats(eng, &st));
     acc += st.accepted; tried += st.tried;
     if (st.device_ms > mdevice_ms) mdevice_ms = st.device_ms;
+    if (st.exchange_wait_ns > xwait) xwait = st.exchange_wait_ns;
+    xwaits += st.exchange_waits;
   }
   maccept = tried ? (double)acc / (double)tried : 0.0;
+  mxwait_ms = (double)xwait * 1e-6;
   logfile << "Acceptance rate (main loop) = " << maccept << "  device time = " << mdevice_ms << " ms  ("
           << (double)tchains * (nburn + nsamp) / (mdevice_ms * 1e-3) << " chain-steps/s)" << std::endl;
+  if (G > 1)
+    logfile << "Exchange wait (slowest engine) = " << mxwait_ms << " ms in " << xwaits << " launches that waited for a peer's pool slots"
+            << std::endl;
   return OK;
 }

@@ -27,6 +27,12 @@ public:
                                 // MPI_Allgather (src/mcpar.cc:127-140).  More engines than devices share devices.
   int pool_m;                   // remote-mixture pool size; 0 = every chain, as the reference
   int thin;                     // keep every thin-th step
+  int coin_group;               // -1: one local/remote coin per rank (nc chains), as the reference (mcpar.cc:106-109);
+                                // 0: one coin per step for the whole job (needed by the d >= 32 kernels)
+  int remote_mode;              // 0: the reference's genRemote (mcpar.cc:315-451); 1: normalised sum-mixture proposal
+  int pool_lag;                 // 0 / 1: read the pool one exchange later (takes the GPU exchange off the critical path)
+  long long history_bytes;      // device budget for the sample history ring (default 1 GiB per engine): rows are
+                                // read back into MCout in pieces of at most that size
   unsigned long long seed;      // Philox key; reference seed by default (mcpar.cc:271)
 
   MCPar(int np, int nc = 1, int mpisiz = 1, int mpirank = 0, Real pl = 0.9, Real armin = 0.2,
@@ -37,12 +43,13 @@ public:
 
   double last_device_ms() const { return mdevice_ms; }
   double last_accept_rate() const { return maccept; }
+  double last_exchange_wait_ms() const { return mxwait_ms; }
 
 private:
   int nparam, nchain, size, rank, tchains;
   std::vector<mcgpu_engine *> engs;
   void destroy_engines();
-  double mdevice_ms, maccept;
+  double mdevice_ms, maccept, mxwait_ms;
   MCPar(const MCPar &); MCPar &operator=(const MCPar &);
 };
 

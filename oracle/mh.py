@@ -20,7 +20,8 @@ class Cfg(C.Structure):
                 ("pl", C.c_double), ("armin", C.c_double), ("armax", C.c_double),
                 ("dfac", C.c_double), ("ifac", C.c_double), ("sync", C.c_int),
                 ("pinit_per_rank", C.c_int), ("trace_steps", C.c_int), ("trace_musig", C.c_int),
-                ("seed", C.c_uint64), ("coin_group", C.c_int), ("pool_m", C.c_int), ("thin", C.c_int)]
+                ("seed", C.c_uint64), ("coin_group", C.c_int), ("pool_m", C.c_int), ("thin", C.c_int),
+                ("remote_mode", C.c_int), ("pool_lag", C.c_int)]
 
 
 def lib_path():
@@ -143,13 +144,15 @@ def run_replay(lik, nparam, nchain, nranks, nsamp, nburn, pinit, Z, U, I=None, i
 
 def run_counter(lik, nparam, nchain, nsamp, nburn, pinit, incov=None, par=None, seed=8675309,
                 coin_group=32, pool_m=0, thin=1, pl=0.9, armin=0.2, armax=0.5, dfac=0.2, ifac=1.5,
-                sync=10, trace=False, want_rows=True):
-    """Normal-mode semantics (counter-based Philox per global chain) on N=nchain chains."""
+                sync=10, trace=False, want_rows=True, remote_mode=0, pool_lag=0):
+    """Normal-mode semantics (counter-based Philox per global chain) on N=nchain chains.
+    remote_mode 0: the reference's max-mixture rejection loop; 1: normalised sum-mixture proposal."""
     N, d = nchain, nparam
     pinit = np.ascontiguousarray(pinit, dtype=np.float64)
     assert pinit.size == N * d
     cfg = _cfg(lik, d, N, 1, nsamp, nburn, par, pl, armin, armax, dfac, ifac, sync)
     cfg.seed, cfg.coin_group, cfg.pool_m, cfg.thin = seed, coin_group, pool_m, thin
+    cfg.remote_mode, cfg.pool_lag = remote_mode, pool_lag
     M = pool_m if 0 < pool_m < N else N
     nkeep = (nsamp + thin - 1) // thin
     inc = None if incov is None else np.ascontiguousarray(incov, dtype=np.float64).ravel()

@@ -151,22 +151,15 @@ int orc_loglik(int lik, int d, const double *par, int npset, const double *x, do
 
 /* ------------------------------------------------------------------ */
 /* Sobol + qriguess: src/mcutil.cc:3-34.  MKL's direction numbers are   */
-/* unobtainable (unpinned); Joe-Kuo (2008) numbers for dims 1..16,      */
+/* unobtainable (unpinned); Joe-Kuo (2008) numbers for dims 1..64,      */
 /* gray-code order, first point = origin, value = integer * 2^-32.      */
 /* ------------------------------------------------------------------ */
-typedef struct { int s; uint32_t a; uint32_t m[7]; } jk_t;
-static const jk_t JK[16] = {
-  {0,0,{0}},
-  {1,0,{1}}, {2,1,{1,3}}, {3,1,{1,3,1}}, {3,2,{1,1,1}}, {4,1,{1,1,3,3}},
-  {4,4,{1,3,5,13}}, {5,2,{1,1,5,5,17}}, {5,4,{1,1,5,5,5}}, {5,7,{1,1,7,11,19}},
-  {5,11,{1,1,5,1,1}}, {5,13,{1,1,1,3,11}}, {5,14,{1,3,5,5,31}}, {6,1,{1,3,3,9,7,49}},
-  {6,13,{1,1,1,15,21,21}}, {6,16,{1,3,1,13,27,49}},
-};
+#include "sobol_jk64.h"     /* generated by tools/gen_sobol_table.py from the public Joe-Kuo file */
 
 static void sobol_dirs(int dim, uint32_t v[32])
 {
   if (dim == 0) { for (int i = 0; i < 32; ++i) v[i] = 1u << (31 - i); return; }
-  const jk_t *p = &JK[dim]; const int s = p->s;
+  const sobol_jk_t *p = &SOBOL_JK[dim]; const int s = p->s;
   for (int i = 0; i < 32; ++i) {
     if (i < s) v[i] = p->m[i] << (31 - i);
     else {
@@ -180,7 +173,7 @@ static void sobol_dirs(int dim, uint32_t v[32])
  * (what vslSkipAheadStream + vsRngUniform deliver, mcutil.cc:23-25) */
 int orc_sobol_points(int dimen, uint64_t first_scalar, size_t nscalar, double *out)
 {
-  if (dimen < 1 || dimen > 16) return -1;
+  if (dimen < 1 || dimen > SOBOL_JK_NDIM) return -1;
   uint32_t (*v)[32] = (uint32_t (*)[32])malloc(sizeof(uint32_t) * 32 * (size_t)dimen);
   for (int k = 0; k < dimen; ++k) sobol_dirs(k, v[k]);
   for (size_t q = 0; q < nscalar; ++q) {
@@ -197,11 +190,11 @@ int orc_sobol_points(int dimen, uint64_t first_scalar, size_t nscalar, double *o
 
 void orc_qriguess(int rank, int npset, int d, const double *plo, const double *phi, double *pout)
 {
-  const int ntot = npset * d;                                   /* mcutil.cc:19 */
-  double *q = (double*)malloc(sizeof(double) * (size_t)ntot);
-  orc_sobol_points(d, rank > 0 ? (uint64_t)rank * (uint64_t)ntot : 0, (size_t)ntot, q);  /* :22-25 */
-  for (int j = 0; j < npset; ++j)                                /* :28-32 */
-    for (int i = 0; i < d; ++i) { int ix = j*d + i; pout[ix] = plo[i] + q[ix]*(phi[i]-plo[i]); }
+  const size_t ntot = (size_t)npset * (size_t)d;                /* mcutil.cc:19 (int there; size_t: 2^20 x 64 fits, 2^26 x 64 would not) */
+  double *q = (double*)malloc(sizeof(double) * ntot);
+  orc_sobol_points(d, rank > 0 ? (uint64_t)rank * (uint64_t)ntot : 0, ntot, q);  /* :22-25 */
+  for (size_t j = 0; j < (size_t)npset; ++j)                     /* :28-32 */
+    for (int i = 0; i < d; ++i) { size_t ix = j*d + i; pout[ix] = plo[i] + q[ix]*(phi[i]-plo[i]); }
   free(q);
 }
 
@@ -219,6 +212,32 @@ static double q_value(int d, const double *ms, const double *x)
     arg += xm*xm/sig2;
   }
   return exp(-0.5*arg);
+}
+
+/* log of the NORMALISED sum-mixture density of the pool at x (up to the constant
+ * -log M - d/2 log 2 pi that cancels in the Hastings ratio):
+ *   L(x) = log sum_s exp(n_s - 1/2 sum_i (mu_si - x_i)^2 / sig2_si),  n_s = -1/2 sum_i log sig2_si,
+ * by log-sum-exp.  Remote mode 1 only; the reference's Q_i (mcpar.cc:367-390) lacks n_s and is
+ * combined by max, not sum. */
+static double pool_lse(int d, int M, const double *pool, const double *x)
+{
+  double m = -INFINITY;
+  for (int s = 0; s < M; ++s) {
+    const double *ms = pool + (size_t)s*d*2;
+    double arg = 0.0, n = 0.0;
+    for (int i = 0; i < d; ++i) { double xm = ms[2*i] - x[i]; arg += xm*xm/ms[2*i+1]; n += log(ms[2*i+1]); }
+    double a = -0.5*n - 0.5*arg;
+    if (a > m) m = a;
+  }
+  if (!(m > -INFINITY)) return m;              /* every term underflowed to -inf (or NaN input) */
+  double sum = 0.0;
+  for (int s = 0; s < M; ++s) {
+    const double *ms = pool + (size_t)s*d*2;
+    double arg = 0.0, n = 0.0;
+    for (int i = 0; i < d; ++i) { double xm = ms[2*i] - x[i]; arg += xm*xm/ms[2*i+1]; n += log(ms[2*i+1]); }
+    sum += exp(-0.5*n - 0.5*arg - m);
+  }
+  return m + log(sum);
 }
 
 /* Welford update with remote adoption, mcpar.cc:186-209, for one parameter */
@@ -511,7 +530,9 @@ int orc_run_counter(const orc_config *cfg, const double *pinit, const double *in
   const int thin = cfg->thin > 0 ? cfg->thin : 1;
   if (d > 256) return -1;
   double *x = malloc(8*(size_t)N*d), *ly = malloc(8*(size_t)N), *mu = calloc((size_t)N*d, 8), *ps = malloc(8*(size_t)N*d);
-  double *pool = calloc((size_t)M*d*2, 8), *T0 = malloc(8*(size_t)d*d);
+  const int lag = cfg->pool_lag > 0 ? 1 : 0;
+  const int first_remote = cfg->sync * (1 + lag);     /* no pool to read before that */
+  double *pool = calloc((size_t)M*d*2, 8), *pool_new = calloc((size_t)M*d*2, 8), *T0 = malloc(8*(size_t)d*d);
   double xt[256], z[257], mut[256], sigt[256];
   memset(mut, 0, sizeof mut); memset(sigt, 0, sizeof sigt);
   memcpy(x, pinit, 8*(size_t)N*d);
@@ -528,18 +549,34 @@ int orc_run_counter(const orc_config *cfg, const double *pinit, const double *in
     const int t = isamp - cfg->nburn;                 /* main-phase step */
     if (!burn && t == 0) { for (size_t i = 0; i < (size_t)N*d; ++i) { mu[i] = 0.0; ps[i] = FPEPS; } nacc = ntry = 0; }
     const double pwgt = burn ? 0.0 : (double)(t + 1), winv = burn ? 0.0 : 1.0 / pwgt;
-    if (!burn && t % cfg->sync == 0)                  /* exchange: refresh the pool (mcpar.cc:127-140) */
+    if (!burn && t % cfg->sync == 0) {                /* exchange: refresh the pool (mcpar.cc:127-140) */
+      if (lag) memcpy(pool, pool_new, 8*(size_t)M*d*2);   /* pool_lag 1: read what the PREVIOUS exchange delivered */
+      double *dst = lag ? pool_new : pool;
       for (int s = 0; s < M; ++s) { size_t g = (size_t)s*stride;
-        for (int i = 0; i < d; ++i) { pool[((size_t)s*d+i)*2] = mu[g*d+i]; pool[((size_t)s*d+i)*2+1] = ps[g*d+i] * (t ? 1.0/(double)t : 0.0); } }
+        for (int i = 0; i < d; ++i) { dst[((size_t)s*d+i)*2] = mu[g*d+i]; dst[((size_t)s*d+i)*2+1] = ps[g*d+i] * (t ? 1.0/(double)t : 0.0); } }
+    }
     for (int g = 0; g < N; ++g) {
       double *xg = x + (size_t)g*d;
-      int remotep = 0; double cfac = 1.0;
-      if (!burn && t >= cfg->sync) {                   /* mcpar.cc:142-159, one coin per group */
+      int remotep = 0; double cfac = 1.0, lcfac = 0.0;
+      if (!burn && t >= first_remote) {                   /* mcpar.cc:142-159, one coin per group */
         remotep = !((double)draw_word(cfg, (uint64_t)(g / G) * G, step, 0, 2*NP + 1) * W32 <= cfg->pl);
       }
       if (!remotep) {                                  /* genLocal with the scaled factor */
         for (int p = 0; p < NP; ++p) normal_pair(draw_word(cfg, g, step, 0, 2*p), draw_word(cfg, g, step, 0, 2*p + 1), &z[2*p], &z[2*p+1]);
         for (int i = 0; i < d; ++i) { double acc = xg[i]; for (int q = 0; q <= i; ++q) acc += T0[i*d+q] * z[q]; xt[i] = acc; }
+      } else if (cfg->remote_mode == 1) {              /* sum-mixture independence proposal, no rejection loop:
+                                                          x' ~ (1/M) sum_s N(mu_s, diag sig2_s), drawn as candidate 0 of
+                                                          the remote stream (word 0 -> component, word 1 unused);
+                                                          Hastings factor q(x)/q(x') with normalised components */
+        ++riters;
+        const int c = (int)(((uint64_t)draw_word(cfg, g, step, SLOT_REMOTE, 0) * (uint64_t)M) >> 32);
+        for (int p = 0; p < NP; ++p) normal_pair(draw_word(cfg, g, step, SLOT_REMOTE, 2 + 2*p), draw_word(cfg, g, step, SLOT_REMOTE, 3 + 2*p), &z[2*p], &z[2*p+1]);
+        for (int i = 0; i < d; ++i) {
+          mut[i] = pool[((size_t)c*d+i)*2]; sigt[i] = sqrt(pool[((size_t)c*d+i)*2+1]);
+          xt[i] = mut[i] + sigt[i]*z[i];
+        }
+        lcfac = pool_lse(d, M, pool, xg) - pool_lse(d, M, pool, xt);
+        for (int i = 0; i < d; ++i) sigt[i] *= sigt[i];
       } else {                                         /* genRemote, per-chain rejection loop over the pool */
         double qmax = 0, qsum = 0; int c = 0;
         for (uint32_t it = 0;; ++it) {
@@ -566,6 +603,7 @@ int orc_run_counter(const orc_config *cfg, const double *pinit, const double *in
       orc_loglik(cfg->lik, d, par, 1, xt, &lyt);
       double u = ((double)draw_word(cfg, g, step, 0, 2*NP) + 0.5) * W32;
       double pac = exp(lyt - ly[g]); if (!burn) pac *= cfac;
+      if (remotep && cfg->remote_mode == 1) pac = exp((lyt - ly[g]) + lcfac);   /* one exponential of the summed logs */
       int a = u < pac;
       ++ntry; nacc += a;
       if (tr_accept) tr_accept[(size_t)isamp*N + g] = (unsigned char)(a | (remotep << 1));
@@ -586,11 +624,11 @@ int orc_run_counter(const orc_config *cfg, const double *pinit, const double *in
   if (st_ly) memcpy(st_ly, ly, 8*(size_t)N);
   if (st_mu) memcpy(st_mu, mu, 8*(size_t)N*d);
   if (st_psum2) memcpy(st_psum2, ps, 8*(size_t)N*d);
-  if (pool_out) memcpy(pool_out, pool, 8*(size_t)M*d*2);
+  if (pool_out) memcpy(pool_out, lag ? pool_new : pool, 8*(size_t)M*d*2);   /* the latest publication */
   if (acc_counts) { acc_counts[0] = nacc; acc_counts[1] = ntry; }
   if (cov_out) memcpy(cov_out, T0, 8*(size_t)d*d);
   if (remote_iters) *remote_iters = riters;
 done:
-  free(x); free(ly); free(mu); free(ps); free(pool); free(T0);
+  free(x); free(ly); free(mu); free(ps); free(pool); free(pool_new); free(T0);
   return rc;
 }

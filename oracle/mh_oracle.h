@@ -39,6 +39,11 @@ typedef struct orc_config {
   int coin_group;        /* chains sharing one local/remote coin (power of two <= 32); 0 = whole job */
   int pool_m;            /* remote-mixture pool size, 0 => all chains    */
   int thin;              /* keep every thin-th main step in rows         */
+  int remote_mode;       /* 0: the reference's max-mixture rejection loop (mcpar.cc:315-451);
+                            1: sum-mixture independence proposal with NORMALISED components and
+                               no rejection loop (Murray 2010)            */
+  int pool_lag;          /* 0: window w reads the pool published at the end of window w-1;
+                            1: one window older (takes the exchange off the critical path)       */
 } orc_config;
 
 /* ---- primitives ---- */

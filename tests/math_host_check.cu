@@ -45,9 +45,21 @@ int main()
     if (fabsl(sinl(a)) > 0.1L) { double er = ulp_err(s, sinl(a)); if (er > e_sin) e_sin = er; }
     if (fabsl(cosl(a)) > 0.1L) { double er = ulp_err(c, cosl(a)); if (er > e_cos) e_cos = er; }
   }
+  // mc_sqrt_pos with the SFU seed off by +-2^-21 (twice the documented bound), mc_log_pos on its two call sites
+  double e_sqrt = 0, e_logpos = 0;
+  for (int i = 0; i < 2000000; ++i) {
+    const double L = (i & 3) == 0 ? rnd() * 1e-9 : rnd() * 44.5;
+    const double er = ulp_err(mcgpu::mc_sqrt_pos(L, (i & 4) ? 4.76837158203125e-7 : -4.76837158203125e-7), sqrtl((long double)L));
+    if (er > e_sqrt) e_sqrt = er;
+    const double v = (i & 1) ? ((double)(unsigned)(rnd() * 4294967295.0) + 1.0) * (1.0 / 4294967296.0) : 1.0 + rnd();
+    if (fabs(v - 1.0) > 0.02) { const double el = ulp_err(mcgpu::mc_log_pos(v, T), logl((long double)v)); if (el > e_logpos) e_logpos = el; }
+    if (mcgpu::mc_log_pos(v, T) != mcgpu::mc_log(v, T)) e_logpos = 1e9;       // same arithmetic as the checked routine
+  }
+  const double sq0 = mcgpu::mc_sqrt_pos(0.0);
   double sp[4] = {mcgpu::mc_exp(-800.0, T), mcgpu::mc_exp(800.0, T), mcgpu::mc_exp(NAN, T), mcgpu::mc_log(0.0, T)};
   printf("{\"exp_ulp\": %.3f, \"log_ulp\": %.3f, \"log_near1_abs\": %.3e, \"sin_ulp\": %.3f, \"cos_ulp\": %.3f, "
+         "\"sqrt_ulp\": %.3f, \"sqrt0\": %g, \"logpos_ulp\": %.3f, "
          "\"sincos_abs\": %.3e, \"exp_m800\": %g, \"exp_p800_inf\": %d, \"exp_nan\": %d, \"log0_minf\": %d}\n",
-         e_exp, e_log, e_log01, e_sin, e_cos, abs_sc, sp[0], (int)isinf(sp[1]), (int)isnan(sp[2]), (int)(isinf(sp[3]) && sp[3] < 0));
+         e_exp, e_log, e_log01, e_sin, e_cos, e_sqrt, sq0, e_logpos, abs_sc, sp[0], (int)isinf(sp[1]), (int)isnan(sp[2]), (int)(isinf(sp[3]) && sp[3] < 0));
   return 0;
 }

@@ -28,9 +28,11 @@ def test_python_binding_lists_the_same_symbols():
 
 def test_config_struct_layout_matches_header(mcgpu_lib):
     from mcpar_b200 import engine
-    # 4*int32, 3*int64, 2*int32, 5*double, uint64, 4*int32, int64
-    assert C.sizeof(engine.Config) == 16 + 24 + 8 + 40 + 8 + 16 + 8
-    assert C.sizeof(engine.Stats) == 8 * 8 + 8
+    # 4*int32, 3*int64, 2*int32, 5*double, uint64, 4*int32, int64, 2*int32
+    assert C.sizeof(engine.Config) == 16 + 24 + 8 + 40 + 8 + 16 + 8 + 8
+    assert C.sizeof(engine.Stats) == 8 * 8 + 8 + 16
+    hdr = open(os.path.join(ROOT, "include", "mcgpu.h")).read()
+    assert "#define MCGPU_ABI_VERSION 2" in hdr and engine.Config().abi_version == 0
 
 
 def test_no_cpu_fallback_without_gpu(mcgpu_lib):
