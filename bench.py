@@ -1,24 +1,38 @@
 #!/usr/bin/env python
 """bench.py -- MH chain-steps/s of the B200 engine (and of the reference on the host cores).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dgauss|rosen2d|rosen16]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dgauss|rosen2d|rosen16|gmix64]
+                  [--remote-mode reference|summix] [--pool M] [--lag 0|1]
   python bench.py --impl reference ...        # the reference's own CPU loop (oracle/_ref)
 
-A "step" is one exchange window of the hot path: `sync` (=10) Metropolis-Hastings
-steps of every chain (proposal, likelihood, accept, update, running moments), the
-thinned sample-history store and the publication of the exchange pool; under
-torchrun the NCCL all-gather of the pool is part of the step.  Workload at N=1 is
-BASELINE.json configs[1] (mcpar-dgauss: DualGaussian(5), 2^20 chains, one B200);
-SURVEY.md 8(d) C2 fixes the rest (identity incov, PLOCAL 0.9, SYNCSTEP 10, thin 10).
-Weak scaling: 2^20 chains per GPU.
+A "step" is one exchange window of the hot path: `sync` (=10) Metropolis-Hastings steps of every chain
+(proposal, likelihood, accept, update, running moments), the thinned sample-history store, the publication
+of the exchange pool and the exchange itself (in-kernel peer-to-peer stores over NVLink, or an NCCL
+all-gather).  Workload at N=1 is BASELINE.json configs[1] (mcpar-dgauss: DualGaussian(5), 2^20 chains, one
+B200); SURVEY.md 8(d) fixes the rest (identity incov, PLOCAL 0.9, SYNCSTEP 10, thin 10).  Weak scaling:
+2^20 chains per GPU.
+
+What the line holds (contract: the task's bench section):
+  value / ms_per_step   K timed windows, state resident, CUDA events on the launching stream, max over ranks.
+                        Before the timed region the sampler is advanced `--advance` untimed windows so that
+                        the rejection loop of the reference's remote proposal sits at its plateau (its
+                        iteration count rises for ~2000 windows): the value does not depend on K.
+  remote mode           `reference` (default): the reference's max-mixture rejection loop over a pool of M
+                        components; `summix`: the normalised sum-mixture proposal (no rejection loop).  The
+                        headline is the default mode; "modes" holds short measurements of the other
+                        configurations (sum-mixture at M = 16 and at the blueprint's M = 256).
+  e2e                   a whole MCPar::run-shaped job through the C ABI with HOST buffers: host pinit in,
+                        burn-in 500, 1000 steps, rows (thin 10) drained to a pinned host sink of the
+                        reference MCout's element type (float) while the next window computes, final logL out.
+  roofline              FP64 pipe: flops per chain-step counted by ncu (profiles/fp64_work.json) x chain-steps/s
+                        over the DFMA peak measured in this run.
 """
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -29,16 +43,17 @@ METRIC = "mh_chain_steps_per_sec"
 UNIT = "chain-steps/s"
 SEED = 8675309                      # reference seed, src/mcpar.cc:271
 
-# hardware-equivalent fp64 flops per chain-step (calls weighted
-# log~50, sqrt~14, sincos~40, exp~30, div~18) and textbook flops
+# SURVEY.md 8(d) a-priori estimates of the hardware-equivalent fp64 flops per chain-step (used only until
+# profiles/fp64_work.json holds the figure ncu counted for the workload) and textbook flops
 WORKLOADS = {
-    "dgauss":  dict(lik="dualgaussian", par=[5.0], d=2, F_hw=280.0, F_alg=46.0, name="mcpar-dgauss"),
-    "rosen2d": dict(lik="rosenbrock1", par=None, d=2, F_hw=167.0, F_alg=38.0, name="mcpar-rosen1 shape, 2-D Rosenbrock"),
-    "rosen16": dict(lik="rosenbrock1", par=None, d=16, F_hw=1350.0, F_alg=516.0, name="mcpar-rosen2 (d=16)"),
+    "dgauss":  dict(lik="dualgaussian", par=[5.0], d=2, F_hw=280.0, F_alg=46.0, name="mcpar-dgauss", advance=3000),
+    "rosen2d": dict(lik="rosenbrock1", par=None, d=2, F_hw=167.0, F_alg=38.0, name="mcpar-rosen1 shape, 2-D Rosenbrock", advance=3000),
+    "rosen16": dict(lik="rosenbrock1", par=None, d=16, F_hw=1350.0, F_alg=516.0, name="mcpar-rosen2 (d=16)", advance=300),
     # GaussMix d=64, K=64, exchange every sweep (SYNCSTEP 1), diagonal incov
     "gmix64":  dict(lik="gaussmix", par="gmix64", d=64, F_hw=22600.0, F_alg=17500.0, name="sum-of-Gaussians mixture d=64 K=64",
-                    sync=1, thin=100),
+                    sync=1, thin=100, advance=200),
 }
+RMODE = {"reference": 0, "summix": 1}
 
 
 def gmix64_params(seed=SEED):
@@ -62,53 +77,90 @@ def incov_for(wl):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of ONE GPU sampled during the run by an NVML polling thread (every rank
+    runs its own, started before the warm-up, so no rank enters the timed loop late)."""
 
-    def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, index, period=0.01):
+        self.samples, self.reasons, self.stop_flag, self.mx = [], set(), False, None
+        self.t_mark = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "50"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:                                   # the CUDA ordinal need not be the NVML index: go by PCI address
+                import torch
+                pr = torch.cuda.get_device_properties(index)
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            return
+        self.period = period
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = int(get_reasons(self.h))
+                self.samples.append((time.perf_counter(), mhz))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def mark(self):
+        """samples from here on were taken under load (pre-advance + timed region)"""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0}
+        if self.nv is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush(); self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 7:
-                continue
-            try:
-                sm.append(float(c[0])); mx.append(float(c[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, c[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        os.unlink(self.f.name)
+        self.stop_flag = True
+        self.th.join(timeout=2)
+        sm = [m for t, m in self.samples if self.t_mark is None or t >= self.t_mark]
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), reasons=sorted(self.reasons), samples=len(sm),
+                       how="NVML polled every %g ms by every rank from before the warm-up; median over the advance + timed region" % (1e3 * self.period))
         return out
+
+
+def pin_to_gpu_numa(local):
+    """Run this rank's host threads (and first-touch its pinned buffers) on the NUMA node of its GPU."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/" % (dom, bus, dev)
+        node = int(open(path + "numa_node").read().strip())
+        cpus = open(path + "local_cpulist").read().strip()
+        ids = []
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids += list(range(int(a), int(b or a) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "cpus": len(ids)}
+    except Exception as ex:          # noqa: BLE001  (not fatal: the buffers are then wherever the kernel puts them)
+        return {"numa_node": None, "error": str(ex)[:80]}
 
 
 def cpu_reference_run(wl, nranks, nchain, nburn, nsamp, pl=0.9, bits=64):
     """Time the reference's own MCPar::run (oracle/_ref: its unmodified sources on shim
     MPI/MKL, thread ranks) on the host cores.  Returns chain-steps/s."""
-    import numpy as np
     from oracle.ref import Ref, available
     from conftest import tiled_pinit
     if not available(bits):
@@ -194,6 +246,224 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+class Job:
+    """One sharded (or single) engine of the job on this rank, with its exchange wiring."""
+
+    def __init__(self, ctx, Cg, rmode, M, ring, lag=None, chains_total=None, ranks=None):
+        import numpy as np
+        from mcpar_b200 import engine
+        from mcpar_b200.sharded import ShardedRunner, DistGroup
+        a, W = ctx["args"], ctx["W"]
+        self.ctx, self.Cg = ctx, Cg
+        self.world = ctx["world"] if ranks is None else ranks          # ranks that take part (the first `ranks` of the job)
+        self.rank = ctx["rank"]
+        self.active = self.rank < self.world
+        self.N = Cg * self.world if chains_total is None else chains_total
+        self.sync, self.thin = a.sync, a.thin
+        lag = a.lag if lag is None else lag
+        self.e = None
+        if not self.active:
+            return
+        self.e = engine.Engine(W["d"], Cg, mode="normal", nchain_total=self.N, chain0=self.rank * Cg, pl=a.pl, sync=a.sync,
+                               seed=SEED, pool_m=(M if 0 < M < self.N else 0), thin=a.thin, coin_group=a.coin_group,
+                               history_steps=ring, device=ctx["local"], remote_mode=rmode, pool_lag=lag)
+        self.e.set_stream(ctx["stream"].cuda_stream)                   # engine kernels, NCCL ops and timing events share it
+        self.e.set_likelihood(W["lik"], W["par"]); self.e.set_covariance(incov_for(a.workload))
+        self.runner = None
+        if self.world > 1:
+            import torch
+            dist = ctx["dist"]
+            grp = ctx["groups"].get(self.world)
+            as_tensor = lambda ptr: torch.as_tensor(ptr, device=ctx["dev"])
+            self.runner = ShardedRunner(self.e, DistGroup(dist, grp), as_tensor)
+            if a.exchange == "p2p":
+                def gather_bytes(b, grp=grp, n=self.world):
+                    out = [None] * n
+                    dist.all_gather_object(out, b, group=grp)
+                    return out
+                self.runner.enable_p2p(self.rank, self.world, gather_bytes)
+
+    def pinit(self):
+        """this rank's rows of the job's initial points: the reference mains' four points tiled by GLOBAL chain id
+        (conftest.tiled_pinit: chain g starts at P[g mod 4]); GaussMix: chain g at mu_{g mod K}"""
+        import numpy as np
+        from conftest import tiled_pinit
+        W = self.ctx["W"]
+        g0 = self.rank * self.Cg                                       # a multiple of 4 and of K
+        if "pinit" in W:
+            return np.ascontiguousarray(W["pinit"](np.arange(g0, g0 + self.Cg)))
+        assert g0 % 4 == 0
+        return tiled_pinit(self.Cg, W["d"])
+
+    def burn(self, n):
+        if self.runner is None:
+            self.e.burnin(n)
+        else:
+            self.runner.burnin(n)
+
+    def window(self):
+        if self.runner is None:
+            self.e.sample(self.sync)
+        else:
+            self.runner.window(self.sync)
+
+    def barrier(self):
+        if self.world > 1:
+            self.ctx["dist"].barrier(group=self.ctx["groups"].get(self.world))
+
+    def close(self):
+        if self.e is not None:
+            self.e.synchronize()
+            self.barrier()                                             # peers may still map this engine's exchange region
+            self.e.close()
+            self.e = None
+
+
+def timed_windows(ctx, job, K, flush):
+    """K windows, one CUDA-event pair each on the launching stream, the L2 flushed between them (outside the
+    pairs).  Returns (ms max over ranks, per-rank ms list, stats delta)."""
+    import torch
+    stream, dist = ctx["stream"], ctx["dist"]
+    torch.cuda.synchronize()
+    s0 = job.e.stats()
+    job.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(K):
+        if flush is not None:
+            flush.zero_()                                              # L2 flush, outside the event pair
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(stream); job.window(); b.record(stream)
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    job.barrier()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    per_rank = [ms / K]
+    if job.world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=ctx["dev"])
+        allt = [torch.zeros_like(t) for _ in range(job.world)]
+        dist.all_gather(allt, t, group=ctx["groups"].get(job.world))
+        per_rank = [float(x.item()) / K for x in allt]
+        ms = max(per_rank) * K
+    s1 = job.e.stats()
+    delta = {k: s1[k] - s0[k] for k in s1 if isinstance(s1[k], int)}
+    return ms, per_rank, delta
+
+
+def measure(ctx, Cg, rmode, M, K, advance, warmup, flush, lag=None, ranks=None, clocks=None):
+    """Resident throughput of one configuration: burn-in 500, `advance` untimed windows, `warmup` untimed
+    windows, K timed windows.  Returns a dict (on every active rank)."""
+    a = ctx["args"]
+    job = Job(ctx, Cg, rmode, M, ring=max(8, 4 * ((a.sync + a.thin - 1) // a.thin)), lag=lag, ranks=ranks)
+    if not job.active:
+        return None
+    job.e.set_state(job.pinit())
+    job.burn(500)
+    job.e.sample_begin((advance + warmup + K) * a.sync)
+    if clocks is not None:
+        clocks.mark()                                                  # the GPU is busy from here to the end of the timed region
+    for _ in range(advance + warmup):
+        job.window()
+    ms, per_rank, d = timed_windows(ctx, job, K, flush)
+    ck = clocks.stop() if clocks is not None else None
+    mean, cov = job.e.moments()
+    st = job.e.stats()
+    out = {"value": job.N * a.sync * K / (ms * 1e-3), "ms_per_step": ms / K, "per_rank_ms_per_step": per_rank,
+           "chains_total": job.N, "n_gpus": job.world, "pool_m": M if 0 < M < job.N else job.N,
+           "remote_mode": "summix" if rmode else "reference", "lag": a.lag if lag is None else lag, "steps": K, "advance": advance,
+           "launches": d["kernel_launches"] + (K if job.world > 1 and a.exchange == "nccl" else 0),
+           "remote_fraction": d["remote_steps"] / max(1, d["tried"]),
+           "remote_iterations_mean": d["remote_iterations"] / max(1, d["remote_steps"]),
+           "exact_fallback_rate": d["exact_fallbacks"] / max(1, d["remote_iterations"]),
+           "accept_rate": d["accepted"] / max(1, d["tried"]),
+           "exchange_wait_ms_per_step": d["exchange_wait_ns"] * 1e-6 / K, "exchange_waits": d["exchange_waits"],
+           "posterior_mean": [float(x) for x in mean[:4]], "posterior_var": [float(cov[i, i]) for i in range(min(4, len(mean)))],
+           "clocks": ck}
+    job.close()
+    return out
+
+
+def sharded_equals_single(ctx):
+    """Untimed check at N > 1: a short sharded run (all ranks, the bench's exchange) against the same run on ONE
+    engine hosting every chain (rank 0): final states must be bit-identical."""
+    import numpy as np
+    import torch
+    a, world, rank, dist = ctx["args"], ctx["world"], ctx["rank"], ctx["dist"]
+    Cg, M, nburn, nsamp = 1 << 14, 16, 110, 60
+    import hashlib
+    res = {}
+    for rmode in (0, 1):
+        job = Job(ctx, Cg, rmode, M, ring=8)
+        job.e.set_state(job.pinit())
+        job.burn(nburn)
+        job.e.sample_begin(nsamp)
+        for _ in range(nsamp // a.sync):
+            job.window()
+        job.e.synchronize()
+        st = job.e.state()
+        mine = np.concatenate([st["p"].ravel(), st["ly"], st["mu"].ravel(), st["psum2"].ravel()])
+        parts = [None] * world
+        dist.all_gather_object(parts, mine.tobytes())
+        job.close()
+        if rank == 0:
+            one = Job(ctx, Cg * world, rmode, M, ring=8, ranks=1, chains_total=Cg * world)
+            one.e.set_state(one.pinit())
+            one.burn(nburn)
+            one.e.sample_begin(nsamp); one.e.sample(nsamp); one.e.synchronize()
+            s1 = one.e.state()
+            one.e.close(); one.e = None
+            ok = True
+            for r in range(world):
+                sl = slice(r * Cg, (r + 1) * Cg)
+                ref = np.concatenate([s1["p"][sl].ravel(), s1["ly"][sl], s1["mu"][sl].ravel(), s1["psum2"][sl].ravel()])
+                ok = ok and parts[r] == ref.tobytes()
+            res["summix" if rmode else "reference"] = bool(ok)
+            res["state_sha1_" + ("summix" if rmode else "reference")] = hashlib.sha1(b"".join(parts)).hexdigest()[:16]
+        dist.barrier()
+    return res
+
+
+def e2e_job(ctx, Cg, rmode, M, f32, reps):
+    """MCPar::run-shaped job through the C ABI with HOST buffers (H2D of pinit, D2H of the rows and the final
+    logL inside the clock).  Returns best seconds, construction seconds, bytes."""
+    import numpy as np
+    import torch
+    a, W = ctx["args"], ctx["W"]
+    nb_e, ns_e = 500, 1000
+    kept_e = (ns_e + a.thin - 1) // a.thin
+    d = W["d"]
+    sink = torch.empty((kept_e, Cg, d + 1), dtype=torch.float32 if f32 else torch.float64).pin_memory().numpy()
+    best, best_c, fin = None, None, None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        job = Job(ctx, Cg, rmode, M, ring=min(kept_e, 16))             # device history: a ring of 16 kept steps
+        host_pin = torch.from_numpy(job.pinit()).pin_memory().numpy()
+        job.barrier()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        job.e.set_state(host_pin)                                      # H2D inside the timed region
+        job.e.attach_host_sink(sink)                                   # D2H drains on a side stream per window
+        job.burn(nb_e)
+        job.e.sample_begin(ns_e)
+        for _ in range(ns_e // a.sync):
+            job.window()
+        fin = job.e.state()["ly"]
+        job.e.synchronize()                                            # compute + drain finished
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        job.close()
+        tt = torch.tensor([t2 - t1, t1 - t0], dtype=torch.float64, device=ctx["dev"])
+        if ctx["world"] > 1:
+            ctx["dist"].all_reduce(tt, op=ctx["dist"].ReduceOp.MAX)
+        sec, con = float(tt[0].item()), float(tt[1].item())
+        if best is None or sec < best:
+            best, best_c = sec, con
+    nwin = (nb_e + ns_e) // a.sync
+    return {"seconds": best, "construction_seconds": best_c, "chain_steps": Cg * ctx["world"] * (nb_e + ns_e),
+            "h2d": int(Cg * d * 8 // nwin), "d2h": int((sink.nbytes + fin.nbytes) // nwin), "nwin": nwin}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,14 +473,21 @@ def main():
     ap.add_argument("--workload", default="dgauss", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=1 << 20, help="chains per GPU")
     ap.add_argument("--pool", type=int, default=16, help="remote-mixture pool size M")
+    ap.add_argument("--remote-mode", default="reference", choices=sorted(RMODE),
+                    help="reference: the reference's max-mixture rejection loop; summix: normalised sum-mixture proposal")
+    ap.add_argument("--lag", type=int, default=1, choices=[0, 1],
+                    help="1: a window reads the pool published two windows earlier (exchange off the critical path)")
     ap.add_argument("--pl", type=float, default=0.9)
     ap.add_argument("--coin-group", type=int, default=0, help="0: one local/remote coin per step for the whole job; 1..32: per group of chains")
     ap.add_argument("--thin", type=int, default=10)
     ap.add_argument("--sync", type=int, default=10)
+    ap.add_argument("--advance", type=int, default=-1, help="untimed windows before the timed region (-1: the workload's default)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: in-kernel peer-to-peer stores over NVLink (default) or an NCCL all-gather call per window")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-modes", action="store_true", help="skip the secondary measurements of the other remote modes")
+    ap.add_argument("--no-check", action="store_true", help="N>1: skip the sharded == single-engine check")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                         # timing rule: W >= 3
@@ -222,7 +499,6 @@ def main():
     import torch
     import torch.distributed as dist
     from mcpar_b200 import engine
-    from conftest import tiled_pinit
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -230,49 +506,30 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa(local)
+    clocks = ClockSampler(local)                 # every rank, before anything is timed
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = dict(WORKLOADS[args.workload])
     if W["par"] == "gmix64":
         K_, d_, gmu, gs2, gw = gmix64_params()
         W["par"] = np.concatenate([[float(K_)], gmu.ravel(), gs2.ravel(), gw])
-        W["pinit"] = lambda N_: gmu[np.arange(N_) % K_]            # chain g starts at mu_{g mod K}
+        W["pinit"] = lambda g_: gmu[g_ % K_]                       # chain g starts at mu_{g mod K}
     if "sync" in W and args.sync == 10:
         args.sync = W["sync"]
     if "thin" in W and args.thin == 10:
         args.thin = W["thin"]
+    if args.advance < 0:
+        args.advance = W["advance"]
     d, Cg, sync, thin = W["d"], args.chains, args.sync, args.thin
     N = Cg * world
     K, Wu = args.steps, args.warmup
-    nburn = 500
-    nsamp = (K + Wu) * sync
-    kept = (nsamp + thin - 1) // thin
+    rmode = RMODE[args.remote_mode]
 
     stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)                 # engine kernels, NCCL ops and timing events share it
-    e = engine.Engine(d, Cg, mode="normal", nchain_total=N, chain0=rank * Cg, pl=args.pl, sync=sync,
-                      seed=SEED, pool_m=args.pool, thin=thin, coin_group=args.coin_group, history_steps=kept, device=local)
-    e.set_stream(stream.cuda_stream)
-    e.set_likelihood(W["lik"], W["par"]); e.set_covariance(incov_for(args.workload))
-    pin = np.ascontiguousarray((W["pinit"](N) if "pinit" in W else tiled_pinit(N, d))[rank * Cg:(rank + 1) * Cg])
-    e.set_state(pin)
-
-    # ---- sharded runs: pool all-gather + tuning all-reduce over NCCL (mcpar_b200/sharded.py)
-    from mcpar_b200.sharded import ShardedRunner, DistGroup
-    as_tensor = lambda ptr: torch.as_tensor(ptr, device=dev)
-
-    def gather_bytes(b):
-        out = [None] * world
-        dist.all_gather_object(out, b)
-        return out
-
-    def make_runner(eng):
-        if world == 1:
-            return None
-        r = ShardedRunner(eng, DistGroup(dist), as_tensor)
-        if args.exchange == "p2p":
-            r.enable_p2p(rank, world, gather_bytes)
-        return r
+    torch.cuda.set_stream(stream)
+    ctx = {"args": args, "W": W, "rank": rank, "world": world, "local": local, "dev": dev, "stream": stream, "dist": dist,
+           "groups": {world: None}}
 
     if world > 1 and args.exchange == "p2p":
         # probe with a throwaway engine that every rank can map every peer's exchange region (CUDA IPC +
@@ -283,7 +540,8 @@ def main():
             h = pe.p2p_export()
         except engine.McgpuError as ex:
             sys.stderr.write("rank %d: peer-to-peer export failed (%s)\n" % (rank, ex))
-        hs = gather_bytes(h)
+        hs = [None] * world
+        dist.all_gather_object(hs, h)
         ok = int(all(len(x) == engine.P2P_HANDLE_BYTES for x in hs))
         if ok:
             try:
@@ -301,117 +559,44 @@ def main():
             if rank == 0:
                 sys.stderr.write("peer-to-peer exchange unavailable on this box: using the NCCL all-gather exchange\n")
 
-    runner = [make_runner(e)]
-
-    def burn(n):
-        if world == 1:
-            e.burnin(n)
-        else:
-            runner[0].burnin(n)
-
-    def window():
-        if world == 1:
-            e.sample(sync)
-        else:
-            runner[0].window(sync)
-
-    burn(nburn)
-    e.sample_begin(nsamp)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    for _ in range(Wu):
-        window()
-    torch.cuda.synchronize()
-    l0 = e.stats()["kernel_launches"]
+    head = measure(ctx, Cg, rmode, args.pool, K, args.advance, Wu, flush, clocks=clocks)
+    ck = head["clocks"]
 
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clocks = ClockSampler(local) if rank == 0 else None
-    evs = []
-    for _ in range(K):
-        flush.zero_()                                                    # L2 flush, outside the event pair
-        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-        a.record(stream); window(); b.record(stream)
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ck = clocks.stop() if clocks else None
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    per_rank_ms = [ms / K]
-    if world > 1:
-        allt = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(allt, t)
-        per_rank_ms = [float(x.item()) / K for x in allt]                # diagnostic: skew between GPUs
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    st = e.stats()
-    launches = st["kernel_launches"] - l0 + (K if world > 1 and args.exchange == "nccl" else 0)   # + NCCL all-gathers
-    value = N * sync * K / (ms * 1e-3)
-    acc_rate = st["accepted"] / max(1, st["tried"])
-    mean, cov = e.moments()
+    # ---- the other remote-proposal configurations, measured the same way (shorter)
+    modes = None
+    if not args.no_modes:
+        modes = {}
+        Km = min(K, 200)
+        todo = [("summix_M16", 1, 16), ("summix_M256", 1, 256)] if W["d"] <= 16 else [("summix_M256", 1, 256)]
+        if rmode == 1:
+            todo = [("reference_M16", 0, 16)] + [t for t in todo if t[2] != args.pool]
+        for name, rm, M in todo:
+            r = measure(ctx, Cg, rm, M, Km, min(args.advance, 300), Wu, flush)
+            modes[name] = {k: r[k] for k in ("value", "ms_per_step", "pool_m", "remote_mode", "steps", "advance", "remote_fraction",
+                                             "remote_iterations_mean", "exact_fallback_rate", "accept_rate", "posterior_mean",
+                                             "exchange_wait_ms_per_step")}
+
+    check = None
+    if world > 1 and not args.no_check:
+        check = sharded_equals_single(ctx)
 
     # ---- end to end: MCPar::run-shaped job through the C ABI with HOST buffers
     e2e = None
     if not args.no_e2e:
-        nb_e, ns_e = 500, 1000
-        kept_e = (ns_e + thin - 1) // thin
-        if world > 1:
-            dist.barrier()
-        e.close(); del flush; torch.cuda.empty_cache()
-        host_rows = torch.empty((kept_e, Cg, d + 1), dtype=torch.float64).pin_memory().numpy()
-        host_pin = torch.from_numpy(np.ascontiguousarray(pin)).pin_memory().numpy()
-        host_rows32 = torch.empty((kept_e, Cg, d + 1), dtype=torch.float32).pin_memory().numpy()
-        best = None; best32 = None
-        for rep in range(6):                    # reps 0-2: fp64 sink (the e2e figure); 3-5: fp32 sink (reported beside it)
-            sink_rows = host_rows if rep < 3 else host_rows32
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            e = engine.Engine(d, Cg, mode="normal", nchain_total=N, chain0=rank * Cg, pl=args.pl, sync=sync,
-                              seed=SEED, pool_m=args.pool, thin=thin, coin_group=args.coin_group, history_steps=kept_e, device=local)
-            e.set_stream(stream.cuda_stream)
-            e.set_likelihood(W["lik"], W["par"]); e.set_covariance(incov_for(args.workload))
-            runner[0] = make_runner(e)                                  # construction: engines + their exchange wiring
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            e.set_state(host_pin)                                       # H2D inside the timed region
-            e.attach_host_sink(sink_rows)                               # D2H drains on a side stream per window
-            burn(nb_e)
-            e.sample_begin(ns_e)
-            for _ in range(ns_e // sync):
-                window()
-            fin = e.state()["ly"]
-            e.synchronize()                                              # compute + drain finished
-            torch.cuda.synchronize()
-            t2 = time.perf_counter()
-            if world > 1:
-                dist.barrier()                                           # peers may still map this engine's exchange region
-            e.close()
-            tt = torch.tensor([t2 - t1], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            sec = float(tt.item())
-            if rep < 3:
-                best = sec if best is None or sec < best else best
-            else:
-                best32 = sec if best32 is None or sec < best32 else best32
-        nwin = (nb_e + ns_e) // sync
-        e2e = {"value": N * (nb_e + ns_e) / best, "unit": UNIT,
-               "h2d_bytes_per_step": int(pin.nbytes // nwin),
-               "d2h_bytes_per_step": int((host_rows.nbytes + fin.nbytes) // nwin),
-               "job": "set_state(host pinit) + burnin 500 + 1000 steps + history(thin %d) and final logL to pinned host; "
-                      "bytes are per 10-step window of the 150-window job; best of 3" % thin,
-               "seconds": best,
-               "fp32_sink": {"value": N * (nb_e + ns_e) / best32, "seconds": best32,
-                             "d2h_bytes_per_step": int((host_rows32.nbytes + fin.nbytes) // nwin),
-                             "note": "same job with the rows narrowed on the device to fp32, the element type of the "
-                                     "reference's MCout (mcgpu_history_attach_host_f32); compute stays fp64"}}
+        del flush; torch.cuda.empty_cache()
+        f32 = e2e_job(ctx, Cg, rmode, args.pool, True, 3)              # rows in the reference MCout's element type (float)
+        f64 = e2e_job(ctx, Cg, rmode, args.pool, False, 2)
+        e2e = {"value": f32["chain_steps"] / f32["seconds"], "unit": UNIT,
+               "h2d_bytes_per_step": f32["h2d"], "d2h_bytes_per_step": f32["d2h"],
+               "job": "set_state(host pinit) + burnin 500 + 1000 steps + history(thin %d, fp32 rows = the reference MCout's element "
+                      "type, narrowed on the device; device history = a ring of 16 kept steps drained on a side stream) and final logL "
+                      "to pinned host; bytes are per %d-step window of the %d-window job; best of 3" % (thin, sync, f32["nwin"]),
+               "seconds": f32["seconds"], "construction_seconds": f32["construction_seconds"],
+               "construction": "engine create + likelihood/covariance upload + exchange wiring (CUDA IPC attach), outside the e2e clock, max over ranks",
+               "host_numa": numa,
+               "fp64_sink": {"value": f64["chain_steps"] / f64["seconds"], "seconds": f64["seconds"], "d2h_bytes_per_step": f64["d2h"],
+                             "note": "same job with fp64 rows on the host (twice the PCIe bytes)"}}
 
     if rank == 0:
         peak = engine.measure_fp64_peak(local)
@@ -421,58 +606,53 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        per_gpu = value / world
+        per_gpu = head["value"] / world
         bytes_step = 2 * (3 * d + 1) * 8 / sync + (d + 1) * 8 / thin     # state round trip + history, SURVEY 8(d)
-        traffic = None
+        key = "%s/%s/M%d" % (args.workload, args.remote_mode, args.pool)
+        prof = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "fp64_work.json"))).get(key, {})
         except Exception:
             pass
-        # a remote step adds (iterations + 1) x M x (3d + 1 flops + 1 exp [= 30]) per chain on top
-        # of the local-step figure F_hw; the remote fraction and the iterations are counted by the kernels
-        Mpool = args.pool if 0 < args.pool < N else N
-        f_rem = st["remote_steps"] / max(1, st["tried"])
-        iters = st["remote_iterations"] / max(1, st["remote_steps"])
-        F_rem = (iters + 1.0) * Mpool * (3 * d + 1 + 30.0)
-        F_tot = W["F_hw"] + f_rem * F_rem
-        ach = per_gpu * W["F_hw"] / 1e12
-        ach_rem = per_gpu * F_tot / 1e12
+        F = prof.get("fp64_flops_per_chain_step")
+        ach = per_gpu * (F if F else W["F_hw"]) / 1e12
         roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                "traffic": traffic,
-                "flops_per_chain_step": W["F_hw"],
-                "with_remote_loop_work": {"achieved": ach_rem, "frac": ach_rem / peak if peak else None,
-                                          "flops_per_chain_step": F_tot, "remote_fraction": f_rem,
-                                          "remote_iterations_mean": iters},
-                "note": "achieved = chain-steps/s/GPU x F_hw (%g hardware-equivalent fp64 flops per chain-step of this "
-                        "workload, SURVEY.md 8d; the same definition as in every earlier bench line); "
-                        "with_remote_loop_work adds SURVEY 8d's remote term, remote_fraction x (iterations+1) x M x "
-                        "(3d+1 flops + exp=30), with the fraction and the iterations counted by the kernels in this run "
-                        "-- that work is algorithmic: the kernels retire it in fp32 under rigorous bounds, not on the FP64 pipe; "
-                        "peak = DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no fp64 figure); "
-                        "kernel time = CUDA events around each window launch; ncu pipe utilisation: profiles/README.md" % W["F_hw"],
+                "traffic": prof.get("dram_bytes_per_launch"),
+                "flops_per_chain_step": F if F else W["F_hw"],
+                "flops_source": ("ncu: (dadd + dmul + 2 dfma) thread instructions of the window kernels / chain-steps, %s" % prof.get("source", "profiles/fp64_work.json")
+                                 if F else "SURVEY.md 8(d) a-priori estimate (no ncu count committed for %s)" % key),
+                "fp64_pipe_util_ncu": prof.get("fp64_pipe_pct"),
+                "note": "achieved = chain-steps/s/GPU x fp64 flops per chain-step; peak = DFMA micro-kernel measured in this run "
+                        "(MEASURED_PEAKS.json has no fp64 figure); kernel time = CUDA events around each window launch; traffic and the "
+                        "pipe utilisation come from the committed ncu capture of this configuration (profiles/README.md), null if none",
                 "achieved_textbook_tflops": per_gpu * W["F_alg"] / 1e12,
                 "hbm": {"achieved": per_gpu * bytes_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": per_gpu * bytes_step / 1e9 / hbm_peak, "bytes_per_chain_step": bytes_step,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         cpu = None if (args.no_cpu or world > 1) else cpu_baseline(args.workload)   # rank 0 at N = 1 only
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "%s: %s d=%d, %d chains/GPU x %d GPU, PLOCAL %.2f, SYNCSTEP %d, pool M=%d, %s, thin %d, "
-                                       "seed %d; step = one %d-step exchange window" % (
-                                           W["name"], W["lik"], d, Cg, world, args.pl, sync, args.pool,
+                "config": {"workload": "%s: %s d=%d, %d chains/GPU x %d GPU, PLOCAL %.2f, SYNCSTEP %d, remote mode %s, pool M=%d, pool lag %d, %s, "
+                                       "thin %d, seed %d; step = one %d-step exchange window; %d untimed windows before the timed region" % (
+                                           W["name"], W["lik"], d, Cg, world, args.pl, sync, args.remote_mode, args.pool, args.lag,
                                            "one local/remote coin per step" if args.coin_group == 0 else "coin per %d chains" % args.coin_group,
-                                           thin, SEED, sync),
+                                           thin, SEED, sync, args.advance + Wu),
                            "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
                            "parallelism": ("single GPU" if world == 1 else
                                            "chains sharded by global id; pool exchanged inside the window kernel by peer-to-peer stores over NVLink"
                                            if args.exchange == "p2p" else
                                            "chains sharded by global id; pool all-gather over NCCL each window")},
-                "clocks": ck, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "per_rank_ms_per_step": per_rank_ms, "accept_rate": acc_rate, "posterior_mean": [float(x) for x in mean],
-                "posterior_var": [float(cov[i, i]) for i in range(d)]}
+                "clocks": ck, "e2e": e2e, "gpu_launches": int(head["launches"]), "roofline": roof, "cpu_baseline": cpu,
+                "per_rank_ms_per_step": head["per_rank_ms_per_step"], "accept_rate": head["accept_rate"],
+                "remote_fraction": head["remote_fraction"], "remote_iterations_mean": head["remote_iterations_mean"],
+                "exact_fallback_rate": head["exact_fallback_rate"],
+                "exchange_wait_ms_per_step": head["exchange_wait_ms_per_step"],
+                "posterior_mean": head["posterior_mean"], "posterior_var": head["posterior_var"],
+                "modes": modes, "sharded_equals_single": check}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

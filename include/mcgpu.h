@@ -115,6 +115,8 @@ typedef struct mcgpu_stats {
   int64_t exchange_wait_ns;             /* peer-to-peer exchange: time the window kernels' first CTA spent
                                            waiting for the peers' pool slots (globaltimer)   */
   int64_t exchange_waits;               /* ... and how many launches had to wait at all      */
+  int64_t exact_fallbacks;              /* remote candidates / steps whose fp32 bounds did not settle the
+                                           decision and were redone exactly in fp64 */
 } mcgpu_stats;
 
 const char *mcgpu_version(void);

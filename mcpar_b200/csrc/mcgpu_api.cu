@@ -44,7 +44,7 @@ struct mcgpu_engine {
   // NORMAL / REPLAY_LOCAL state (SoA) or VERIFY state (AoS per rank)
   double *x = nullptr, *ly = nullptr, *mu = nullptr, *ps = nullptr;
   double *factor = nullptr;
-  unsigned long long *counts = nullptr;   // [0,1] window, [2,3] cumulative, [4,5] main-phase stats, [6,7] remote chain-steps / candidate iterations, [8,9] exchange wait ns / waits
+  unsigned long long *counts = nullptr;   // [0,1] window, [2,3] cumulative, [4,5] main-phase stats, [6,7] remote chain-steps / candidate iterations, [8,9] exchange wait ns / waits, [10] exact-path fallbacks of the bounded tests
   // exchange region (one allocation, IPC-exportable): NPOOL pool buffers [M][d][2] + the arrival counter
   char *xchg = nullptr; size_t pool_bytes = 0, xchg_bytes = 0;
   double *pool[4] = {nullptr, nullptr, nullptr, nullptr}; int M = 0; long long stride = 1; bool pool_in_smem = true;
@@ -931,6 +931,7 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
             int len = 1;
             while (k + len < n && is_remote(t + len) == rem) ++len;
             p.step0 = (uint32_t)(e->nburn_total + t); p.nsteps = len; p.t0 = (int)t;
+            p.hist_ring0 = e->hist ? (int)((t / e->cfg.thin) % e->hist_cap) : 0;
             p.pool_next = (k + len == n) ? publish : nullptr;
             if (rem && !prepped) CK(pool_prep());
             CK(launch_steps_any(e, rem ? PH_REMOTE : PH_LOCAL, p));
@@ -1496,7 +1497,7 @@ int mcgpu_get_stats(mcgpu_engine *e, mcgpu_stats *out)
     CK(cudaMemcpy(h, e->counts, 96, cudaMemcpyDeviceToHost));
     out->accepted = (int64_t)h[4]; out->tried = (int64_t)h[5];
     out->remote_steps = (int64_t)h[6]; out->remote_iterations = (int64_t)h[7];
-    out->exchange_wait_ns = (int64_t)h[8]; out->exchange_waits = (int64_t)h[9];
+    out->exchange_wait_ns = (int64_t)h[8]; out->exchange_waits = (int64_t)h[9]; out->exact_fallbacks = (int64_t)h[10];
   }
   return MCGPU_OK;
 }

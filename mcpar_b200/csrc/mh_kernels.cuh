@@ -327,7 +327,7 @@ __device__ __forceinline__ float normal_pair_f32(uint32_t wa, uint32_t wb, float
 template <int D, bool RK>
 __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uint32_t step, uint32_t slot, const StepParams &p,
                                                  const float2 *sPf, const float2 *sSf, const double2 *sPmh, const double *sPs,
-                                                 float mu_max, float isig_max, const MathTables &T)
+                                                 float mu_max, float isig_max, const MathTables &T, unsigned int *s_fallback)
 {
   constexpr int CH = 8;
   constexpr int NP = (D + 1) / 2;
@@ -420,6 +420,7 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
       if (u * (Sd * (1.0 - eps)) >= 1.0) return false;              // u >= r_hi
     }
   }
+  atomicAdd(s_fallback, 1u);                            // statistics: candidates the fp32 bounds did not settle
   return remote_exact<D>(tlo, thi, step, slot, p.key0, p.key1, sPmh, sPs, M, T);   // rare: the bounds straddle u (also the NaN path)
 }
 
@@ -611,7 +612,7 @@ mh_steps_kernel(const StepParams p)
   constexpr bool CAN_REMOTE = RNGK == RNG_PHILOX && (MIXED || ALLREMOTE);
   extern __shared__ __align__(16) double smem[];
   __shared__ unsigned char s_rank[4][32];               // per warp: lanes of the chains still in the remote loop
-  __shared__ unsigned int s_stat[2];                    // remote chain-steps of this CTA and the candidates they tried
+  __shared__ unsigned int s_stat[3];                    // remote chain-steps of this CTA, the candidates they tried, exact-path fallbacks
   __shared__ unsigned int s_itacc[128];                 // per chain: index of the accepted candidate of the current remote step
   // smem: math tables | [D*D] factor | [nsteps] 1/pwgt table | pool: mu, -1/(2 sig^2), sigma
   double *sT = smem + MCGPU_MATH_SMEM;
@@ -641,7 +642,7 @@ mh_steps_kernel(const StepParams p)
   const int leader = lane & ~(p.coin_group - 1);
 
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) sT[i] = p.factor[i];
-  if (CAN_REMOTE && threadIdx.x < 2) s_stat[threadIdx.x] = 0u;
+  if (CAN_REMOTE && threadIdx.x < 3) s_stat[threadIdx.x] = 0u;
   if (MAIN)
     for (int k = threadIdx.x; k < p.nsteps; k += blockDim.x) sW[k] = 1.0 / (double)(p.t0 + k + 1);
   __syncthreads();
@@ -731,7 +732,7 @@ mh_steps_kernel(const StepParams p)
           const uint32_t it = __shfl_sync(0xffffffffu, it_next, tgt) + (uint32_t)kk;
           const uint32_t tlo = __shfl_sync(0xffffffffu, glo, tgt), thi = __shfl_sync(0xffffffffu, ghi, tgt);
           const bool acc = remote_candidate<D, true>(tlo, thi, step, MCGPU_SLOT_REMOTE | (it << 6), p, sPf, sSf, sPmh, sPs,
-                                                           s_scal[0], s_scal[1], T);
+                                                           s_scal[0], s_scal[1], T, &s_stat[2]);
           const unsigned accmask = __ballot_sync(0xffffffffu, acc);
           if (pending) {
             const unsigned cm = c_stride_mask[n] << my_r;             // lanes my_r, my_r+n, ... served this chain
@@ -840,6 +841,7 @@ mh_steps_kernel(const StepParams p)
         if (!p.exact_tests && summix_bounds<D>(x, xt, cpick, p.pool_m, sPf, sNb, s_scal, cf_lo, cf_hi))
           dec = accept_test_bounded(u_acc, lyt - ly, cf_lo, cf_hi);
         if (dec < 0) {
+          atomicAdd(&s_stat[2], 1u);                     // statistics: remote steps the fp32 bounds did not settle
           PointD<D> po, pn;
 #pragma unroll
           for (int i = 0; i < D; ++i) { po.v[i] = x[i]; pn.v[i] = xt[i]; }
@@ -940,6 +942,7 @@ mh_steps_kernel(const StepParams p)
     __syncthreads();
     if (threadIdx.x == 0 && s_stat[0]) {
       atomicAdd(p.counts + 2, (unsigned long long)s_stat[0]); atomicAdd(p.counts + 3, (unsigned long long)s_stat[1]);
+      if (s_stat[2]) atomicAdd(p.counts + 6, (unsigned long long)s_stat[2]);
     }
   }
 }

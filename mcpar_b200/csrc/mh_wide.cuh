@@ -232,7 +232,7 @@ mh_wide_kernel(const WideParams p)
   const long long jb = ((long long)blockIdx.x * (blockDim.x / L) + gib) * NCH;
   long long jc[NCH]; bool live[NCH]; uint32_t glo[NCH], ghi[NCH];
   double x0[NCH], x1[NCH], ly[NCH], mu0[NCH], mu1[NCH], ps0[NCH], ps1[NCH];
-  unsigned int nacc[NCH], nit = 0;                // accepted steps; candidate iterations of the remote steps
+  unsigned int nacc[NCH], nit = 0, nfb = 0;       // accepted steps; candidate iterations of the remote steps; exact-path fallbacks
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     live[c] = jb + c < p.C;
@@ -362,6 +362,7 @@ mh_wide_kernel(const WideParams p)
         if (!__all_sync(0xffffffffu, alldec)) {        // rare: exact pacpt = qimax / qisum, warp-wide
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
+            nfb += (!decided[c] && !done[c] && live[c]) ? 1u : 0u;
             double qmax;
             const double qsum = wide_pool_exact_sum<D, NCH>(sx, c, r, p, qmax, T) + MCGPU_FPEPS;
             qmax = qmax > MCGPU_FPEPS ? qmax : MCGPU_FPEPS;
@@ -418,6 +419,8 @@ mh_wide_kernel(const WideParams p)
       }
       if (!__all_sync(0xffffffffu, alldec)) {          // rare: exact log q(x) - log q(x'), warp-wide
         double lo_[NCH], ln_[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) nfb += (dec[c] < 0 && live[c]) ? 1u : 0u;
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) { sx[i0 * NCH + c] = xt0[c]; sx[(i0 + 1) * NCH + c] = xt1[c]; }
@@ -498,12 +501,13 @@ mh_wide_kernel(const WideParams p)
     atomicAdd(p.counts + 1, (unsigned long long)nlive * (unsigned long long)p.nsteps);
   }
   if (REMOTE) {                                 // main-phase statistics: counts[2] remote chain-steps, [3] candidates
-    unsigned int wi = r == 0 ? nit : 0u;        // every lane of a group counted the same
+    unsigned int wi = r == 0 ? nit : 0u, wf = r == 0 ? nfb : 0u;   // every lane of a group counted the same
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wi += __shfl_xor_sync(0xffffffffu, wi, o);
+    for (int o = 16; o > 0; o >>= 1) { wi += __shfl_xor_sync(0xffffffffu, wi, o); wf += __shfl_xor_sync(0xffffffffu, wf, o); }
     if ((threadIdx.x & 31) == 0) {
       atomicAdd(p.counts + 2, (unsigned long long)nlive * (unsigned long long)p.nsteps);
       atomicAdd(p.counts + 3, (unsigned long long)wi);
+      if (wf) atomicAdd(p.counts + 6, (unsigned long long)wf);
     }
   }
 }

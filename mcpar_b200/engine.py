@@ -55,7 +55,8 @@ class Stats(C.Structure):
     _fields_ = [("burn_steps", C.c_int64), ("main_steps", C.c_int64), ("accepted", C.c_int64),
                 ("tried", C.c_int64), ("kernel_launches", C.c_int64), ("remote_steps", C.c_int64),
                 ("remote_iterations", C.c_int64), ("history_rows", C.c_int64),
-                ("device_ms", C.c_double), ("exchange_wait_ns", C.c_int64), ("exchange_waits", C.c_int64)]
+                ("device_ms", C.c_double), ("exchange_wait_ns", C.c_int64), ("exchange_waits", C.c_int64),
+                ("exact_fallbacks", C.c_int64)]
 
 
 _lib = None

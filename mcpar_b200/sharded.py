@@ -65,12 +65,25 @@ class DistGroup:
 class ShardedRunner:
     """Drives ONE engine of a sharded run; every rank executes the same sequence."""
 
-    def __init__(self, engine, group, as_tensor):
+    def __init__(self, engine, group, as_tensor, cuda_stream=None):
         """engine: mcpar_b200.engine.Engine created with nchain < nchain_total.
-        group: DistGroup-like.  as_tensor: DevicePtr -> tensor aliasing that memory."""
+        group: DistGroup-like.  as_tensor: DevicePtr -> tensor aliasing that memory.
+        The collectives below run on torch's CURRENT stream and touch buffers the engine's kernels write
+        (the next pool, the tuning counters), so the engine is put on that stream here (`cuda_stream`: a
+        cudaStream_t as int, default torch.cuda.current_stream()): launches and collectives are then ordered."""
         self.e, self.g, self.as_tensor = engine, group, as_tensor
         self._views = {}
         self._cnt = None
+        if hasattr(engine, "set_stream"):
+            if cuda_stream is None:
+                try:
+                    import torch
+                    if torch.cuda.is_available():
+                        cuda_stream = torch.cuda.current_stream().cuda_stream
+                except ImportError:
+                    pass
+            if cuda_stream is not None:
+                engine.set_stream(cuda_stream)
 
     def burnin(self, nburn):
         """Burn-in with GLOBAL acceptance-rate tuning: the window counters are summed over

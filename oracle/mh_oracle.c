@@ -624,7 +624,15 @@ int orc_run_counter(const orc_config *cfg, const double *pinit, const double *in
   if (st_ly) memcpy(st_ly, ly, 8*(size_t)N);
   if (st_mu) memcpy(st_mu, mu, 8*(size_t)N*d);
   if (st_psum2) memcpy(st_psum2, ps, 8*(size_t)N*d);
-  if (pool_out) memcpy(pool_out, lag ? pool_new : pool, 8*(size_t)M*d*2);   /* the latest publication */
+  if (pool_out) {                                    /* the latest publication: the engine publishes at the END of every
+                                                        window, so a run that ends on a boundary has one more than the loop
+                                                        above has read */
+    double *last = lag ? pool_new : pool;
+    if (cfg->nsamp > 0 && cfg->nsamp % cfg->sync == 0)
+      for (int s = 0; s < M; ++s) { size_t g = (size_t)s*stride;
+        for (int i = 0; i < d; ++i) { last[((size_t)s*d+i)*2] = mu[g*d+i]; last[((size_t)s*d+i)*2+1] = ps[g*d+i] * (1.0/(double)cfg->nsamp); } }
+    memcpy(pool_out, last, 8*(size_t)M*d*2);
+  }
   if (acc_counts) { acc_counts[0] = nacc; acc_counts[1] = ntry; }
   if (cov_out) memcpy(cov_out, T0, 8*(size_t)d*d);
   if (remote_iters) *remote_iters = riters;

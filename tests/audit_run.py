@@ -10,8 +10,8 @@ from conftest import tiled_pinit                        # noqa: E402
 from mcpar_b200 import engine                           # noqa: E402
 
 
-def run(lik, par, d, N, M, pl, cg, nburn, nsamp):
-    e = engine.Engine(d, N, mode="normal", pool_m=M, pl=pl, coin_group=cg, history_steps=nsamp)
+def run(lik, par, d, N, M, pl, cg, nburn, nsamp, rmode=0):
+    e = engine.Engine(d, N, mode="normal", pool_m=M, pl=pl, coin_group=cg, history_steps=nsamp, remote_mode=rmode)
     e.run(nsamp, nburn, tiled_pinit(N, d), lik, par)
     out = dict(hist=e.history(), p=e.state()["p"], pool=e.musig(), acc=np.array(e.stats()["accepted"]),
                rit=np.array(e.stats()["remote_iterations"]))
@@ -24,6 +24,11 @@ CASES = {
     "rosen2": ("rosenbrock1", None, 2, 4096, 32, 0.5, 0, 150, 300),
     "rosen2_groups": ("rosenbrock1", None, 2, 4096, 12, 0.6, 8, 150, 200),
     "rosen4": ("rosenbrock1", None, 4, 2048, 8, 0.5, 0, 150, 200),
+    # remote mode 1 (sum-mixture proposal): the fp32 bounds on q(x)/q(x') against the all-fp64 evaluation
+    "dgauss_sum": ("dualgaussian", [5.0], 2, 8192, 64, 0.5, 0, 150, 300, 1),
+    "rosen2_sum256": ("rosenbrock1", None, 2, 4096, 256, 0.5, 0, 150, 300, 1),
+    "rosen2_sum_groups": ("rosenbrock1", None, 2, 4096, 12, 0.6, 8, 150, 200, 1),
+    "rosen4_sum": ("rosenbrock1", None, 4, 2048, 8, 0.5, 0, 150, 200, 1),
 }
 
 if __name__ == "__main__":

@@ -27,14 +27,17 @@ def main():
         return out
 
     cases = [("dualgaussian", [5.0], 2, 4096, 16, 0), ("rosenbrock1", None, 2, 2048, 8, 32), ("rosenbrock1", None, 16, 512, 8, 0)]
-    for (lik, par, d, Cg, M, cg), xchg in [(c, x) for x in ("nccl", "p2p") for c in cases]:
+    runs = [(c, x, 0, 0) for x in ("nccl", "p2p") for c in cases]
+    # remote mode 1 (sum-mixture proposal) with the pool read one exchange late (4 pool buffers), both exchanges
+    runs += [(c, "p2p", 1, 1) for c in cases] + [(cases[0], "nccl", 1, 1)]
+    for (lik, par, d, Cg, M, cg), xchg, rmode, lag in runs:
         N, nburn, nsamp, sync, pl = Cg * world, 130, 60, 10, 0.7
         check_even_pool(Shard(rank, world, Cg), M)
         pin = tiled_pinit(N, d)
         stream = torch.cuda.Stream(device=dev)
         torch.cuda.set_stream(stream)
         e = engine.Engine(d, Cg, mode="normal", nchain_total=N, chain0=rank * Cg, pool_m=M, pl=pl, sync=sync,
-                          coin_group=cg, history_steps=nsamp, device=local)
+                          coin_group=cg, history_steps=nsamp, device=local, remote_mode=rmode, pool_lag=lag)
         e.set_stream(stream.cuda_stream)
         e.set_likelihood(lik, par); e.set_covariance(None); e.set_state(pin[rank * Cg:(rank + 1) * Cg])
         r = ShardedRunner(e, DistGroup(dist), lambda ptr: torch.as_tensor(ptr, device=dev))
@@ -49,12 +52,14 @@ def main():
         gathered = [None] * world
         dist.all_gather_object(gathered, (mine, hist, fac))
         if rank == 0:
-            one = engine.Engine(d, N, mode="normal", pool_m=M, pl=pl, sync=sync, coin_group=cg, history_steps=nsamp, device=local)
+            one = engine.Engine(d, N, mode="normal", pool_m=M, pl=pl, sync=sync, coin_group=cg, history_steps=nsamp, device=local,
+                                remote_mode=rmode, pool_lag=lag)
             one.run(nsamp, nburn, pin, lik, par)
             same = (np.array_equal(np.concatenate([g[0] for g in gathered]), one.state()["p"])
                     and np.array_equal(np.concatenate([g[1] for g in gathered], axis=1), one.history())
                     and all(np.array_equal(g[2], one.factor()) for g in gathered))
-            print("dist_check", xchg, lik, "d=%d" % d, "world=%d" % world, "OK" if same else "MISMATCH", flush=True)
+            print("dist_check", xchg, lik, "d=%d" % d, "world=%d" % world, "remote_mode=%d lag=%d" % (rmode, lag),
+                  "OK" if same else "MISMATCH", flush=True)
             ok = ok and same
             one.close()
     dist.barrier()

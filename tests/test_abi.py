@@ -30,7 +30,7 @@ def test_config_struct_layout_matches_header(mcgpu_lib):
     from mcpar_b200 import engine
     # 4*int32, 3*int64, 2*int32, 5*double, uint64, 4*int32, int64, 2*int32
     assert C.sizeof(engine.Config) == 16 + 24 + 8 + 40 + 8 + 16 + 8 + 8
-    assert C.sizeof(engine.Stats) == 8 * 8 + 8 + 16
+    assert C.sizeof(engine.Stats) == 8 * 8 + 8 + 24
     hdr = open(os.path.join(ROOT, "include", "mcgpu.h")).read()
     assert "#define MCGPU_ABI_VERSION 2" in hdr and engine.Config().abi_version == 0
 

@@ -92,3 +92,82 @@ def test_accept_test_interval_contains_exp_delta():
         rel = np.abs(np.exp(delta) / e32.astype(np.float64) - 1.0)
         assert rel.max() < 1.0e-4, rel.max()
     assert rel.max() < 2.0e-5                      # the margin is five times what the model needs
+
+
+# ---------------------------------------------------------------- remote mode 1: sum-mixture proposal
+def _summix_model(rng, M, D, npts, mu_scale, sig_lo, sig_hi, far):
+    """summix_bounds (mh_kernels.cuh) in numpy float32 against the exact fp64 q(x)/q(x'); returns the true
+    ratio, the kernel's interval and which points the fast path decides."""
+    mu = rng.uniform(-mu_scale, mu_scale, (M, D))
+    mu[: M // 2] = mu[0] + rng.normal(0, 0.3, (M // 2, D))
+    sig = np.exp(rng.uniform(np.log(sig_lo), np.log(sig_hi), (M, D)))
+    g = np.sqrt(L2E / (2.0 * sig * sig))
+    nb = (-0.5 * np.log(sig * sig)).sum(1) * L2E
+    gmu32, g32, nb32 = f32(g * mu), f32(g), f32(nb)
+    mumax = np.nextafter(f32(np.abs(mu).max()), f32(np.inf))
+    isig = np.nextafter(f32((1.0 / sig).max()), f32(np.inf))
+    nbmax = np.nextafter(f32(np.abs(nb).max()), f32(np.inf))
+    c = rng.integers(0, M, npts)
+    xn = mu[c] + sig[c] * rng.standard_normal((npts, D))                       # x' ~ component c
+    co = rng.integers(0, M, npts)
+    xo = mu[co] + sig[co] * rng.standard_normal((npts, D)) * (4.0 if far else 1.2)   # the chain's state (far: in the tails)
+
+    def lse_true(x):
+        a = (-0.5 * np.log(sig * sig)).sum(1)[None] - 0.5 * (((x[:, None, :] - mu[None]) / sig[None]) ** 2).sum(-1)
+        m = a.max(1)
+        return m + np.log(np.exp(a - m[:, None]).sum(1))
+    true = np.exp(lse_true(xo) - lse_true(xn))
+
+    xof, xnf = f32(xo), f32(xn)
+    ref = nb32[c].copy()
+    for i in range(D):
+        y = (gmu32[c, i] - g32[c, i] * xnf[:, i]).astype(f32)
+        ref = (ref - y * y).astype(f32)
+
+    def ssum(xf, sgn):
+        acc = (nb32[None] - ref[:, None]).astype(f32)
+        for i in range(D):
+            y = (gmu32[None, :, i] - g32[None, :, i] * xf[:, None, i]).astype(f32)
+            acc = (acc - y * y).astype(f32)
+        ex = f32(np.exp2(acc.astype(np.float64)) * (1.0 + sgn * 2.4e-7))             # ex2.approx at the edge of its bound
+        ex[ex < f32(1.1754944e-38)] = 0                                                # ftz
+        part = [ex[:, q::4].sum(1, dtype=f32) for q in range(4)]                       # 4 partial sums + tree
+        return ((part[0] + part[1]).astype(f32) + (part[2] + part[3]).astype(f32)).astype(f32)
+    out = []
+    for sgn_o, sgn_n in ((1.0, -1.0), (-1.0, 1.0)):
+        so, sn = ssum(xof, sgn_o), ssum(xnf, sgn_n)
+        ok = (sn < 1e30) & (so < 1e30) & (sn > 0.5)
+        th_n = f32(1.6e-7) * (mumax + np.abs(xnf).max(1)) * isig
+        th_o = f32(1.6e-7) * (mumax + np.abs(xof).max(1)) * isig
+        lvl = nbmax - ref + f32(np.log2(M)) + f32(30.0)
+        En = np.maximum(lvl - np.log2(np.maximum(sn, f32(1e-37))), 30.0)
+        Eo = np.maximum(lvl - np.log2(np.maximum(so, f32(1e-37))), 30.0)
+        cu, cn = (4.0 + D) * 6.0e-8, 2.4e-7 * nbmax + 1.0e-5 + 1.0e-8 * M
+        eps_n = 0.75 * (2.0 * th_n * np.sqrt(D * En) + cu * En + D * th_n * th_n) + cn
+        eps_o = 0.75 * (2.0 * th_o * np.sqrt(D * Eo) + cu * Eo + D * th_o * th_o) + cn
+        ok &= (th_n < 1e-3) & (th_o < 1e-3) & (eps_n < 0.02) & (eps_o < 0.02)
+        lo = so * (1.0 - eps_o) / (sn * (1.0 + eps_n)) * (1.0 - 1.0e-6)
+        hi = (so * (1.0 + eps_o) + 2.0e-38 * M) / (sn * (1.0 - eps_n)) * (1.0 + 1.0e-6)
+        out.append((lo.astype(np.float64), hi.astype(np.float64), ok))
+    return true, out
+
+
+@pytest.mark.parametrize("M,D,mu_scale,sig_lo,sig_hi", [
+    (16, 2, 6.0, 0.5, 2.5),          # the benchmark's regime
+    (256, 2, 6.0, 0.5, 2.5),         # the blueprint's pool size (configs 4 and 5)
+    (16, 2, 6.0, 0.05, 3.0),         # widths spread over a factor 60: normalisations differ by 2^12
+    (64, 4, 5.0, 0.3, 2.0),
+    (16, 2, 300.0, 0.5, 2.0),        # far from the origin: roundings of mu and x dominate theta
+])
+@pytest.mark.parametrize("far", [False, True])
+def test_summix_interval_contains_the_true_hastings_factor(M, D, mu_scale, sig_lo, sig_hi, far):
+    rng = np.random.default_rng(77 + M + D)
+    true, runs = _summix_model(rng, M, D, 60000, mu_scale, sig_lo, sig_hi, far)
+    for lo, hi, ok in runs:
+        assert ok.mean() > 0.5, "the case must exercise the fast path"
+        inside = (true[ok] >= lo[ok]) & (true[ok] <= hi[ok])
+        assert inside.all(), "q(x)/q(x') outside the kernel's interval for %d points" % (~inside).sum()
+        width = (hi[ok] / np.maximum(lo[ok], 1e-300))
+        # and the interval is tight: ~3e-4 of the uniforms fall inside it in the benchmark's regime (narrow
+        # components or a far origin widen it through theta, still within 2 %)
+        assert np.median(width) < (1.0004 if (mu_scale == 6.0 and sig_lo == 0.5) else 1.02)

@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("case", ["dgauss", "rosen2", "rosen2_groups", "rosen4"])
+@pytest.mark.parametrize("case", ["dgauss", "rosen2", "rosen2_groups", "rosen4",
+                                  "dgauss_sum", "rosen2_sum256", "rosen2_sum_groups", "rosen4_sum"])
 def test_fp32_bounded_decisions_equal_fp64_decisions(case, tmp_path):
     outs = {}
     for mode in ("0", "1"):

@@ -50,7 +50,10 @@ def test_restart_continues_bit_for_bit(lik, par, d, N, M, cg, thin):
     assert np.array_equal(e.factor(), ref["fac"]) and np.array_equal(e.musig(), ref["pool"])
     nh = head.shape[0]
     assert np.array_equal(head, ref["hist"][:nh])
-    assert np.array_equal(e.history()[nh:], ref["hist"][nh:])
+    # the history is not part of the blob: after a load the device serves only the rows produced since
+    assert np.array_equal(e.history(first=nh), ref["hist"][nh:])
+    with pytest.raises(eng.McgpuError, match="no longer on the device"):
+        e.history(first=0, count=1)
     s = e.stats()
     assert (s["accepted"], s["tried"], s["remote_steps"], s["remote_iterations"]) == \
         (ref["st"]["accepted"], ref["st"]["tried"], ref["st"]["remote_steps"], ref["st"]["remote_iterations"])

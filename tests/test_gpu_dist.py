@@ -18,4 +18,4 @@ def test_sharded_nccl_and_p2p_equal_single_engine():
                         "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(ROOT, "tests", "dist_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("OK") == 6 and "MISMATCH" not in r.stdout
+    assert r.stdout.count("OK") == 10 and "MISMATCH" not in r.stdout

@@ -145,3 +145,53 @@ def test_counter_mode_pool_equal_all_chains_when_m_zero():
     N = 64
     o = mh.run_counter("rosenbrock1", 2, N, 40, 60, tiled_pinit(N, 2), pool_m=0, trace=True)
     assert o["pool"].shape == (N, 2, 2) and o["remote"][60 + 10:].any() and not o["remote"][:70].any()
+
+
+# ---------------------------------------------------------------- counter mode: remote mode 1, pool lag, Sobol
+def test_sobol_points_match_scipy():
+    """orc_sobol_points (Joe-Kuo direction numbers, gray-code order, 32-bit integers) against scipy's
+    unscrambled Sobol generator -- an independent implementation over the same public table."""
+    import ctypes as C
+    from scipy.stats import qmc
+    lib = mh.lib()
+    for d in (1, 2, 16, 17, 64):
+        n = 2048
+        out = np.empty(n * d)
+        assert lib.orc_sobol_points(d, C.c_uint64(0), C.c_size_t(n * d), out.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(out.reshape(n, d), qmc.Sobol(d, scramble=False, bits=32).random(n))
+    skip = np.empty(3 * 5)
+    lib.orc_sobol_points(5, C.c_uint64(7 * 5), C.c_size_t(15), skip.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(skip.reshape(3, 5), qmc.Sobol(5, scramble=False, bits=32).random(10)[7:])   # rank skip-ahead, mcutil.cc:22-23
+
+
+def test_sum_mixture_mode_leaves_the_target_invariant():
+    """Remote mode 1 (x' ~ uniform mixture of the pool's Gaussians, Hastings factor q(x)/q(x') with normalised
+    components) is an exact independence sampler: chains started from the DualGaussian target stay there --
+    mean and small-mode mass within 4.5 standard errors -- while the reference's max-mixture correction with
+    unnormalised Q_i (mode 0, mcpar.cc:367-439) visibly drifts at the same size."""
+    from scipy import stats
+    N, nsamp = 16384, 300
+    rng = np.random.default_rng(11)
+    comp = rng.random(N) < 1.0 / 6.0
+    pin = rng.standard_normal((N, 2)) + 5.0 * comp[:, None]
+    pright = (5.0 * stats.norm.sf(2.5) + stats.norm.cdf(2.5)) / 6.0
+    var = 1.0 + 25.0 * 5.0 / 36.0
+    se_m, se_p = np.sqrt(var / N), np.sqrt(pright * (1.0 - pright) / N)
+    for lag in (0, 1):
+        o = mh.run_counter("dualgaussian", 2, N, nsamp, 100, pin, par=[5.0], pool_m=16, pl=0.9, coin_group=0, thin=100,
+                           remote_mode=1, pool_lag=lag, trace=True)
+        h = o["rows"][-1]
+        assert abs(h[:, 0].mean() - 5.0 / 6.0) < 4.5 * se_m and abs((h[:, 0] > 2.5).mean() - pright) < 4.5 * se_p
+        rem = o["remote"][100:]
+        assert not rem[:10 * (1 + lag)].any() and rem[10 * (1 + lag):].any()     # remote steps start at t = sync (1 + lag)
+        assert o["remote_iters"][0] == rem.sum()                                   # one candidate per remote step
+        assert o["accept"][100:][rem].mean() > 0.5                                # and most of them are accepted
+    o0 = mh.run_counter("dualgaussian", 2, N, nsamp, 100, pin, par=[5.0], pool_m=16, pl=0.9, coin_group=0, thin=100)
+    assert abs((o0["rows"][-1][:, 0] > 2.5).mean() - pright) > 3.0 * se_p         # the reference algorithm's bias
+
+
+def test_pool_lag_changes_nothing_without_remote_steps():
+    pin = tiled_pinit(64, 2)
+    a = mh.run_counter("rosenbrock1", 2, 64, 40, 60, pin, pool_m=8, pl=1.0, coin_group=0)
+    b = mh.run_counter("rosenbrock1", 2, 64, 40, 60, pin, pool_m=8, pl=1.0, coin_group=0, pool_lag=1, remote_mode=1)
+    assert np.array_equal(a["rows"], b["rows"]) and np.array_equal(a["pool"], b["pool"])
