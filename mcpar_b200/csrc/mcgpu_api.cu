@@ -222,6 +222,8 @@ cudaError_t launch_steps_any(mcgpu_engine *e, int phase, const StepParams &p)
     w.xstat = p.xstat;
     w.hist = p.hist; w.thin = p.thin; w.hist_cap = p.hist_cap; w.hist_ring0 = p.hist_ring0;
     w.pnb = e->pprep + (size_t)3 * e->d * e->mpad; w.summix = e->remote_mode;
+    w.pf = reinterpret_cast<const float2*>(e->pprep + ((size_t)3 * e->d + 1) * e->mpad);        // fp32 copy behind the fp64 arrays
+    w.pnbf = reinterpret_cast<const float*>(w.pf + (size_t)e->d * e->mpad); w.pscal = w.pnbf + e->mpad;
     w.gm2 = reinterpret_cast<const double2*>(e->gm_t);
     w.gm_lw = e->gm_t ? e->gm_t + (size_t)2 * e->d * e->kpad : nullptr; w.kpad = e->kpad;
     return fast::launch_wide(e->lik, e->d, phase == PH_REMOTE && e->remote_mode == 1 ? PH_REMOTE_SUM : phase, w, e->stream);
@@ -626,17 +628,23 @@ int mcgpu_set_likelihood(mcgpu_engine *e, int lik, const double *par, int npar)
     const int d = e->d, L = d / 2;
     if (!e->factor_cm) { CK(cudaMalloc((void**)&e->factor_cm, (size_t)d * d * 8)); CK(cudaMalloc((void**)&e->diag_d, sizeof(int))); }
     e->mpad = (e->M + L - 1) / L * L;
-    if (!e->pprep) CK(cudaMalloc((void**)&e->pprep, ((size_t)3 * d + 1) * e->mpad * 8));   // (mu, h) pairs, sigma, n_s
+    // (mu, h) pairs, sigma, n_s in fp64; then the fp32 copy: (g mu, g) pairs, n_s log2 e, 4 scalars
+    if (!e->pprep) CK(cudaMalloc((void**)&e->pprep, ((size_t)3 * d + 1) * e->mpad * 8 + ((size_t)2 * d + 1) * e->mpad * 4 + 16));
     if (e->gm_t) { cudaFree(e->gm_t); e->gm_t = nullptr; }
     if (lik == MCGPU_GAUSSMIX) {                        // [d][Kpad] (mu, 1/s2) pairs, then [Kpad] log w; padding has weight 0
       e->kpad = (K + 2 * L - 1) / (2 * L) * (2 * L);
       std::vector<double> t((size_t)2 * d * e->kpad + e->kpad, 0.0);
+      // exponent of component k expanded: c_k + sum_i x_i (a_ki x_i + b_ki), a = -1/(2 s2), b = mu/s2,
+      // c = log w - 1/2 sum_i mu^2/s2 (two DFMA per component, parameter and chain in wide_loglik)
       for (int k = 0; k < e->kpad; ++k) {
+        long double cacc = 0.0L;
         for (int i = 0; i < d; ++i) {
-          t[((size_t)i * e->kpad + k) * 2] = k < K ? dev[(size_t)k * d + i] : 0.0;
-          t[((size_t)i * e->kpad + k) * 2 + 1] = k < K ? dev[(size_t)K * d + (size_t)k * d + i] : 0.0;
+          const double mu = k < K ? dev[(size_t)k * d + i] : 0.0, is2 = k < K ? dev[(size_t)K * d + (size_t)k * d + i] : 0.0;
+          t[((size_t)i * e->kpad + k) * 2] = -0.5 * is2;
+          t[((size_t)i * e->kpad + k) * 2 + 1] = mu * is2;
+          cacc += (long double)mu * mu * is2;
         }
-        t[(size_t)2 * d * e->kpad + k] = k < K ? dev[(size_t)2 * K * d + k] : -INFINITY;
+        t[(size_t)2 * d * e->kpad + k] = k < K ? (double)((long double)dev[(size_t)2 * K * d + k] - 0.5L * cacc) : -INFINITY;
       }
       CK(cudaMalloc((void**)&e->gm_t, t.size() * 8));
       CK(cudaMemcpyAsync(e->gm_t, t.data(), t.size() * 8, cudaMemcpyHostToDevice, e->stream));
@@ -908,6 +916,9 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
           prepped = true; ++e->launches;
           return fast::launch_pool_prep(pool_cur(e), e->M, e->mpad, e->d, reinterpret_cast<double2*>(e->pprep),
                                         e->pprep + (size_t)2 * e->d * e->mpad, e->pprep + (size_t)3 * e->d * e->mpad,
+                                        reinterpret_cast<float2*>(e->pprep + ((size_t)3 * e->d + 1) * e->mpad),
+                                        reinterpret_cast<float*>(e->pprep + ((size_t)3 * e->d + 1) * e->mpad) + (size_t)2 * e->d * e->mpad,
+                                        reinterpret_cast<float*>(e->pprep + ((size_t)3 * e->d + 1) * e->mpad) + ((size_t)2 * e->d + 1) * e->mpad,
                                         p.arrivals, p.wait_target, p.xflag, p.xstat, e->stream);
         };
         auto is_remote = [&](long long tt) {

@@ -55,10 +55,12 @@ cudaError_t launch_wide(int lik, int d, int phase, const WideParams &p, cudaStre
 }
 
 cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd, double *pnb,
+                             float2 *pf, float *pnbf, float *pscal,
                              const unsigned long long *arrivals, unsigned long long wait_target, int *xflag,
                              unsigned long long *xstat, cudaStream_t st)
 {
-  pool_prep_kernel<<<(D * mpad + 127) / 128, 128, 0, st>>>(pool, M, mpad, D, pmh, psd, pnb, arrivals, wait_target, xflag, xstat);
+  cudaMemsetAsync(pscal, 0, 4 * sizeof(float), st);
+  pool_prep_kernel<<<(D * mpad + 127) / 128, 128, 0, st>>>(pool, M, mpad, D, pmh, psd, pnb, pf, pnbf, pscal, arrivals, wait_target, xflag, xstat);
   return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@ namespace fast {
 bool wide_supported(int lik, int d);
 cudaError_t launch_wide(int lik, int d, int phase, const WideParams &p, cudaStream_t st);
 cudaError_t launch_pool_prep(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd, double *pnb,
+                             float2 *pf, float *pnbf, float *pscal,
                              const unsigned long long *arrivals, unsigned long long wait_target, int *xflag,
                              unsigned long long *xstat, cudaStream_t st);
 cudaError_t launch_factor_prep(const double *rm, double *cm, int D, int *diag, cudaStream_t st);

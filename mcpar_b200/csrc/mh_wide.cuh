@@ -49,6 +49,30 @@ __device__ __forceinline__ float group_sumf(float v)
   return v;
 }
 
+template <int L>
+__device__ __forceinline__ float group_maxf(float v)
+{
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// the same for fp32 staging (remote mode 1: the pool test runs in fp32)
+template <int NCH>
+__device__ __forceinline__ void load_staged_f(const float *s, float (&v)[NCH])
+{
+  if (NCH % 4 == 0) {
+#pragma unroll
+    for (int c = 0; c < NCH; c += 4) { const float4 t = *reinterpret_cast<const float4 *>(s + c); v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w; }
+  } else if (NCH % 2 == 0) {
+#pragma unroll
+    for (int c = 0; c < NCH; c += 2) { const float2 t = *reinterpret_cast<const float2 *>(s + c); v[c] = t.x; v[c + 1] = t.y; }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) v[c] = s[c];
+  }
+}
+
 // the NCH staged values of one parameter (16-byte aligned when NCH is even): LDS.128 where possible
 template <int NCH>
 __device__ __forceinline__ void load_staged(const double *s, double (&v)[NCH])
@@ -78,8 +102,12 @@ __device__ __forceinline__ void wide_loglik(const double (&x0)[NCH], const doubl
     }
   } else {
     // GaussMix: lane r evaluates components r, r+L, ... two at a time (kpad is a multiple of 2L;
-    // padding components carry log w = -inf).  One pointer walks a component's (mu, 1/s2) pairs
-    // down the parameters; the partner component sits L pairs further.
+    // padding components carry c = -inf).  The exponent is expanded once on the host,
+    //     log w_k - 1/2 sum_i (x_i - mu_ki)^2 / s2_ki = c_k + sum_i x_i (a_ki x_i + b_ki),
+    //     a = -1/(2 s2), b = mu / s2, c = log w - 1/2 sum_i mu^2 / s2,
+    // so a (component, parameter, chain) costs two DFMA instead of DADD + DMUL + DFMA (the terms reach
+    // ~50 per parameter against a sum of ~ -d/2: ~1e-13 absolute on the log-likelihood at d = 64).  One pointer
+    // walks a component's (a, b) pairs down the parameters; the partner component sits L pairs further.
     double m[NCH], s[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) { m[c] = -INFINITY; s[c] = 0.0; }
@@ -96,14 +124,14 @@ __device__ __forceinline__ void wide_loglik(const double (&x0)[NCH], const doubl
         load_staged<NCH>(sx + i * NCH, xi);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const double d0 = xi[c] - a.x, d1 = xi[c] - b.x;
-          q0[c] += d0 * d0 * a.y; q1[c] += d1 * d1 * b.y;
+          q0[c] = fma(fma(a.x, xi[c], a.y), xi[c], q0[c]);
+          q1[c] = fma(fma(b.x, xi[c], b.y), xi[c], q1[c]);
         }
       }
       const double lw0 = __ldg(p.gm_lw + k), lw1 = __ldg(p.gm_lw + k + L);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        const double a0 = lw0 - 0.5 * q0[c], a1 = lw1 - 0.5 * q1[c];
+        const double a0 = lw0 + q0[c], a1 = lw1 + q1[c];
         if (a0 > m[c]) { s[c] = s[c] * mc_exp(m[c] - a0, T) + 1.0; m[c] = a0; } else if (a0 > -INFINITY) s[c] += mc_exp(a0 - m[c], T);
         if (a1 > m[c]) { s[c] = s[c] * mc_exp(m[c] - a1, T) + 1.0; m[c] = a1; } else if (a1 > -INFINITY) s[c] += mc_exp(a1 - m[c], T);
       }
@@ -157,6 +185,71 @@ __device__ __forceinline__ void wide_pool_eval(const double *sx, int r, const Wi
   for (int c = 0; c < NCH; ++c) {
     amax[c] = group_max<L>(m[c]);
     S[c] = group_sumf<L>(m[c] == -INFINITY ? 0.0f : sl[c] * ex2_approx((float)(m[c] - amax[c]) * L2E));   // a lane that saw no live slot adds 0
+  }
+}
+
+// Remote mode 1, fast path: bounds on q(x)/q(x') for the group's NCH chains from an fp32 evaluation of both
+// mixtures in ONE pass over the pool (summix_bounds of mh_kernels.cuh, spread over the group's lanes: lane r
+// takes pool slots r, r+L, ...; same error analysis with D parameters per term).  sf holds the fp32 points,
+// [0][D][NCH] = x', [1][D][NCH] = x.  The fp32 copy of the pool (8 bytes per slot and parameter: 131 KB at
+// M = 256, d = 64) stays in L1, where the fp64 pairs (262 KB) streamed from L2 for every group.
+template <int D, int NCH>
+__device__ __forceinline__ void wide_summix_bounds(const float *sf, int r, const int (&cpick)[NCH], const WideParams &p,
+                                                   float (&cf_lo)[NCH], float (&cf_hi)[NCH], bool (&ok)[NCH])
+{
+  constexpr int L = D / 2;
+  const int i0 = 2 * r;
+  const float *sn = sf, *so = sf + D * NCH;
+  float ref[NCH], xabs_n[NCH], xabs_o[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {                    // level of both sums: the picked component's exponent at x'
+    const float2 f0 = __ldg(p.pf + (size_t)i0 * p.mpad + cpick[c]), f1 = __ldg(p.pf + (size_t)(i0 + 1) * p.mpad + cpick[c]);
+    const float xn0 = sn[i0 * NCH + c], xn1 = sn[(i0 + 1) * NCH + c], xo0 = so[i0 * NCH + c], xo1 = so[(i0 + 1) * NCH + c];
+    const float y0 = fmaf(-f0.y, xn0, f0.x), y1 = fmaf(-f1.y, xn1, f1.x);
+    ref[c] = __ldg(p.pnbf + cpick[c]) - group_sumf<L>(fmaf(y0, y0, y1 * y1));
+    xabs_n[c] = group_maxf<L>(fmaxf(fabsf(xn0), fabsf(xn1)));
+    xabs_o[c] = group_maxf<L>(fmaxf(fabsf(xo0), fabsf(xo1)));
+  }
+  float Sn[NCH], So[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) { Sn[c] = 0.0f; So[c] = 0.0f; }
+  for (int s = r; s < p.mpad; s += L) {
+    const float nb = __ldg(p.pnbf + s);
+    float an[NCH], ao[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { an[c] = nb - ref[c]; ao[c] = an[c]; }
+    const float2 *g = p.pf + s;
+#pragma unroll 4
+    for (int i = 0; i < D; ++i) {
+      const float2 f = __ldg(g);
+      g += p.mpad;
+      float xn[NCH], xo[NCH];
+      load_staged_f<NCH>(sn + i * NCH, xn);
+      load_staged_f<NCH>(so + i * NCH, xo);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const float yn = fmaf(-f.y, xn[c], f.x), yo = fmaf(-f.y, xo[c], f.x);
+        an[c] = fmaf(-yn, yn, an[c]); ao[c] = fmaf(-yo, yo, ao[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { Sn[c] += ex2_approx(an[c]); So[c] += ex2_approx(ao[c]); }
+  }
+  const float mumax = __ldg(p.pscal), isig = __ldg(p.pscal + 1), nbmax = __ldg(p.pscal + 2);
+  const float l2m = lg2_approx((float)p.pool_m), cD = (float)D, cu = (4.0f + cD) * 6.0e-8f;
+  const float cn = 2.4e-7f * nbmax + 1.0e-5f + 1.0e-8f * (float)p.pool_m;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float sn_ = group_sumf<L>(Sn[c]), so_ = group_sumf<L>(So[c]);
+    ok[c] = (sn_ < 1.0e30f) && (so_ < 1.0e30f) && (sn_ > 0.5f);
+    const float th_n = 1.6e-7f * (mumax + xabs_n[c]) * isig, th_o = 1.6e-7f * (mumax + xabs_o[c]) * isig;
+    const float lvl = nbmax - ref[c] + l2m + 30.0f;
+    const float En = fmaxf(lvl - lg2_approx(sn_), 30.0f), Eo = fmaxf(lvl - lg2_approx(fmaxf(so_, 1.0e-37f)), 30.0f);
+    const float eps_n = 0.75f * (2.0f * th_n * sqrtf(cD * En) + cu * En + cD * th_n * th_n) + cn;
+    const float eps_o = 0.75f * (2.0f * th_o * sqrtf(cD * Eo) + cu * Eo + cD * th_o * th_o) + cn;
+    ok[c] = ok[c] && th_n < 1.0e-3f && th_o < 1.0e-3f && eps_n < 0.02f && eps_o < 0.02f;
+    cf_lo[c] = __fdividef(so_ * (1.0f - eps_o), sn_ * (1.0f + eps_n)) * (1.0f - 1.0e-6f);
+    cf_hi[c] = __fdividef(fmaf(so_, 1.0f + eps_o, 2.0e-38f * (float)p.pool_m), sn_ * (1.0f - eps_n)) * (1.0f + 1.0e-6f);
   }
 }
 
@@ -255,7 +348,7 @@ mh_wide_kernel(const WideParams p)
     const int t = p.t0 + k;
     double u_acc[NCH], xt0[NCH], xt1[NCH], cfac[NCH];
     int cpick[NCH];
-    double lcf_m[NCH]; float so_[NCH], sn_[NCH];    // remote mode 1: log q(x) - log q(x') = lcf_m + log(so / sn)
+    float cf_lo[NCH], cf_hi[NCH]; bool cf_ok[NCH];  // remote mode 1: fp32 bounds on q(x)/q(x')
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const Words wacc = philox4x32_10_rk(glo[c], ghi[c], step, (uint32_t)ABLK, p.rk);
@@ -305,19 +398,18 @@ mh_wide_kernel(const WideParams p)
         normal_pair_t((qq & 1) ? b.w2 : b.w0, (qq & 1) ? b.w3 : b.w1, za, zb, T);
         xt0[c] = __ldg(p.pmh + (size_t)i0 * p.mpad + cpick[c]).x + __ldg(p.psd + (size_t)i0 * p.mpad + cpick[c]) * za;
         xt1[c] = __ldg(p.pmh + (size_t)(i0 + 1) * p.mpad + cpick[c]).x + __ldg(p.psd + (size_t)(i0 + 1) * p.mpad + cpick[c]) * zb;
-        sx[i0 * NCH + c] = xt0[c]; sx[(i0 + 1) * NCH + c] = xt1[c];
+      }
+      // both points in fp32 in the normals' staging area (unused in a remote step): [0] = x', [1] = x
+      float *sf = reinterpret_cast<float *>(sz);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        sf[i0 * NCH + c] = (float)xt0[c]; sf[(i0 + 1) * NCH + c] = (float)xt1[c];
+        sf[D * NCH + i0 * NCH + c] = (float)x0[c]; sf[D * NCH + (i0 + 1) * NCH + c] = (float)x1[c];
+        nit += live[c] ? 1u : 0u;
       }
       __syncwarp();
-      double am_n[NCH], am_o[NCH];
-      wide_pool_eval<D, NCH, true>(sx, r, p, am_n, sn_);
+      wide_summix_bounds<D, NCH>(sf, r, cpick, p, cf_lo, cf_hi, cf_ok);
       __syncwarp();
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) { sx[i0 * NCH + c] = x0[c]; sx[(i0 + 1) * NCH + c] = x1[c]; }
-      __syncwarp();
-      wide_pool_eval<D, NCH, true>(sx, r, p, am_o, so_);
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) { lcf_m[c] = am_o[c] - am_n[c]; nit += live[c] ? 1u : 0u; }
     } else {
       // genRemote: the group's chains run the reference's rejection loop in step: candidate
       // iteration `it` of every chain is evaluated together (lane r tests pool slots r, r+L, ...
@@ -405,16 +497,11 @@ mh_wide_kernel(const WideParams p)
     const double pwgt = (double)(t + 1), winv = 1.0 / pwgt;
     int dec[NCH];
     if (SUMMIX) {
-      // u < exp(lyt - ly + log q(x) - log q(x')): the fp64 maxima go into the exponent, the fp32 sums (each
-      // right to eps: float conversion of the exponents, ex2.approx, <= M/L rescales) bound the rest
-      const float eps = 1.0e-4f + 1.0e-6f * (float)p.pool_m;
+      // u < exp(lyt - ly) q(x)/q(x') from the fp32 bounds on the Hastings factor wherever they settle it
       bool alldec = true;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        dec[c] = -1;
-        if (sn_[c] > 0.5f && sn_[c] < 1.0e30f && so_[c] > 0.5f && so_[c] < 1.0e30f)      // each sum holds its maximum's term: >= 1
-          dec[c] = accept_test_bounded(u_acc[c], (lyt[c] - ly[c]) + lcf_m[c], __fdividef(so_[c] * (1.0f - eps), sn_[c] * (1.0f + eps)) * (1.0f - 1.0e-6f),
-                                       __fdividef(so_[c] * (1.0f + eps), sn_[c] * (1.0f - eps)) * (1.0f + 1.0e-6f));
+        dec[c] = cf_ok[c] ? accept_test_bounded(u_acc[c], lyt[c] - ly[c], cf_lo[c], cf_hi[c]) : -1;
         alldec = alldec && dec[c] >= 0;
       }
       if (!__all_sync(0xffffffffu, alldec)) {          // rare: exact log q(x) - log q(x'), warp-wide
@@ -514,6 +601,7 @@ mh_wide_kernel(const WideParams p)
 
 // pool [M][D][2] (mu, sigma^2) -> pmh [D][Mpad] (mu, -1/(2 sigma^2)), psd [D][Mpad] sigma; padding slots get Q = 0
 static __global__ void pool_prep_kernel(const double *pool, int M, int mpad, int D, double2 *pmh, double *psd, double *pnb,
+                                        float2 *pf, float *pnbf, float *pscal,
                                         const unsigned long long *arrivals, unsigned long long wait_target, int *xflag,
                                         unsigned long long *xstat)
 {
@@ -522,14 +610,20 @@ static __global__ void pool_prep_kernel(const double *pool, int M, int mpad, int
   if (idx < mpad) {                                   // n_s = -1/2 sum_i log sig2_si (remote mode 1); padding 0
     double n = 0.0;
     if (idx < M) for (int i = 0; i < D; ++i) n -= 0.5 * log(pool[((size_t)idx * D + i) * 2 + 1]);
-    pnb[idx] = n;
+    pnb[idx] = n; pnbf[idx] = (float)(n * 1.4426950408889634);
+    atomicMax(reinterpret_cast<int *>(pscal + 2), __float_as_int(__double2float_ru(fabs(n * 1.4426950408889634))));
   }
   if (idx >= D * mpad) return;
   const int i = idx / mpad, s = idx % mpad;
   if (s < M) {
-    const double s2 = pool[((size_t)s * D + i) * 2 + 1];
-    pmh[idx] = make_double2(pool[((size_t)s * D + i) * 2], -0.5 / s2); psd[idx] = sqrt(s2);
-  } else { pmh[idx] = make_double2(1.0e300, -1.0); psd[idx] = 0.0; }
+    const double m = pool[((size_t)s * D + i) * 2], s2 = pool[((size_t)s * D + i) * 2 + 1];
+    const double sd = sqrt(s2), g = sqrt(0.5 * 1.4426950408889634 / s2);     // g = sqrt(log2(e) / (2 sig^2)), as stage_pool
+    pmh[idx] = make_double2(m, -0.5 / s2); psd[idx] = sd;
+    pf[idx] = make_float2((float)(g * m), (float)g);
+    // pool-wide max |mu| and max 1/sigma for the fp32 error bound (non-negative floats order like their bit patterns)
+    atomicMax(reinterpret_cast<int *>(pscal), __float_as_int(__double2float_ru(fabs(m))));
+    atomicMax(reinterpret_cast<int *>(pscal + 1), __float_as_int(__double2float_ru(1.0 / sd)));
+  } else { pmh[idx] = make_double2(1.0e300, -1.0); psd[idx] = 0.0; pf[idx] = make_float2(1.0e18f, 0.0f); }
 }
 
 // row-major lower factor -> column-major copy + "is diagonal" flag
