@@ -49,7 +49,9 @@ enum {
   MCGPU_ROSENBROCK2 = 1,    /* rosenbrock.cc:25-41,  par: none (verify mode + eval) */
   MCGPU_GAUSSIAN = 2,       /* rosenbrock.cc:44-61,  par: mu[2], sig2[2] (optional) */
   MCGPU_DUALGAUSSIAN = 3,   /* rosenbrock.cc:63-78,  par: w (optional, default 5)   */
-  MCGPU_GAUSSMIX = 4        /* new: par = K, mu[K][d], sig2[K][d], w[K]             */
+  MCGPU_GAUSSMIX = 4,       /* new: par = K, mu[K][d], sig2[K][d], w[K]             */
+  MCGPU_HOST_LIKELIHOOD = 100 /* the likelihood is a host callback (a user-written VLFunc, src/vlfunc.hh:9-12):
+                               the engine steps with mcgpu_step_propose / mcgpu_step_accept      */
 };
 
 enum {
@@ -168,6 +170,21 @@ int  mcgpu_sample_group(mcgpu_engine *const *engines, int world, int nsteps);
 int  mcgpu_exchange_begin(mcgpu_engine *e, void **dev_buffer, size_t *total_bytes,
                           size_t *own_offset, size_t *own_bytes);
 int  mcgpu_exchange_end(mcgpu_engine *e);
+
+/* Host-callback likelihood (what a user-written VLFunc such as the R-backed RFunc of
+ * src/rfunc.cc:48-67 needs).  After mcgpu_set_likelihood(e, MCGPU_HOST_LIKELIHOOD, NULL, 0) the step is split
+ * around the plugin call, exactly where MCPar::run makes it (src/mcpar.cc:59-60, :151-160):
+ *   mcgpu_set_state_host   pinit AND the caller's L(nchain, pinit, lylast) (mcpar.cc:47-53)
+ *   mcgpu_step_propose     one step's trial points -- genLocal / genRemote with the normal mode's counter-based
+ *                          draws -- copied to the host, ptrial [nchain][nparam]
+ *   (the caller evaluates its VLFunc: L(nchain, ptrial, lytrial))
+ *   mcgpu_step_accept      lytrial [nchain] in; accept test, state update, running moments, sample store,
+ *                          pool publication; burn-in tuning at its boundaries
+ * nburn burn-in steps come first, then mcgpu_sample_begin and nsamp main steps.  One engine hosting every chain
+ * (no sharding); any nparam <= 64; both remote modes.  mcgpu_burnin / mcgpu_sample refuse such an engine. */
+int  mcgpu_set_state_host(mcgpu_engine *e, const double *pinit, const double *lylast);
+int  mcgpu_step_propose(mcgpu_engine *e, double *ptrial);
+int  mcgpu_step_accept(mcgpu_engine *e, const double *lytrial);
 
 /* Peer-to-peer exchange between sharded engines (replaces MPI_Allgather(MPI_IN_PLACE),
  * src/mcpar.cc:127-140, without a collective call): after attaching, the window

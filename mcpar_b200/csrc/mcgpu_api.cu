@@ -56,6 +56,8 @@ struct mcgpu_engine {
   int *overrun = nullptr;
   double *Zd = nullptr, *Ud = nullptr; int *Id = nullptr; long long nz = 0, nu = 0, ni = 0;
 
+  // host-callback likelihood (MCGPU_HOST_LIKELIHOOD): AoS state, one step per propose / accept pair
+  bool hostlik = false, proposed = false; double *aux = nullptr, *lytrial_d = nullptr; int *flags_d = nullptr;   // (ptrial: below)
   // wide kernels (d >= 8, job-wide coin): AoS state, column-major factor, prepared pool, transposed GaussMix
   bool wide = false;
   double *factor_cm = nullptr; int *diag_d = nullptr;
@@ -577,7 +579,8 @@ int mcgpu_destroy(mcgpu_engine *e)
   void *ptrs[] = {e->x, e->ly, e->mu, e->ps, e->factor, e->counts, e->xchg, e->xflag_d, e->peers_d, e->hist, e->overrun,
                   e->Zd, e->Ud, e->Id, e->ptrial, e->sig, e->mutrial, e->sigtrial, e->musig, e->snap[0], e->snap[1],
                   e->soff, e->cursors, e->irate_d, e->rstats, e->tr_accept, e->tr_remote, e->tr_trial_ly,
-                  e->tr_trial_p, e->tr_cfac, e->tr_iters, e->lik_dev, e->factor_cm, e->diag_d, e->pprep, e->gm_t, e->hist_f32};
+                  e->tr_trial_p, e->tr_cfac, e->tr_iters, e->lik_dev, e->factor_cm, e->diag_d, e->pprep, e->gm_t, e->hist_f32,
+                  e->aux, e->lytrial_d, e->flags_d};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (void *q : e->peer_opened) cudaIpcCloseMemHandle(q);
   for (int i = 0; i < 2; ++i) { if (e->pin[i]) cudaFreeHost(e->pin[i]); if (e->pin_ev[i]) cudaEventDestroy(e->pin_ev[i]); }
@@ -605,6 +608,17 @@ int mcgpu_set_likelihood(mcgpu_engine *e, int lik, const double *par, int npar)
 {
   if (!e) return MCGPU_EINVAL;
   DeviceGuard g(e->dev);
+  if (lik == MCGPU_HOST_LIKELIHOOD) {                     // the likelihood stays with the caller: mcgpu_step_propose / accept
+    if (e->cfg.mode != MCGPU_MODE_NORMAL || e->sharded) return fail(e, MCGPU_EINVAL, "a host likelihood needs one NORMAL-mode engine hosting every chain");
+    if (e->have_state && !e->hostlik) return fail(e, MCGPU_ESTATE, "likelihood change would change the state layout: create a new engine");
+    if (!e->ptrial) {
+      CK(cudaMalloc((void**)&e->ptrial, (size_t)e->C * e->d * 8)); CK(cudaMalloc((void**)&e->aux, (size_t)e->C * 8));
+      CK(cudaMalloc((void**)&e->lytrial_d, (size_t)e->C * 8)); CK(cudaMalloc((void**)&e->flags_d, (size_t)e->C * sizeof(int)));
+    }
+    e->hostlik = true; e->wide = false; e->lik = lik; e->lik_k = 0;
+    return MCGPU_OK;
+  }
+  if (e->hostlik) return fail(e, MCGPU_ESTATE, "this engine was set up for a host likelihood: create a new engine");
   std::vector<double> dev; int K = 0; std::string err;
   int rc = prepare_lik(lik, e->d, par, npar, e->lp, dev, K, err);
   if (rc) { e->err = err; return rc; }
@@ -684,6 +698,7 @@ int mcgpu_set_state(mcgpu_engine *e, const double *pinit)
 {
   if (!e || !pinit) return MCGPU_EINVAL;
   if (e->lik < 0) return fail(e, MCGPU_ESTATE, "set_likelihood first");
+  if (e->hostlik) return fail(e, MCGPU_ESTATE, "host likelihood: the initial log-likelihoods come from the caller (mcgpu_set_state_host)");
   DeviceGuard g(e->dev);
   const int d = e->d;
   if (e->verify) {
@@ -725,9 +740,10 @@ int mcgpu_set_streams(mcgpu_engine *e, int local_rank, const double *Z, size_t n
   return MCGPU_OK;
 }
 
-static int ready_to_step(mcgpu_engine *e)
+static int ready_to_step(mcgpu_engine *e, bool hostlik_ok = false)
 {
   if (!e->have_state) return fail(e, MCGPU_ESTATE, "set_state first");
+  if (e->hostlik && !hostlik_ok) return fail(e, MCGPU_ESTATE, "host likelihood: step with mcgpu_step_propose / mcgpu_step_accept");
   if (!e->have_factor) { int rc = mcgpu_set_covariance(e, nullptr); if (rc) return rc; }
   if (e->wide) { ++e->launches; CK(fast::launch_factor_prep(e->factor, e->factor_cm, e->d, e->diag_d, e->stream)); }
   if (e->verify || e->replay_local) { int rc = upload_streams(e); if (rc) return rc; }
@@ -808,7 +824,8 @@ int mcgpu_sample_begin(mcgpu_engine *e, int nsamp)
 {
   if (!e || nsamp < 0) return MCGPU_EINVAL;
   DeviceGuard g(e->dev);
-  int rc = ready_to_step(e); if (rc) return rc;
+  int rc = ready_to_step(e, true); if (rc) return rc;
+  if (e->proposed) return fail(e, MCGPU_ESTATE, "a proposal is pending: call mcgpu_step_accept");
   const int d = e->d;
   CK(cudaStreamSynchronize(e->side));
   e->nsamp = nsamp; e->t_main = 0; e->sampling = true; e->exchange_pending = false; e->hist_kept = 0; e->sink_sent = 0;
@@ -875,6 +892,7 @@ int mcgpu_sample(mcgpu_engine *e, int nsteps)
 {
   if (!e || nsteps < 0) return MCGPU_EINVAL;
   if (!e->sampling) return fail(e, MCGPU_ESTATE, "sample_begin first");
+  if (e->hostlik) return fail(e, MCGPU_ESTATE, "host likelihood: step with mcgpu_step_propose / mcgpu_step_accept");
   if (e->t_main + nsteps > e->nsamp) return fail(e, MCGPU_EINVAL, "more steps than sample_begin announced");
   DeviceGuard g(e->dev);
   const int sync = e->cfg.sync;
@@ -1136,6 +1154,87 @@ int mcgpu_burnin_group(mcgpu_engine *const *engines, int world, int nburn)
   return MCGPU_OK;
 }
 
+// ---- host-callback likelihood: one step = propose (device) -> VLFunc (host) -> accept (device) ------------
+int mcgpu_set_state_host(mcgpu_engine *e, const double *pinit, const double *lylast)
+{
+  if (!e || !pinit || !lylast) return MCGPU_EINVAL;
+  if (!e->hostlik) return fail(e, MCGPU_ESTATE, "mcgpu_set_likelihood(e, MCGPU_HOST_LIKELIHOOD, NULL, 0) first");
+  DeviceGuard g(e->dev);
+  CK(cudaMemcpyAsync(e->x, pinit, (size_t)e->C * e->d * 8, cudaMemcpyHostToDevice, e->stream));     // chain-major, as given
+  CK(cudaMemcpyAsync(e->ly, lylast, (size_t)e->C * 8, cudaMemcpyHostToDevice, e->stream));          // L(nchain, pvals, lylast), mcpar.cc:53
+  e->proposed = false;
+  return state_installed(e);
+}
+
+static void fill_hostlik(mcgpu_engine *e, HostLikParams &p)
+{
+  memset(&p, 0, sizeof p);
+  p.x = e->x; p.ly = e->ly; p.mu = e->mu; p.ps = e->ps; p.ptrial = e->ptrial; p.aux = e->aux; p.flags = e->flags_d;
+  p.lytrial = e->lytrial_d; p.C = e->C; p.chain0 = e->cfg.chain0; p.d = e->d; p.factor = e->factor;
+  p.counts = e->counts; p.mcounts = e->counts + 4;
+  p.key0 = (uint32_t)e->cfg.seed; p.key1 = (uint32_t)(e->cfg.seed >> 32);
+  p.main_phase = e->sampling ? 1 : 0;
+  p.step = (uint32_t)(e->sampling ? e->nburn_total + e->t_main : e->burn_done);
+  p.t = (int)e->t_main; p.first_remote_t = e->cfg.sync * (1 + e->lag); p.coin_group = e->cfg.coin_group; p.pl = e->cfg.pl;
+  p.pool = pool_cur(e); p.pool_next = pool_next(e); p.pool_m = e->M; p.pool_stride = e->stride; p.remote_mode = e->remote_mode;
+  p.hist = e->hist; p.hist_row = -1;
+}
+
+int mcgpu_step_propose(mcgpu_engine *e, double *ptrial)
+{
+  if (!e || !ptrial) return MCGPU_EINVAL;
+  if (!e->hostlik) return fail(e, MCGPU_ESTATE, "not a host-likelihood engine");
+  if (e->proposed) return fail(e, MCGPU_ESTATE, "a proposal is pending: call mcgpu_step_accept");
+  if (e->sampling && e->t_main >= e->nsamp) return fail(e, MCGPU_EINVAL, "more steps than sample_begin announced");
+  DeviceGuard g(e->dev);
+  int rc = ready_to_step(e, true);
+  if (rc) return rc;
+  HostLikParams p; fill_hostlik(e, p);
+  ++e->launches;
+  CK(exact::launch_hostlik_propose(p, e->stream));
+  CK(cudaMemcpyAsync(ptrial, e->ptrial, (size_t)e->C * e->d * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->proposed = true;
+  return MCGPU_OK;
+}
+
+int mcgpu_step_accept(mcgpu_engine *e, const double *lytrial)
+{
+  if (!e || !lytrial) return MCGPU_EINVAL;
+  if (!e->hostlik || !e->proposed) return fail(e, MCGPU_ESTATE, "mcgpu_step_propose first");
+  DeviceGuard g(e->dev);
+  CK(cudaMemcpyAsync(e->lytrial_d, lytrial, (size_t)e->C * 8, cudaMemcpyHostToDevice, e->stream));
+  HostLikParams p; fill_hostlik(e, p);
+  int publish = 0; double pub_winv = 0.0;
+  if (e->sampling) {
+    const int thin = e->cfg.thin;
+    if (e->hist && e->t_main % thin == 0) {
+      int rc = ring_guard(e, e->t_main / thin + 1); if (rc) return rc;
+      p.hist_row = (int)((e->t_main / thin) % e->hist_cap);
+    }
+    publish = (e->t_main + 1) % e->cfg.sync == 0;
+    pub_winv = 1.0 / (double)(e->t_main + 1);
+  }
+  ++e->launches;
+  CK(exact::launch_hostlik_accept(p, publish, pub_winv, e->stream));
+  CK(cudaStreamSynchronize(e->stream));                   // lytrial is the caller's (pageable) buffer
+  e->proposed = false;
+  if (!e->sampling) {
+    ++e->burn_done;
+    e->nburn_total = (int)e->burn_done;
+    if (e->burn_done == (long long)e->irate + 2) {         // tune after step index irate+1 (isamp > irate, mcpar.cc:78)
+      e->tune_pending = true;
+      int rc = mcgpu_tune(e); if (rc) return rc;
+    }
+  } else {
+    ++e->t_main;
+    e->hist_kept = (e->t_main + e->cfg.thin - 1) / e->cfg.thin;
+    if (e->hist) { int rc = drain_to_sink(e); if (rc) return rc; }
+    if (publish) ++e->npub;
+  }
+  return MCGPU_OK;
+}
+
 int mcgpu_tuning_counters(mcgpu_engine *e, void **dev_counts)
 {
   if (!e || !dev_counts) return MCGPU_EINVAL;
@@ -1199,7 +1298,7 @@ int mcgpu_get_state(mcgpu_engine *e, double *pvals, double *lylast, double *mu, 
     if (mu) CK(cudaMemcpyAsync(mu, e->mu, nb, cudaMemcpyDeviceToHost, e->stream));
     if (sig) CK(cudaMemcpyAsync(sig, e->sig, nb, cudaMemcpyDeviceToHost, e->stream));
     if (psum2) CK(cudaMemcpyAsync(psum2, e->ps, nb, cudaMemcpyDeviceToHost, e->stream));
-  } else if (e->wide) {
+  } else if (e->wide || e->hostlik) {
     if (pvals) CK(cudaMemcpyAsync(pvals, e->x, nb, cudaMemcpyDeviceToHost, e->stream));
     if (mu) CK(cudaMemcpyAsync(mu, e->mu, nb, cudaMemcpyDeviceToHost, e->stream));
     if (psum2) CK(cudaMemcpyAsync(psum2, e->ps, nb, cudaMemcpyDeviceToHost, e->stream));
@@ -1425,7 +1524,7 @@ size_t ckpt_bytes(const mcgpu_engine *e)
 int mcgpu_checkpoint_size(mcgpu_engine *e, size_t *bytes)
 {
   if (!e || !bytes) return MCGPU_EINVAL;
-  if (e->verify || e->replay_local) return fail(e, MCGPU_ESTATE, "checkpoints exist in NORMAL mode only");
+  if (e->verify || e->replay_local || e->hostlik) return fail(e, MCGPU_ESTATE, "checkpoints exist in NORMAL mode with a device likelihood only");
   *bytes = ckpt_bytes(e);
   return MCGPU_OK;
 }

@@ -146,6 +146,20 @@ struct WideParams {
   const double2 *gm2; const double *gm_lw; int kpad;
 };
 
+// One step of the host-callback likelihood path (mh_hostlik.cuh)
+struct HostLikParams {
+  double *x, *ly, *mu, *ps;            // [C][d], [C], [C][d], [C][d]
+  double *ptrial, *aux; int *flags;    // [C][d]; [C] = cfac (remote mode 0) or log cfac (mode 1); [C]: bit 0 remote, bits 8.. component
+  const double *lytrial;               // [C], from the host
+  long long C, chain0; int d;
+  const double *factor;                // [d][d] row-major lower factor (scaled by tuning)
+  unsigned long long *counts;          // {accepted, tried} of the tuning window
+  unsigned long long *mcounts;         // main phase: {accepted, tried, remote steps, candidates}
+  uint32_t key0, key1, step; int t, main_phase, first_remote_t, coin_group; double pl;
+  const double *pool; double *pool_next; int pool_m; long long pool_stride; int remote_mode;
+  double *hist; int hist_row;          // ring row of this step's kept sample, or -1
+};
+
 // runtime-dispatched likelihood description (verification mode, batched evaluation)
 struct LikSpec { int lik, d, k; double lp[8]; const double *dev; };
 

@@ -26,6 +26,8 @@ cudaError_t launch_init_loglik(int lik, int d, const StepParams &p, cudaStream_t
 cudaError_t launch_tune(unsigned long long *counts, unsigned long long *cum, double *factor, int dd,
                         double armin, double armax, double dfac, double ifac, cudaStream_t st);
 cudaError_t launch_verify(const VerifyParams &p, int nranks_local, cudaStream_t st);
+cudaError_t launch_hostlik_propose(const HostLikParams &p, cudaStream_t st);
+cudaError_t launch_hostlik_accept(const HostLikParams &p, int publish, double pub_winv, cudaStream_t st);
 cudaError_t launch_loglik_aos(const LikSpec &L, const double *x, double *y, int npset, cudaStream_t st);
 }
 }

@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MCGPU_LIB") or os.path.join(HERE, "libmcgpu.so")   # MCGPU_LIB: A/B experiments with alternative builds
 
-LIK = {"rosenbrock1": 0, "rosenbrock2": 1, "gaussian": 2, "dualgaussian": 3, "gaussmix": 4}
+LIK = {"rosenbrock1": 0, "rosenbrock2": 1, "gaussian": 2, "dualgaussian": 3, "gaussmix": 4, "host": 100}
 MODE = {"normal": 0, "verify": 1, "replay_local": 2}
 ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ECUDA", -4: "ESTATE", -5: "ENOMEM", -6: "ESTREAM",
           -7: "EPEER"}
@@ -22,7 +22,7 @@ EXPORTS = [
     "mcgpu_version", "mcgpu_device_count", "mcgpu_last_error", "mcgpu_create", "mcgpu_destroy",
     "mcgpu_set_stream", "mcgpu_set_likelihood", "mcgpu_set_covariance", "mcgpu_set_state",
     "mcgpu_set_streams", "mcgpu_burnin", "mcgpu_sample_begin", "mcgpu_sample", "mcgpu_sample_group",
-    "mcgpu_set_state_sobol",
+    "mcgpu_set_state_sobol", "mcgpu_set_state_host", "mcgpu_step_propose", "mcgpu_step_accept",
     "mcgpu_exchange_begin", "mcgpu_exchange_end", "mcgpu_p2p_export", "mcgpu_p2p_attach",
     "mcgpu_p2p_attach_local", "mcgpu_burnin_group", "mcgpu_tuning_counters", "mcgpu_burnin_some",
     "mcgpu_tune", "mcgpu_synchronize", "mcgpu_get_state", "mcgpu_get_factor", "mcgpu_get_musig",
@@ -219,6 +219,36 @@ class Engine:
         plo = np.ascontiguousarray(plo, dtype=np.float64); phi = np.ascontiguousarray(phi, dtype=np.float64)
         assert plo.size == self.d and phi.size == self.d
         self._ck(self.lib.mcgpu_set_state_sobol(self.h, _p(plo), _p(phi), C.c_uint64(first_point)))
+
+    # -- host-callback likelihood (a VLFunc that lives on the host) ---------------
+    def set_state_host(self, pinit, lylast):
+        pinit = np.ascontiguousarray(pinit, dtype=np.float64); lylast = np.ascontiguousarray(lylast, dtype=np.float64)
+        assert pinit.size == self.C * self.d and lylast.size == self.C
+        self._ck(self.lib.mcgpu_set_state_host(self.h, _p(pinit), _p(lylast)))
+
+    def step_propose(self, out=None):
+        pt = out if out is not None else np.empty((self.C, self.d))
+        self._ck(self.lib.mcgpu_step_propose(self.h, _p(pt)))
+        return pt
+
+    def step_accept(self, lytrial):
+        ly = np.ascontiguousarray(lytrial, dtype=np.float64)
+        assert ly.size == self.C
+        self._ck(self.lib.mcgpu_step_accept(self.h, _p(ly)))
+
+    def run_host(self, nsamp, nburn, pinit, loglik, incov=None):
+        """MCPar::run with a HOST likelihood callable loglik(x [n][d]) -> [n] (the VLFunc plugin call, mcpar.cc:53,60,160)."""
+        self.set_likelihood("host")
+        self.set_covariance(incov)
+        pinit = np.ascontiguousarray(pinit, dtype=np.float64).reshape(self.C, self.d)
+        self.set_state_host(pinit, loglik(pinit))
+        pt = np.empty((self.C, self.d))
+        for _ in range(nburn):
+            self.step_propose(pt); self.step_accept(loglik(pt))
+        self.sample_begin(nsamp)
+        for _ in range(nsamp):
+            self.step_propose(pt); self.step_accept(loglik(pt))
+        self.synchronize()
 
     def set_streams(self, local_rank, Z, U, I=None):
         Z = np.ascontiguousarray(Z, dtype=np.float64).ravel()

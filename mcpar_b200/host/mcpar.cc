@@ -48,10 +48,14 @@ MCPar::~MCPar() { destroy_engines(); }
 
 int MCPar::run(int nsamp, int nburn, const Real *pinit, VLFunc &L, MCout &outsamples, Real *incov)
 {
+  // A likelihood with a device functor runs inside the fused step kernels.  Any other VLFunc (a user-written
+  // plugin, src/vlfunc.hh:9-12) is called HERE, on the host, once per step between the engine's propose and
+  // accept kernels -- the same place MCPar::run calls it (src/mcpar.cc:60, :160); everything else stays on the GPU.
   DeviceVLFunc *dl = dynamic_cast<DeviceVLFunc *>(&L);
-  if (!dl) {
-    fprintf(stderr, "MCPar::run: this likelihood has no device functor; the B200 engine has no host path\n");
-    return ERROR;
+  const bool hostlik = dl == 0;
+  if (hostlik && ngpu > 1) {
+    fprintf(stderr, "MCPar::run: a host likelihood runs on one engine (ngpu = 1)\n");
+    return INVALID;
   }
   // log file, as the reference: rank 0 writes mcpar-log.000.txt in the working directory
   std::stringstream logname;
@@ -104,22 +108,43 @@ int MCPar::run(int nsamp, int nburn, const Real *pinit, VLFunc &L, MCout &outsam
   }
   eng = engs[0];
 
-  const std::vector<double> &par = dl->params();
+  static const std::vector<double> nopar;
+  const std::vector<double> &par = dl ? dl->params() : nopar;
   // pinit holds np*nc values; every rank starts from the same block (the mains pass the
   // same array on every rank, mcpar-rosen1.cc:43)
   std::vector<Real> p0((size_t)cg_chains * nparam);
   for (int r = 0; r < rpg; ++r) memcpy(&p0[(size_t)r * nchain * nparam], pinit, sizeof(Real) * (size_t)nchain * nparam);
+  std::vector<Real> ptrial, lytrial;                                  // host likelihood: one step's trial points and their logL
+  // the plugin is called with rank-sized batches, as each MPI rank called it: L(nchain, x, y) (mcpar.cc:53,60,160)
+  struct Plugin {
+    VLFunc &L; int nchain, nparam, size;
+    void operator()(const Real *x, Real *y) { for (int r = 0; r < size; ++r) L(nchain, x + (size_t)r * nchain * nparam, y + (size_t)r * nchain); }
+  } plugin = {L, nchain, nparam, size};
   for (int g = 0; g < G; ++g) {
     eng = engs[g];
-    CHECK(mcgpu_set_likelihood(eng, dl->lik_id(), par.empty() ? 0 : &par[0], (int)par.size()));
-    CHECK(mcgpu_set_covariance(eng, incov));
-    CHECK(mcgpu_set_state(eng, &p0[0]));
+    if (hostlik) {
+      CHECK(mcgpu_set_likelihood(eng, MCGPU_HOST_LIKELIHOOD, 0, 0));
+      CHECK(mcgpu_set_covariance(eng, incov));
+      ptrial.resize(p0.size()); lytrial.resize((size_t)cg_chains);
+      plugin(&p0[0], &lytrial[0]);                                    // L(nchain, pvals, lylast), mcpar.cc:53
+      CHECK(mcgpu_set_state_host(eng, &p0[0], &lytrial[0]));
+    } else {
+      CHECK(mcgpu_set_likelihood(eng, dl->lik_id(), par.empty() ? 0 : &par[0], (int)par.size()));
+      CHECK(mcgpu_set_covariance(eng, incov));
+      CHECK(mcgpu_set_state(eng, &p0[0]));
+    }
   }
   eng = engs[0];
   if (G > 1) CHECK(mcgpu_p2p_attach_local(&engs[0], G));
 
   logfile << "Starting burn-in.  Samples = " << nburn << std::endl;
-  if (G > 1) CHECK(mcgpu_burnin_group(&engs[0], G, nburn));            // tuning counters summed over the engines
+  if (hostlik) {
+    for (int isamp = 0; isamp < nburn; ++isamp) {                     // propose -> plugin -> accept (+ tuning inside accept)
+      CHECK(mcgpu_step_propose(eng, &ptrial[0]));
+      plugin(&ptrial[0], &lytrial[0]);
+      CHECK(mcgpu_step_accept(eng, &lytrial[0]));
+    }
+  } else if (G > 1) CHECK(mcgpu_burnin_group(&engs[0], G, nburn));     // tuning counters summed over the engines
   else CHECK(mcgpu_burnin(eng, nburn));
 
   logfile << "Starting main sample loop:  nsamp = " << nsamp << std::endl;
@@ -145,7 +170,13 @@ int MCPar::run(int nsamp, int nburn, const Real *pinit, VLFunc &L, MCout &outsam
     if (logging && done % logstep == 0)
       logfile << "sample step " << done << ":\toutsamples size= " << outsamples.size() << "  maxsize = "
               << outsamples.maxsize() << "  ncol= " << outsamples.ncol() << std::endl;
-    if (G == 1) CHECK(mcgpu_sample(eng, n));
+    if (hostlik) {
+      for (int k = 0; k < n; ++k) {
+        CHECK(mcgpu_step_propose(eng, &ptrial[0]));
+        plugin(&ptrial[0], &lytrial[0]);                   // L(nchain, ptrial, lytrial), mcpar.cc:160
+        CHECK(mcgpu_step_accept(eng, &lytrial[0]));
+      }
+    } else if (G == 1) CHECK(mcgpu_sample(eng, n));
     else CHECK(mcgpu_sample_group(&engs[0], G, n));      // one exchange window at a time, engine after engine
     const long long k0 = (done + thin - 1) / thin, k1 = (done + n + thin - 1) / thin;   // kept steps of this piece
     if (k1 > k0) {

@@ -131,3 +131,45 @@ def test_binary_output_and_iteration_bookkeeping(tmp_path):
     chain = np.tile(np.tile(np.arange(4), mcout_io.outstep_of(nsamp)), ranks * (nsamp // mcout_io.outstep_of(nsamp)))
     rank = np.tile(np.repeat(np.arange(ranks), 4 * mcout_io.outstep_of(nsamp)), nsamp // mcout_io.outstep_of(nsamp))
     assert np.array_equal(rows, h[it - 1, rank * 4 + chain])
+
+
+@pytest.mark.parametrize("remote_mode", [0, 1])
+def test_user_written_host_vlfunc_runs_through_mcpar(tmp_path, remote_mode):
+    """a VLFunc without a device functor is called on the host once per step (and per rank
+    batch), between the engine's propose and accept kernels; the run equals the fused run with the same likelihood
+    on the device."""
+    host = os.path.join(ROOT, "mcpar_b200", "host")
+    exe = str(tmp_path / "host_plugin_check")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-O2", "-I", host, "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "host_plugin_check.cc"), "-L", os.path.join(ROOT, "mcpar_b200"),
+                           "-lmcpar", "-lmcgpu", "-Wl,-rpath," + os.path.join(ROOT, "mcpar_b200")])
+    r = subprocess.run([exe, "16", "60", str(remote_mode)], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout + r.stderr
+
+
+def test_host_likelihood_steps_match_counter_oracle():
+    """mcgpu_step_propose / mcgpu_step_accept with the likelihood evaluated by the CALLER (here: the oracle's
+    orc_loglik on the host) against the oracle's counter-mode run: the split path uses plain fp64 arithmetic and
+    CUDA libm, so the two agree to rounding -- both remote modes, lagged pool, d = 2 and a d = 6 case that no fused
+    kernel is instantiated for."""
+    from mcpar_b200 import engine
+    from oracle import mh
+    for lik, par, d, N, M, cg, rmode, lag in [("dualgaussian", [5.0], 2, 128, 8, 0, 0, 0), ("dualgaussian", [5.0], 2, 128, 16, 4, 1, 1),
+                                              ("rosenbrock1", None, 6, 64, 8, 32, 1, 0)]:
+        nburn, nsamp = 110, 45
+        pin = tiled_pinit(N, d)
+        o = mh.run_counter(lik, d, N, nsamp, nburn, pin, par=par, pool_m=M, pl=0.7, coin_group=cg, remote_mode=rmode, pool_lag=lag, trace=True)
+        e = engine.Engine(d, N, mode="normal", pool_m=M, pl=0.7, coin_group=cg, history_steps=nsamp, remote_mode=rmode, pool_lag=lag)
+        calls = []
+        e.run_host(nsamp, nburn, pin, lambda x: (calls.append(len(x)), mh.loglik(lik, d, x, par))[1])
+        h = e.history()
+        same = np.all(np.isclose(h[:, :, :d], o["rows"][:, :, :d], rtol=1e-9, atol=1e-11), axis=-1)
+        assert same.mean() > 0.999, (lik, d, rmode, same.mean())
+        assert np.array_equal(e.factor(), o["cov"]), "burn-in tuning differs"
+        s = e.stats()
+        assert s["remote_steps"] == int(o["remote"][nburn:].sum()) and s["tried"] == nsamp * N
+        assert abs(s["remote_iterations"] - int(o["remote_iters"][0])) <= max(2, int(o["remote_iters"][0]) // 200)
+        assert len(calls) == nburn + nsamp + 1
+        with pytest.raises(engine.McgpuError, match="ESTATE"):
+            e.sample(1)
+        e.close()
