@@ -425,7 +425,8 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
 }
 
 #ifndef MCGPU_MINB_LOCAL
-#define MCGPU_MINB_LOCAL 10   // d = 2 local-only kernels: <= 48 registers, 40 warps per SM
+#define MCGPU_MINB_LOCAL 9    // d = 2 local-only kernels: <= 56 registers, 36 warps per SM (10 -> 48 registers costs ~5 % more
+                              // instructions in rematerialised constants: 7.33e10 vs 7.56e10 chain-steps/s, profiles/r02_tuning.md)
 #endif
 #ifndef MCGPU_MINB
 #define MCGPU_MINB 6      // d = 2: cap registers at 80 (6 CTAs of 128 per SM); gpurun_out/tune.log sweep
@@ -633,6 +634,7 @@ mh_steps_kernel(const StepParams p)
   T.exp_tab = T.log_tab = T.trig_tab = nullptr;
 #endif
 
+  if (MAIN && p.npeers > 0 && *reinterpret_cast<volatile int *>(p.xflag)) return;   // a peer-to-peer wait timed out earlier: stop stepping
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = j < p.C;
   const long long jc = live ? j : p.C - 1;           // idle lanes shadow the last chain, never store

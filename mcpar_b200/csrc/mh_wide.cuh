@@ -301,8 +301,11 @@ __device__ __noinline__ double wide_pool_exact_sum(const double *sx, int c, int 
 #ifndef MCGPU_WIDE_MINB
 #define MCGPU_WIDE_MINB 3       // d >= 32: <= 170 registers, 12 warps per SM (gpurun_out/tune_wide.log)
 #endif
+#ifndef MCGPU_WIDE_MINB_SMALL
+#define MCGPU_WIDE_MINB_SMALL 4 // d <= 16: <= 128 registers, 16 warps per SM
+#endif
 template <int LIK, int D, int NCH, int PHASE>
-__global__ void __launch_bounds__(128, (D >= 32 ? MCGPU_WIDE_MINB : 4))
+__global__ void __launch_bounds__(128, (D >= 32 ? MCGPU_WIDE_MINB : MCGPU_WIDE_MINB_SMALL))
 mh_wide_kernel(const WideParams p)
 {
   constexpr int L = D / 2;                      // lanes per group
@@ -315,6 +318,7 @@ mh_wide_kernel(const WideParams p)
   MathTables T;
   T.exp_tab = smem; T.log_tab = smem + MCGPU_EXP_TAB; T.trig_tab = T.log_tab + 2 * MCGPU_LOG_TAB;
   stage_math_tables(smem);
+  if (p.npeers > 0 && *reinterpret_cast<volatile int *>(p.xflag)) return;   // a peer-to-peer wait timed out earlier: stop stepping (MCGPU_EPEER at the next synchronize)
   const int gib = threadIdx.x / L;              // group within the CTA
   double *sx = smem + MCGPU_MATH_SMEM + (size_t)gib * 2 * D * NCH;
   double *sz = sx + D * NCH;
@@ -444,10 +448,15 @@ mh_wide_kernel(const WideParams p)
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           acc[c] = false; decided[c] = false;
-          if (am[c] > -10.0) {                          // then FPEPS/qmax < 2.3e-10 (mcpar.cc:357-358 offsets)
+          {
+            // pacpt = qimax / qisum with the reference's FPEPS offsets (qimax = max(FPEPS, max Q), qisum = FPEPS +
+            // sum Q, mcpar.cc:357-358, :397): at d >= 16 the largest Q at a candidate is e^(-d/2) ~ FPEPS, so the
+            // offsets are part of the ratio.  max Q = exp(am) in fp64 (am is exact); the sum is max Q * S with S
+            // right to eps (fp32: float conversion of the exponents, ex2.approx, <= M/L rescales).
             const double eps = 1.0e-4 + 2.0e-5 * (double)p.pool_m, Sd = (double)S[c];
-            if (u[c] * (Sd * (1.0 + eps) + 3.0e-10) < 1.0) { acc[c] = true; decided[c] = true; }
-            else if (u[c] * (Sd * (1.0 - eps)) >= 1.0) { decided[c] = true; }
+            const double qm = mc_exp(am[c], T), num = qm > MCGPU_FPEPS ? qm : MCGPU_FPEPS;
+            if (u[c] * (MCGPU_FPEPS + qm * Sd * (1.0 + eps)) < num * (1.0 - 1.0e-13)) { acc[c] = true; decided[c] = true; }
+            else if (u[c] * (MCGPU_FPEPS + qm * Sd * (1.0 - eps)) >= num * (1.0 + 1.0e-13)) { decided[c] = true; }
           }
           alldec = alldec && (decided[c] || done[c]);
         }
