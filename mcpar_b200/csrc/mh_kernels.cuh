@@ -429,7 +429,7 @@ __device__ __forceinline__ bool remote_candidate(uint32_t tlo, uint32_t thi, uin
                               // instructions in rematerialised constants: 7.33e10 vs 7.56e10 chain-steps/s, profiles/r02_tuning.md)
 #endif
 #ifndef MCGPU_MINB
-#define MCGPU_MINB 6      // d = 2: cap registers at 80 (6 CTAs of 128 per SM); gpurun_out/tune.log sweep
+#define MCGPU_MINB 7      // d = 2: cap registers at 72 (7 CTAs of 128 per SM); +2 % over 6 in all three remote configurations (profiles/r02_tuning.md)
 #endif
 // PHASE selects what a launch may contain:
 //   PH_BURN    burn-in steps (local proposals, no moments, no history)            mcpar.cc:56-97

@@ -302,7 +302,7 @@ __device__ __noinline__ double wide_pool_exact_sum(const double *sx, int c, int 
 #define MCGPU_WIDE_MINB 3       // d >= 32: <= 170 registers, 12 warps per SM (gpurun_out/tune_wide.log)
 #endif
 #ifndef MCGPU_WIDE_MINB_SMALL
-#define MCGPU_WIDE_MINB_SMALL 4 // d <= 16: <= 128 registers, 16 warps per SM
+#define MCGPU_WIDE_MINB_SMALL 6 // d <= 16: <= 80 registers, 24 warps per SM (+16 % local, +6 % sum-mixture over 4: profiles/r02_tuning.md)
 #endif
 template <int LIK, int D, int NCH, int PHASE>
 __global__ void __launch_bounds__(128, (D >= 32 ? MCGPU_WIDE_MINB : MCGPU_WIDE_MINB_SMALL))
