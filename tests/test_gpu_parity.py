@@ -446,7 +446,12 @@ def test_full_size_stationarity(pl, rmode, M):
             for i in (0, 1):
                 assert abs(dm[i]) < 5.0 * np.sqrt(var / N)
                 assert abs(h[:, i].var() - var) < 0.03
-                assert stats.kstest(h[::64, i], cdf).pvalue > 1.0e-3   # four KS tests in this case: family-wise 0.4 %
+                # KS over all 2^20 chains (four tests in this case: family-wise 0.4 %) and over the p-values of the 16 stride-16
+                # sub-samples, which a correct sampler leaves uniform.  A single stride-64 sub-sample is not a sound probe: runs that
+                # share the Philox streams of their local steps share their fluctuations (profiles/r02_ks_diag.md).
+                assert stats.kstest(h[:, i], cdf).pvalue > 1.0e-3
+                sub = [stats.kstest(h[j::16, i], cdf).pvalue for j in range(16)]
+                assert stats.kstest(sub, "uniform").pvalue > 1.0e-3
             assert abs(df) < 5.0 * np.sqrt(pright * (1.0 - pright) / N)
         else:                                  # measured: profiles/r02_bias_curve.md (the reference algorithm's own drift)
             assert max(abs(dm[0]), abs(dm[1])) < 0.25 and abs(df) < 0.05
