@@ -93,6 +93,27 @@ MCGPU_HD double mc_exp(double x, const MathTables &T)
   return mc_make(mc_hi(res) + ((n >> 6) << 20), mc_lo(res));   // * 2^k, k in [-1022, 1023]
 }
 
+// exp(x) for x <= 0 without a branch: the polynomial always runs and x <= -708 (also -inf, and NaN, whose
+// result the callers discard) selects 0 at the end -- one integer test and a select instead of a divergent
+// special-case block in the step loop.
+MCGPU_HD double mc_exp_nonpos(double x, const MathTables &T)
+{
+  const bool tiny = ((unsigned)mc_hi(x) & 0x7fffffffu) >= 0x40862000u;
+  const double nd = fma(x, MCK(0), MCK(3));
+  const int n = mc_lo(nd);
+  const double nf = nd - MCK(3);
+  double r = fma(nf, MCK(1), x);
+  r = fma(nf, MCK(2), r);
+  const double t = T.exp_tab[n & 63];
+  double p = fma(r, MCK(4), MCK(5));
+  p = fma(p, r, MCK(6));
+  p = fma(p, r, MCK(7));
+  p = fma(p, r, MCK(8));
+  const double res = fma(t, p * r, t);
+  const double y = mc_make(mc_hi(res) + ((n >> 6) << 20), mc_lo(res));
+  return tiny ? 0.0 : y;
+}
+
 // log(x) for normal positive x.  0 and subnormals give -inf (their logs, below -708, only
 // ever mark proposals that are rejected anyway), negative x gives NaN, +inf and NaN pass through.
 // CHECKED = false: the caller guarantees a normal, positive, finite x (the Box-Muller argument

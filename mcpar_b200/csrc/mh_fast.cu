@@ -1,8 +1,10 @@
 // mh_fast.cu -- production instantiations of the fused step kernels (FMA contraction on).
 #define MCGPU_NS fast
 #include <stdlib.h>
+#include <algorithm>
 #include "mh_kernels.cuh"
 #include "mh_wide.cuh"
+#include "mh_coop.cuh"
 namespace mcgpu { namespace fast {
 #include "mh_dispatch.inl"
 
@@ -47,8 +49,45 @@ static cudaError_t launch_wide_lik(int d, int phase, const WideParams &p, cudaSt
   return cudaErrorInvalidValue;
 }
 
+// ---- CTA-cooperative kernel: GaussMix at d = 64, K <= 64 (mh_coop.cuh) -------------------
+#ifndef MCGPU_COOP_NCW
+#define MCGPU_COOP_NCW 2        // chains per owner warp and batch
+#endif
+template <int PHASE>
+static cudaError_t launch_coop_phase(const WideParams &p, cudaStream_t st)
+{
+  constexpr int D = 64, NCW = MCGPU_COOP_NCW, NB = kCoopWarps * NCW;
+  constexpr bool REMOTE = PHASE == PH_REMOTE_SUM;
+  int SL = 0, lsl = 0;
+  if (REMOTE) { SL = 16; lsl = 4; while (SL < p.mpad) { SL <<= 1; ++lsl; } }
+  const size_t smem = coop_smem_bytes<D, NCW>(SL);
+  int dev = 0, sms = 0;            // per launch: one process may drive engines on several devices, and the attribute is per device
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t rc = cudaFuncSetAttribute(mh_coop_kernel<D, NCW, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (rc != cudaSuccess) return rc;
+  const long long nbatch = (p.C + NB - 1) / NB;
+  const unsigned grid = (unsigned)std::min<long long>(nbatch, (long long)sms * (REMOTE ? 1 : 2));
+  mh_coop_kernel<D, NCW, PHASE><<<grid, kCoopThreads, smem, st>>>(p, (int)nbatch, SL, lsl);
+  return cudaGetLastError();
+}
+
+static bool coop_applies(int lik, int d, int phase, const WideParams &p)
+{
+  static const bool off = getenv("MCGPU_NO_COOP") && atoi(getenv("MCGPU_NO_COOP"));
+  if (off || lik != MCGPU_GAUSSMIX || d != 64 || p.kpad != kCoopKP) return false;
+  if (phase == PH_BURN || phase == PH_LOCAL) return true;
+  return phase == PH_REMOTE_SUM && p.mpad <= 256;      // the reference's rejection loop (PH_REMOTE) stays on the wide kernel
+}
+
 cudaError_t launch_wide(int lik, int d, int phase, const WideParams &p, cudaStream_t st)
 {
+  if (coop_applies(lik, d, phase, p)) {
+    switch (phase) {
+      case PH_BURN:       return launch_coop_phase<PH_BURN>(p, st);
+      case PH_LOCAL:      return launch_coop_phase<PH_LOCAL>(p, st);
+      case PH_REMOTE_SUM: return launch_coop_phase<PH_REMOTE_SUM>(p, st);
+    }
+  }
   if (lik == MCGPU_ROSENBROCK1) return launch_wide_lik<MCGPU_ROSENBROCK1>(d, phase, p, st);
   if (lik == MCGPU_GAUSSMIX) return launch_wide_lik<MCGPU_GAUSSMIX>(d, phase, p, st);
   return cudaErrorInvalidValue;

@@ -114,22 +114,22 @@ template <> struct Lik<MCGPU_DUALGAUSSIAN, 2> {
   static __device__ __forceinline__ double eval(const double (&x)[2], const StepParams &p, const MathTables &T) {
     const double arg1 = 0.5 * (x[0] * x[0] + x[1] * x[1]);
     const double t2a = x[0] - 5.0, t2b = x[1] - 5.0;
-    const double arg2 = 0.5 * (t2a * t2a + t2b * t2b);
+    const double narg2 = -0.5 * (t2a * t2a + t2b * t2b);
 #ifdef MCGPU_EXACT_TU
-    return MC_LOG(p.lp[0] * MC_EXP(-arg1) + MC_EXP(-arg2));
+    return MC_LOG(p.lp[0] * MC_EXP(-arg1) + MC_EXP(narg2));
 #else
     // the same value with one exponential instead of two:  log(w e^-a1 + e^-a2) = M + log(1 + e^-|t1 - t2|),
-    // t1 = log w - a1, t2 = -a2, M = max(t1, t2)  (lp[1] = log w, set on the host).  A term whose
-    // exponential the two-exp form flushes to zero (a > 708) is dropped here too, and
-    // with both dropped the result is log(0) = -inf, as in the reference.
-    // The comparisons run on the integer pipe (high words): arg >= 0, so arg >= 708 <=> hi(arg) >= hi(708);
-    // the sign of t1 - t2 picks the maximum (-inf - -inf = NaN picks either: both are -inf).
-    const double t1 = __double2hiint(arg1) >= 0x40862000 ? -INFINITY : p.lp[1] - arg1;
-    const double t2 = __double2hiint(arg2) >= 0x40862000 ? -INFINITY : -arg2;
-    const double dt = t1 - t2;
-    const double M = __double2hiint(dt) < 0 ? t2 : t1;
-    const double r = M + mc_log_pos(1.0 + MC_EXP(-fabs(dt)), T);   // argument in [1, 2]; NaN when both terms are dropped
-    return __double2hiint(M) != (int)0xfff00000 ? r : -INFINITY;
+    // t1 = log w - a1, t2 = -a2, M = max(t1, t2)  (lp[1] = log w, set on the host).  When BOTH exponentials of
+    // the two-exp form flush to zero (a1, a2 >= 708) the result is log(0) = -inf, as in the
+    // reference; a single flushed term only ever changes the sum below 1e-16 relative (the other term is
+    // then e^37 times larger) unless both are within reach of the flush, where the reference itself runs on
+    // denormals.  The comparisons are integer tests on the high words.
+    const double t1 = p.lp[1] - arg1;
+    const double dt = t1 - narg2;
+    const double M = __double2hiint(dt) < 0 ? narg2 : t1;
+    const double r = M + mc_log_pos(1.0 + mc_exp_nonpos(-fabs(dt), T), T);   // argument in [1, 2]
+    const bool dead = __double2hiint(arg1) >= 0x40862000 && (unsigned)__double2hiint(narg2) >= 0xC0862000u;
+    return dead ? -INFINITY : r;
 #endif
   }
 };
@@ -224,10 +224,12 @@ __device__ __forceinline__ bool accept_test_local(double u, double delta, const 
 #ifdef MCGPU_EXACT_TU
   return u < exp(delta);
 #else
+  if (exact_tests) return accept_exact(u, delta, 1.0, T);              // audit mode
+  // No clamps: ex2.approx saturates the right way -- delta >= 88.8 (also +inf) gives e = +inf > u: accept;
+  // delta <= -87.4 (also -inf) gives e = 0 <= u: reject; NaN fails both comparisons and reaches the exact test,
+  // where u < NaN is false.  In between e carries < 2e-5 relative error (float(delta) and the product 1.3e-5
+  // at |delta| <= 88, the fp32 log2(e) 2e-6, ex2.approx 2.4e-7), inside the 1e-4 margin.
   const float df = (float)delta;
-  if (exact_tests || df != df) return accept_exact(u, delta, 1.0, T);   // audit mode; NaN (-inf - -inf): the comparison is false
-  if (df >= 80.0f) return true;
-  if (df <= -80.0f) return false;
   const float e = ex2_approx(df * 1.4426950408889634f), uf = (float)u;
   if (uf < e * (1.0f - 1.0e-4f)) return true;
   if (uf >= e * (1.0f + 1.0e-4f)) return false;

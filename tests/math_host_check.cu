@@ -55,11 +55,18 @@ int main()
     if (fabs(v - 1.0) > 0.02) { const double el = ulp_err(mcgpu::mc_log_pos(v, T), logl((long double)v)); if (el > e_logpos) e_logpos = el; }
     if (mcgpu::mc_log_pos(v, T) != mcgpu::mc_log(v, T)) e_logpos = 1e9;       // same arithmetic as the checked routine
   }
+  // mc_exp_nonpos: the branch-free variant must agree with mc_exp bit for bit on x <= 0 and flush below -708
+  int nonpos_bad = 0;
+  for (int i = 0; i < 2000000; ++i) {
+    const double x = -rnd() * (i & 1 ? 900.0 : 40.0);
+    if (mcgpu::mc_exp_nonpos(x, T) != mcgpu::mc_exp(x, T)) ++nonpos_bad;
+  }
+  if (mcgpu::mc_exp_nonpos(-INFINITY, T) != 0.0 || mcgpu::mc_exp_nonpos(-0.0, T) != 1.0 || mcgpu::mc_exp_nonpos(-1.0e300, T) != 0.0) ++nonpos_bad;
   const double sq0 = mcgpu::mc_sqrt_pos(0.0);
   double sp[4] = {mcgpu::mc_exp(-800.0, T), mcgpu::mc_exp(800.0, T), mcgpu::mc_exp(NAN, T), mcgpu::mc_log(0.0, T)};
   printf("{\"exp_ulp\": %.3f, \"log_ulp\": %.3f, \"log_near1_abs\": %.3e, \"sin_ulp\": %.3f, \"cos_ulp\": %.3f, "
          "\"sqrt_ulp\": %.3f, \"sqrt0\": %g, \"logpos_ulp\": %.3f, "
-         "\"sincos_abs\": %.3e, \"exp_m800\": %g, \"exp_p800_inf\": %d, \"exp_nan\": %d, \"log0_minf\": %d}\n",
-         e_exp, e_log, e_log01, e_sin, e_cos, e_sqrt, sq0, e_logpos, abs_sc, sp[0], (int)isinf(sp[1]), (int)isnan(sp[2]), (int)(isinf(sp[3]) && sp[3] < 0));
+         "\"sincos_abs\": %.3e, \"exp_m800\": %g, \"exp_p800_inf\": %d, \"exp_nan\": %d, \"log0_minf\": %d, \"exp_nonpos_mismatches\": %d}\n",
+         e_exp, e_log, e_log01, e_sin, e_cos, e_sqrt, sq0, e_logpos, abs_sc, sp[0], (int)isinf(sp[1]), (int)isnan(sp[2]), (int)(isinf(sp[3]) && sp[3] < 0), nonpos_bad);
   return 0;
 }

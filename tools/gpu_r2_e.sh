@@ -15,7 +15,7 @@ for w in 2 4 8; do
   ( time timeout 600 $TR --nproc-per-node $w --master-port $port tests/dist_check.py ) > $O/e${NG}_dist_check_${w}gpu.log 2>&1
   echo "rc=$?" >> $O/e${NG}_dist_check_${w}gpu.log
 done
-if [ "$QUICK" = "1" ]; then SW="--min-exp 14 --max-exp 20 --ref-max-exp 16"; ST="--steps 50"; else SW="--ref-max-exp 20"; ST="--steps 300"; fi
+if [ "$QUICK" = "1" ]; then SW="--min-exp 14 --max-exp 20 --ref-max-exp 16"; ST="--steps 50"; else SW="--ref-max-exp 20"; ST="--steps 200"; fi
 port=$((port + 1))
 ( time timeout 900 $TR --nproc-per-node $NG --master-port $port tools/sweep_c5.py $SW ) > $O/e${NG}_sweep.log 2>&1
 echo "rc=$?" >> $O/e${NG}_sweep.log
@@ -28,7 +28,7 @@ echo "rc=$?" >> $O/e${NG}_c4_reference256.err
 port=$((port + 1))
 ( time timeout 600 $TR --nproc-per-node $NG --master-port $port bench.py --gpus $NG $ST ) > $O/e${NG}_c2_dgauss.json 2> $O/e${NG}_c2_dgauss.err
 echo "rc=$?" >> $O/e${NG}_c2_dgauss.err
-if [ "$QUICK" != "1" ]; then
+if [ "$QUICK" = "2" ]; then
   port=$((port + 1))
   ( time timeout 600 $TR --nproc-per-node $NG --master-port $port bench.py --gpus $NG --remote-mode summix --no-modes $ST ) > $O/e${NG}_c2_dgauss_summix.json 2> $O/e${NG}_c2_dgauss_summix.err
   port=$((port + 1))
