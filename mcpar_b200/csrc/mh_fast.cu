@@ -51,13 +51,13 @@ static cudaError_t launch_wide_lik(int d, int phase, const WideParams &p, cudaSt
 
 // ---- CTA-cooperative kernel: GaussMix at d = 64, K <= 64 (mh_coop.cuh) -------------------
 #ifndef MCGPU_COOP_NCW
-#define MCGPU_COOP_NCW 2        // chains per owner warp and batch
+#define MCGPU_COOP_NCW 4        // chains per owner warp and batch (1 / 2 / 4: 2.56 / 2.03 / 1.78 ms per local step of 2^20 chains)
 #endif
 template <int PHASE>
 static cudaError_t launch_coop_phase(const WideParams &p, cudaStream_t st)
 {
-  constexpr int D = 64, NCW = MCGPU_COOP_NCW, NB = kCoopWarps * NCW;
   constexpr bool REMOTE = PHASE == PH_REMOTE_SUM;
+  constexpr int D = 64, NCW = REMOTE ? 1 : MCGPU_COOP_NCW, NB = kCoopWarps * NCW;   // remote kernels: the pool takes the shared memory
   int SL = 0, lsl = 0;
   if (REMOTE) { SL = 16; lsl = 4; while (SL < p.mpad) { SL <<= 1; ++lsl; } }
   const size_t smem = coop_smem_bytes<D, NCW>(SL);
@@ -66,7 +66,7 @@ static cudaError_t launch_coop_phase(const WideParams &p, cudaStream_t st)
   cudaError_t rc = cudaFuncSetAttribute(mh_coop_kernel<D, NCW, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (rc != cudaSuccess) return rc;
   const long long nbatch = (p.C + NB - 1) / NB;
-  const unsigned grid = (unsigned)std::min<long long>(nbatch, (long long)sms * (REMOTE ? 1 : 2));
+  const unsigned grid = (unsigned)std::min<long long>(nbatch, (long long)sms);   // persistent: one CTA per SM
   mh_coop_kernel<D, NCW, PHASE><<<grid, kCoopThreads, smem, st>>>(p, (int)nbatch, SL, lsl);
   return cudaGetLastError();
 }

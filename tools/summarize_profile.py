@@ -55,6 +55,23 @@ def full(path, warpsteps):
             if m in hdr:
                 i = hdr.index(m)
                 print("  %-70s %s %s" % (m, row[i], units[i]))
+        # warp stall reasons (cycles a warp spent stalled per instruction it issued), largest first
+        st = []
+        for i, m in enumerate(hdr):
+            if "issue_stalled" in m and m.endswith("_per_warp_active.pct"):
+                try:
+                    st.append((float(row[i]), m.replace("smsp__average_warps_issue_stalled_", "").replace("_per_warp_active.pct", "")))
+                except ValueError:
+                    pass
+        if not st:
+            for i, m in enumerate(hdr):
+                if "issue_stalled" in m and m.endswith(".ratio"):
+                    try:
+                        st.append((float(row[i]), m.replace("smsp__average_warp_latency_issue_stalled_", "").replace("smsp__average_warps_issue_stalled_", "").replace(".ratio", "")))
+                    except ValueError:
+                        pass
+        if st:
+            print("  warp stall reasons: " + ", ".join("%s %.2f" % (n, v) for v, n in sorted(st, reverse=True)[:8]))
         src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--launch-skip", str(k), "--launch-count", "1"],
                              capture_output=True, text=True).stdout
         srows = list(csv.reader(src.splitlines()))
