@@ -76,6 +76,47 @@ def incov_for(wl):
     return None
 
 
+def remote_plan(seed, d, nburn, nsteps, pl, first_remote_t):
+    """The job-wide local/remote coin of main steps 0..nsteps-1, evaluated on the host exactly as the engine does
+    (mcgpu_api.cu host_coin: word 2*NP+1 of chain 0's local Philox4x32-10 stream at step nburn + t; remote iff
+    t >= first_remote_t and not coin <= pl, mcpar.cc:142-152).  Returns a list of 0/1."""
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    idx = 2 * ((d + 1) // 2) + 1
+    out = []
+    for t in range(nsteps):
+        c = [0, 0, (nburn + t) & MASK, idx // 4]
+        k0, k1 = seed & MASK, (seed >> 32) & MASK
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [((p1 >> 32) ^ c[1] ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c[3] ^ k1) & MASK, p0 & MASK]
+            k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+        coin = c[idx % 4] / 4294967296.0
+        out.append(1 if (t >= first_remote_t and not coin <= pl) else 0)
+    return out
+
+
+def place_timed_region(seed, d, nburn, sync, lag, pl, advance, warmup, K, slack=200):
+    """Where to start the K timed windows.  With one coin per step for the whole job the share of remote steps inside a
+    short timed region is a draw (K = 20 windows hold 200 coins: 20 +- 4 remote steps), and a remote step costs many
+    local ones, so `value` would depend on K.  The coins are counter-based and known in advance: the region is moved
+    forward by at most `slack` windows to where its remote share is closest to the long-run 1 - pl.  Returns
+    (advance, remote share of the timed region)."""
+    if pl >= 1.0 or K * sync > 200000:
+        return advance, 0.0 if pl >= 1.0 else None
+    plan = remote_plan(seed, d, nburn, (advance + slack + warmup + K) * sync, pl, sync * (1 + lag))
+    cum = [0]
+    for b in plan:
+        cum.append(cum[-1] + b)
+    best, best_err = advance, None
+    for a in range(advance, advance + slack + 1):
+        lo = (a + warmup) * sync
+        share = (cum[lo + K * sync] - cum[lo]) / float(K * sync)
+        err = abs(share - (1.0 - pl))
+        if best_err is None or err < best_err - 1e-12:
+            best, best_err, best_share = a, err, share
+    return best, best_share
+
+
 class ClockSampler:
     """SM clock and throttle reasons of ONE GPU sampled during the run by an NVML polling thread (every rank
     runs its own, started before the warm-up, so no rank enters the timed loop late)."""
@@ -489,6 +530,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="skip the secondary measurements of the other remote modes")
     ap.add_argument("--no-check", action="store_true", help="N>1: skip the sharded == single-engine check")
+    ap.add_argument("--no-place", action="store_true", help="do not move the timed region to a representative share of remote steps")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                         # timing rule: W >= 3
@@ -523,6 +565,9 @@ def main():
     if args.advance < 0:
         args.advance = W["advance"]
     d, Cg, sync, thin = W["d"], args.chains, args.sync, args.thin
+    placed_share = None
+    if args.coin_group == 0 and not args.no_place:
+        args.advance, placed_share = place_timed_region(SEED, d, 500, sync, args.lag, args.pl, args.advance, args.warmup, args.steps)
     N = Cg * world
     K, Wu = args.steps, args.warmup
     rmode = RMODE[args.remote_mode]
@@ -612,7 +657,8 @@ def main():
         key = "%s/%s/M%d" % (args.workload, args.remote_mode, args.pool)
         prof = {}
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "fp64_work.json"))).get(key, {})
+            allprof = json.load(open(os.path.join(ROOT, "profiles", "fp64_work.json")))
+            prof = allprof.get(key) or allprof.get("%s/local" % args.workload, {})      # no count for the mode: the local step's (a lower bound)
         except Exception:
             pass
         F = prof.get("fp64_flops_per_chain_step")
@@ -635,7 +681,8 @@ def main():
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%s: %s d=%d, %d chains/GPU x %d GPU, PLOCAL %.2f, SYNCSTEP %d, remote mode %s, pool M=%d, pool lag %d, %s, "
-                                       "thin %d, seed %d; step = one %d-step exchange window; %d untimed windows before the timed region" % (
+                                       "thin %d, seed %d; step = one %d-step exchange window; %d untimed windows before the timed region (placed where the "
+                                       "region's share of remote steps is closest to 1 - PLOCAL: the coins are counter-based)" % (
                                            W["name"], W["lik"], d, Cg, world, args.pl, sync, args.remote_mode, args.pool, args.lag,
                                            "one local/remote coin per step" if args.coin_group == 0 else "coin per %d chains" % args.coin_group,
                                            thin, SEED, sync, args.advance + Wu),

@@ -46,23 +46,24 @@ __device__ __forceinline__ void nb_arrive(int id, int cnt) { __threadfence_block
 
 // dynamic shared memory of one CTA; SL = pool slots held side by side (power of two, 16..256; 0: no pool)
 template <int D, int NCW>
-__host__ __device__ constexpr size_t coop_smem_bytes(int SL)
+__host__ __device__ constexpr size_t coop_smem_bytes(int SL, bool pool_in_smem)
 {
   constexpr int NB = kCoopWarps * NCW, CP = 2 * NB;
   size_t b = sizeof(double) * ((size_t)MCGPU_MATH_SMEM + (size_t)2 * NB * D + (size_t)2 * NB * D + (size_t)2 * NB * 4 +
                                (size_t)kCoopWarps * D * NCW + (size_t)NB * 4 * kCoopKP);
-  if (SL > 0) b += sizeof(float) * ((size_t)2 * D * CP + (size_t)kCoopHalf * CP + (size_t)SL) + sizeof(float2) * (size_t)D * SL;
+  if (SL > 0) b += sizeof(float) * ((size_t)2 * D * CP + (size_t)kCoopHalf * CP + (size_t)SL) + (pool_in_smem ? sizeof(float2) * (size_t)D * SL : 0);
   return b;
 }
 
-template <int D, int NCW, int PHASE>
+// POOLSM: the fp32 pool is staged in shared memory (128 KB at M = 256: leaves room for one chain per owner warp only) or read
+// through L1 (`__ldg`, coalesced over the slots; two chains per owner warp)
+template <int D, int NCW, int PHASE, bool POOLSM = true>
 __global__ void __launch_bounds__(kCoopThreads, 1)
 mh_coop_kernel(const WideParams p, const int nbatch, const int SL, const int lsl)
 {
   constexpr int L = D / 2, NW = kCoopWarps, NB = NW * NCW, KP = kCoopKP, DQ = D / 4, CP = 2 * NB;
   static_assert(L == 32, "one warp owns a chain: d = 64");
   static_assert(NB % 8 == 0, "the mixture warps take eight chains at a time");
-  static_assert(PHASE != PH_REMOTE_SUM || NB == 8, "remote kernels: one group of eight chains per batch (the pool partials ride on it)");
   constexpr bool MAIN = PHASE != PH_BURN, REMOTE = PHASE == PH_REMOTE_SUM;
   constexpr int ABLK = (2 * L) / 4, AW = (2 * L) % 4;   // accept uniform: word 2*NP of the local stream
   extern __shared__ __align__(16) double smem[];
@@ -81,13 +82,14 @@ mh_coop_kernel(const WideParams p, const int nbatch, const int SL, const int lsl
   if (p.npeers > 0 && *reinterpret_cast<volatile int *>(p.xflag)) return;   // a peer-to-peer wait timed out earlier: stop stepping
 
   const int tid = threadIdx.x, warp = tid >> 5, r = tid & 31;
-  if (REMOTE) {
+  if (REMOTE && POOLSM) {
     for (int idx = tid; idx < D * SL; idx += kCoopThreads) {
       const int i = idx >> lsl, s = idx & (SL - 1);
       spool[idx] = s < p.mpad ? __ldg(p.pf + (size_t)i * p.mpad + s) : make_float2(1.0e18f, 0.0f);   // padding: Q = 0
     }
-    for (int s = tid; s < SL; s += kCoopThreads) snb[s] = s < p.mpad ? __ldg(p.pnbf + s) : 0.0f;
   }
+  if (REMOTE)
+    for (int s = tid; s < SL; s += kCoopThreads) snb[s] = s < p.mpad ? __ldg(p.pnbf + s) : 0.0f;
   // batches of this CTA, dealt alternately to the two slots; a slot runs cnt = (its batches) * nsteps iterations
   const int nb_cta = (int)blockIdx.x < nbatch ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int cnt0 = ((nb_cta + 1) >> 1) * p.nsteps, cnt1 = (nb_cta >> 1) * p.nsteps;
@@ -123,44 +125,43 @@ mh_coop_kernel(const WideParams p, const int nbatch, const int SL, const int lsl
             q[cc] = fma(fma(A[j + 1], xv[cc].y, B[j + 1]), xv[cc].y, q[cc]);
           }
         }
-        if (c0 == 0 && seq > 0 && !REMOTE) nb_sync(CB_EMPTY, kCoopThreads);   // the owners have read the previous batch's partials
-        if (!REMOTE) {
+        if (c0 == 0 && seq > 0) nb_sync(CB_EMPTY, kCoopThreads);   // the owners have read the previous batch's partials (and pool totals)
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) sq[((c0 + cc) * 4 + h) * KP + kc] = q[cc];
-        } else {
-          // pool slot sl, parameter chunk ch: -sum_{i in chunk} (g mu - g y_i)^2 for the 2 NB points of the batch
-          const int sl = tid & (SL - 1), ch = tid >> lsl, dpc = (D * SL) >> 8;
-          float acc[CP];
+        for (int cc = 0; cc < 8; ++cc) sq[((c0 + cc) * 4 + h) * KP + kc] = q[cc];
+      }
+      if (REMOTE) {
+        // pool slot sl, parameter chunk ch: -sum_{i in chunk} (g mu - g y_i)^2 for the 2 NB points of the batch
+        const int sl = tid & (SL - 1), ch = tid >> lsl, dpc = (D * SL) >> 8;
+        float acc[CP];
 #pragma unroll
-          for (int v = 0; v < CP; ++v) acc[v] = 0.0f;
-          const float2 *pp = spool + (size_t)ch * dpc * SL + sl;
-          const float4 *xv4 = reinterpret_cast<const float4 *>(sxf + (size_t)s * D * CP + (size_t)ch * dpc * CP);
+        for (int v = 0; v < CP; ++v) acc[v] = 0.0f;
+        const float2 *pp = POOLSM ? spool + (size_t)ch * dpc * SL + sl : p.pf + (size_t)ch * dpc * p.mpad + (sl < p.mpad ? sl : 0);
+        const int pstride = POOLSM ? SL : p.mpad;
+        const bool pad = !POOLSM && sl >= p.mpad;       // slots beyond the pool: Q = 0
+        const float4 *xv4 = reinterpret_cast<const float4 *>(sxf + (size_t)s * D * CP + (size_t)ch * dpc * CP);
 #pragma unroll 2
-          for (int ii = 0; ii < dpc; ++ii) {
-            const float2 f = pp[(size_t)ii * SL];
+        for (int ii = 0; ii < dpc; ++ii) {
+          float2 f = POOLSM ? pp[(size_t)ii * pstride] : __ldg(pp + (size_t)ii * pstride);
+          if (pad) f = make_float2(1.0e18f, 0.0f);
 #pragma unroll
-            for (int v = 0; v < CP / 4; ++v) {
-              const float4 t4 = xv4[ii * (CP / 4) + v];
-              float y;
-              y = fmaf(-f.y, t4.x, f.x); acc[4 * v] = fmaf(-y, y, acc[4 * v]);
-              y = fmaf(-f.y, t4.y, f.x); acc[4 * v + 1] = fmaf(-y, y, acc[4 * v + 1]);
-              y = fmaf(-f.y, t4.z, f.x); acc[4 * v + 2] = fmaf(-y, y, acc[4 * v + 2]);
-              y = fmaf(-f.y, t4.w, f.x); acc[4 * v + 3] = fmaf(-y, y, acc[4 * v + 3]);
-            }
+          for (int v = 0; v < CP / 4; ++v) {
+            const float4 t4 = xv4[ii * (CP / 4) + v];
+            float y;
+            y = fmaf(-f.y, t4.x, f.x); acc[4 * v] = fmaf(-y, y, acc[4 * v]);
+            y = fmaf(-f.y, t4.y, f.x); acc[4 * v + 1] = fmaf(-y, y, acc[4 * v + 1]);
+            y = fmaf(-f.y, t4.z, f.x); acc[4 * v + 2] = fmaf(-y, y, acc[4 * v + 2]);
+            y = fmaf(-f.y, t4.w, f.x); acc[4 * v + 3] = fmaf(-y, y, acc[4 * v + 3]);
           }
-          if (seq > 0) nb_sync(CB_EMPTY, kCoopThreads); // the owners have read the previous batch's partials and totals
+        }
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) sq[((c0 + cc) * 4 + h) * KP + kc] = q[cc];
-#pragma unroll
-          for (int v = 0; v < CP; ++v) part[((size_t)ch * CP + v) * SL + sl] = acc[v];
-          nb_sync(CB_MIX, kCoopHalf);                   // mixture warps only
-          // totals over the chunks: A_s(y) log2 e = nb_s - sum_i (..)^2, left in part[0][point][slot]
-          const int dc = kCoopHalf >> lsl;
-          for (int v = ch; v < CP; v += dc) {
-            float e = snb[sl];
-            for (int c2 = 0; c2 < dc; ++c2) e += part[((size_t)c2 * CP + v) * SL + sl];
-            part[(size_t)v * SL + sl] = e;              // only this thread reads part[0][v][sl]
-          }
+        for (int v = 0; v < CP; ++v) part[((size_t)ch * CP + v) * SL + sl] = acc[v];
+        nb_sync(CB_MIX, kCoopHalf);                     // mixture warps only
+        // totals over the chunks: A_s(y) log2 e = nb_s - sum_i (..)^2, left in part[0][point][slot]
+        const int dc = kCoopHalf >> lsl;
+        for (int v = ch; v < CP; v += dc) {
+          float e = snb[sl];
+          for (int c2 = 0; c2 < dc; ++c2) e += part[((size_t)c2 * CP + v) * SL + sl];
+          part[(size_t)v * SL + sl] = e;                // only this thread reads part[0][v][sl]
         }
       }
       nb_arrive(CB_DONE0 + s, kCoopThreads);

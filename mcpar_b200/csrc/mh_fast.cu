@@ -53,21 +53,24 @@ static cudaError_t launch_wide_lik(int d, int phase, const WideParams &p, cudaSt
 #ifndef MCGPU_COOP_NCW
 #define MCGPU_COOP_NCW 4        // chains per owner warp and batch (1 / 2 / 4: 2.56 / 2.03 / 1.78 ms per local step of 2^20 chains)
 #endif
+#ifndef MCGPU_COOP_POOLSM
+#define MCGPU_COOP_POOLSM 1     // remote kernels: 1 = fp32 pool staged in shared memory (one chain per owner warp), 0 = read through L1 (two): 2.23 vs 2.72 ms per step of config 4
+#endif
 template <int PHASE>
 static cudaError_t launch_coop_phase(const WideParams &p, cudaStream_t st)
 {
-  constexpr bool REMOTE = PHASE == PH_REMOTE_SUM;
-  constexpr int D = 64, NCW = REMOTE ? 1 : MCGPU_COOP_NCW, NB = kCoopWarps * NCW;   // remote kernels: the pool takes the shared memory
+  constexpr bool REMOTE = PHASE == PH_REMOTE_SUM, POOLSM = MCGPU_COOP_POOLSM != 0;
+  constexpr int D = 64, NCW = REMOTE ? (POOLSM ? 1 : 2) : MCGPU_COOP_NCW, NB = kCoopWarps * NCW;
   int SL = 0, lsl = 0;
   if (REMOTE) { SL = 16; lsl = 4; while (SL < p.mpad) { SL <<= 1; ++lsl; } }
-  const size_t smem = coop_smem_bytes<D, NCW>(SL);
+  const size_t smem = coop_smem_bytes<D, NCW>(SL, POOLSM);
   int dev = 0, sms = 0;            // per launch: one process may drive engines on several devices, and the attribute is per device
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t rc = cudaFuncSetAttribute(mh_coop_kernel<D, NCW, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t rc = cudaFuncSetAttribute(mh_coop_kernel<D, NCW, PHASE, POOLSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (rc != cudaSuccess) return rc;
   const long long nbatch = (p.C + NB - 1) / NB;
   const unsigned grid = (unsigned)std::min<long long>(nbatch, (long long)sms);   // persistent: one CTA per SM
-  mh_coop_kernel<D, NCW, PHASE><<<grid, kCoopThreads, smem, st>>>(p, (int)nbatch, SL, lsl);
+  mh_coop_kernel<D, NCW, PHASE, POOLSM><<<grid, kCoopThreads, smem, st>>>(p, (int)nbatch, SL, lsl);
   return cudaGetLastError();
 }
 
