@@ -16,7 +16,10 @@ What the line holds (contract: the task's bench section):
   value / ms_per_step   K timed windows, state resident, CUDA events on the launching stream, max over ranks.
                         Before the timed region the sampler is advanced `--advance` untimed windows so that
                         the rejection loop of the reference's remote proposal sits at its plateau (its
-                        iteration count rises for ~2000 windows): the value does not depend on K.
+                        iteration count rises for ~2000 windows), and the region is placed (at most 200 windows
+                        later) where its share of remote steps is closest to 1 - PLOCAL -- the job-wide coins are
+                        counter-based and evaluated on the host (place_timed_region): the value does not depend
+                        on K (20 / 50 / 1000 windows agree to 0.3 %, profiles/r02_steps_independence.md).
   remote mode           `reference` (default): the reference's max-mixture rejection loop over a pool of M
                         components; `summix`: the normalised sum-mixture proposal (no rejection loop).  The
                         headline is the default mode; "modes" holds short measurements of the other

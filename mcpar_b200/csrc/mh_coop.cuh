@@ -132,9 +132,11 @@ mh_coop_kernel(const WideParams p, const int nbatch, const int SL, const int lsl
       if (REMOTE) {
         // pool slot sl, parameter chunk ch: -sum_{i in chunk} (g mu - g y_i)^2 for the 2 NB points of the batch
         const int sl = tid & (SL - 1), ch = tid >> lsl, dpc = (D * SL) >> 8;
+        const int dc = kCoopHalf >> lsl;                // parameter chunks (1 when the pool fills the 256 threads: M > 128)
+        const float nb0 = dc == 1 ? snb[sl] : 0.0f;     // one chunk: the sums start at n_s log2 e and ARE the totals
         float acc[CP];
 #pragma unroll
-        for (int v = 0; v < CP; ++v) acc[v] = 0.0f;
+        for (int v = 0; v < CP; ++v) acc[v] = nb0;
         const float2 *pp = POOLSM ? spool + (size_t)ch * dpc * SL + sl : p.pf + (size_t)ch * dpc * p.mpad + (sl < p.mpad ? sl : 0);
         const int pstride = POOLSM ? SL : p.mpad;
         const bool pad = !POOLSM && sl >= p.mpad;       // slots beyond the pool: Q = 0
@@ -155,13 +157,14 @@ mh_coop_kernel(const WideParams p, const int nbatch, const int SL, const int lsl
         }
 #pragma unroll
         for (int v = 0; v < CP; ++v) part[((size_t)ch * CP + v) * SL + sl] = acc[v];
-        nb_sync(CB_MIX, kCoopHalf);                     // mixture warps only
-        // totals over the chunks: A_s(y) log2 e = nb_s - sum_i (..)^2, left in part[0][point][slot]
-        const int dc = kCoopHalf >> lsl;
-        for (int v = ch; v < CP; v += dc) {
-          float e = snb[sl];
-          for (int c2 = 0; c2 < dc; ++c2) e += part[((size_t)c2 * CP + v) * SL + sl];
-          part[(size_t)v * SL + sl] = e;                // only this thread reads part[0][v][sl]
+        if (dc > 1) {
+          nb_sync(CB_MIX, kCoopHalf);                   // mixture warps only
+          // totals over the chunks: A_s(y) log2 e = nb_s - sum_i (..)^2, left in part[0][point][slot]
+          for (int v = ch; v < CP; v += dc) {
+            float e = snb[sl];
+            for (int c2 = 0; c2 < dc; ++c2) e += part[((size_t)c2 * CP + v) * SL + sl];
+            part[(size_t)v * SL + sl] = e;              // only this thread reads part[0][v][sl]
+          }
         }
       }
       nb_arrive(CB_DONE0 + s, kCoopThreads);

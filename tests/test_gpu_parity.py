@@ -227,6 +227,7 @@ def test_production_kernel_replay_local(lik, d, C, par, incov):
     ("rosenbrock1", 8, 40, None, 5, 0.7, 0, 1, 1),
     ("gaussmix", 64, 24, "gmix64", 6, 0.7, 0, 1, 0),
     ("gaussmix", 64, 136, "gmix64", 40, 0.7, 0, 1, 1),
+    ("gaussmix", 64, 256, "gmix64", 0, 0.7, 0, 1, 0),       # every chain in the pool: M = 256, one pool slot per mixture-warp thread
     ("gaussmix", 16, 48, "gmix16", 8, 0.8, 0, 1, 0),
 ])
 def test_normal_mode_matches_counter_oracle(lik, d, N, par, pool_m, pl, cg, rmode, lag):
