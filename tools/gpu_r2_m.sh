@@ -3,6 +3,7 @@
 NG=${1:-8}
 mkdir -p gpurun_out
 O=gpurun_out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/m${NG}_smoke.log 2>&1; tail -1 $O/m${NG}_smoke.log
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node $NG"
 ( time timeout 600 $TR --master-port 29611 bench.py --gpus $NG --workload gmix64 --pool 256 --remote-mode summix --steps 200 ) > $O/m${NG}_c4_summix256.json 2> $O/m${NG}_c4_summix256.err
 echo "rc=$?" >> $O/m${NG}_c4_summix256.err
