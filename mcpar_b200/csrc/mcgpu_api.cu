@@ -223,7 +223,7 @@ cudaError_t launch_steps_any(mcgpu_engine *e, int phase, const StepParams &p)
     w.arrivals = p.arrivals; w.wait_target = p.wait_target; w.pub_wait_target = p.pub_wait_target; w.xflag = p.xflag;   // readers wait in pool_prep, publishers in the kernel
     w.xstat = p.xstat;
     w.hist = p.hist; w.thin = p.thin; w.hist_cap = p.hist_cap; w.hist_ring0 = p.hist_ring0;
-    w.pnb = e->pprep + (size_t)3 * e->d * e->mpad; w.summix = e->remote_mode;
+    w.pnb = e->pprep + (size_t)3 * e->d * e->mpad; w.summix = e->remote_mode; w.exact_tests = p.exact_tests;
     w.pf = reinterpret_cast<const float2*>(e->pprep + ((size_t)3 * e->d + 1) * e->mpad);        // fp32 copy behind the fp64 arrays
     w.pnbf = reinterpret_cast<const float*>(w.pf + (size_t)e->d * e->mpad); w.pscal = w.pnbf + e->mpad;
     w.gm2 = reinterpret_cast<const double2*>(e->gm_t);

@@ -142,6 +142,7 @@ struct WideParams {
   const double *pnb;               // [Mpad] n_s = -1/2 sum_i log sig2_si (remote mode 1: normalised components)
   const float2 *pf; const float *pnbf; const float *pscal;   // fp32 copy [D][Mpad] (g mu, g), [Mpad] n_s log2 e, {max |mu|, max 1/sigma, max |nb|}
   int summix;                      // remote mode 1
+  int exact_tests;                 // audit mode: accept / rejection / Hastings-factor decisions always in fp64 (MCGPU_EXACT_TESTS=1)
   // likelihood: GaussMix parameters, component fastest: gm2 [D][Kpad] = (mu, 1/s2) pairs, gm_lw [Kpad] = log w
   const double2 *gm2; const double *gm_lw; int kpad;
 };

@@ -278,7 +278,7 @@ mh_coop_kernel(const WideParams p, const int nbatch, const int SL, const int lsl
           const float Een = fmaxf(lvl - lg2_approx(snc), 30.0f), Eeo = fmaxf(lvl - lg2_approx(fmaxf(soc, 1.0e-37f)), 30.0f);
           const float eps_n = 0.75f * (2.0f * th_n * sqrtf(cD * Een) + cu * Een + cD * th_n * th_n) + cn;
           const float eps_o = 0.75f * (2.0f * th_o * sqrtf(cD * Eeo) + cu * Eeo + cD * th_o * th_o) + cn;
-          ok = ok && th_n < 1.0e-3f && th_o < 1.0e-3f && eps_n < 0.02f && eps_o < 0.02f;
+          ok = ok && !p.exact_tests && th_n < 1.0e-3f && th_o < 1.0e-3f && eps_n < 0.02f && eps_o < 0.02f;   // (audit mode: always the fp64 route)
           const float cf_lo = __fdividef(soc * (1.0f - eps_o), snc * (1.0f + eps_n)) * (1.0f - 1.0e-6f);
           const float cf_hi = __fdividef(fmaf(soc, 1.0f + eps_o, 2.0e-38f * (float)p.pool_m), snc * (1.0f - eps_n)) * (1.0f + 1.0e-6f);
           int dec = ok ? accept_test_bounded(u_acc, lyt - ly[c], cf_lo, cf_hi) : -1;
@@ -297,7 +297,7 @@ mh_coop_kernel(const WideParams p, const int nbatch, const int SL, const int lsl
           }
           a = dec != 0;
         } else {
-          a = accept_test_local(u_acc, lyt - ly[c], T, 0);      // mcpar.cc:67-69 / :167-169 with cfac = 1
+          a = accept_test_local(u_acc, lyt - ly[c], T, p.exact_tests);      // mcpar.cc:67-69 / :167-169 with cfac = 1
         }
         if (a) { ly[c] = lyt; x0[c] = xt0; x1[c] = xt1; }
         if (r == 0 && live) { wacc += a ? 1u : 0u; ++nlive; }

@@ -413,6 +413,10 @@ mh_wide_kernel(const WideParams p)
       }
       __syncwarp();
       wide_summix_bounds<D, NCH>(sf, r, cpick, p, cf_lo, cf_hi, cf_ok);
+      if (p.exact_tests) {                            // audit mode: every Hastings factor in fp64
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) cf_ok[c] = false;
+      }
       __syncwarp();
     } else {
       // genRemote: the group's chains run the reference's rejection loop in step: candidate
@@ -455,7 +459,8 @@ mh_wide_kernel(const WideParams p)
             // right to eps (fp32: float conversion of the exponents, ex2.approx, <= M/L rescales).
             const double eps = 1.0e-4 + 2.0e-5 * (double)p.pool_m, Sd = (double)S[c];
             const double qm = mc_exp(am[c], T), num = qm > MCGPU_FPEPS ? qm : MCGPU_FPEPS;
-            if (u[c] * (MCGPU_FPEPS + qm * Sd * (1.0 + eps)) < num * (1.0 - 1.0e-13)) { acc[c] = true; decided[c] = true; }
+            if (p.exact_tests) { }                      // audit mode: every rejection test in fp64 (below)
+            else if (u[c] * (MCGPU_FPEPS + qm * Sd * (1.0 + eps)) < num * (1.0 - 1.0e-13)) { acc[c] = true; decided[c] = true; }
             else if (u[c] * (MCGPU_FPEPS + qm * Sd * (1.0 - eps)) >= num * (1.0 + 1.0e-13)) { decided[c] = true; }
           }
           alldec = alldec && (decided[c] || done[c]);
@@ -536,7 +541,7 @@ mh_wide_kernel(const WideParams p)
     }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const bool a = SUMMIX ? dec[c] != 0 : accept_test(u_acc[c], lyt[c] - ly[c], MAIN ? cfac[c] : 1.0, T, 0);   // same inputs in every lane of the group
+      const bool a = SUMMIX ? dec[c] != 0 : accept_test(u_acc[c], lyt[c] - ly[c], MAIN ? cfac[c] : 1.0, T, p.exact_tests);   // same inputs in every lane of the group
       if (a) { ly[c] = lyt[c]; x0[c] = xt0[c]; x1[c] = xt1[c]; }
       nacc[c] += a ? 1u : 0u;
       if (MAIN) {

@@ -11,8 +11,17 @@ from mcpar_b200 import engine                           # noqa: E402
 
 
 def run(lik, par, d, N, M, pl, cg, nburn, nsamp, rmode=0):
+    pin, incov = tiled_pinit(N, d), None
+    if lik == "gaussmix":                               # K = 64 mixture in d = 64 (the cooperative kernel), chains start on the means
+        from oracle import mh
+        K = 64
+        rng = np.random.default_rng(8)
+        gmu = rng.uniform(-5, 5, (K, d)); gs2 = rng.uniform(0.5, 2.0, (K, d))
+        par = mh.gaussmix_params(K, d, gmu, gs2, np.ones(K))
+        pin = gmu[np.arange(N) % K].copy()
+        incov = np.eye(d) * (2.38 ** 2 / d)
     e = engine.Engine(d, N, mode="normal", pool_m=M, pl=pl, coin_group=cg, history_steps=nsamp, remote_mode=rmode)
-    e.run(nsamp, nburn, tiled_pinit(N, d), lik, par)
+    e.run(nsamp, nburn, pin, lik, par, incov)
     out = dict(hist=e.history(), p=e.state()["p"], pool=e.musig(), acc=np.array(e.stats()["accepted"]),
                rit=np.array(e.stats()["remote_iterations"]))
     e.close()
@@ -29,6 +38,11 @@ CASES = {
     "rosen2_sum256": ("rosenbrock1", None, 2, 4096, 256, 0.5, 0, 150, 300, 1),
     "rosen2_sum_groups": ("rosenbrock1", None, 2, 4096, 12, 0.6, 8, 150, 200, 1),
     "rosen4_sum": ("rosenbrock1", None, 4, 2048, 8, 0.5, 0, 150, 200, 1),
+    # wide kernels (d = 16: 8 lanes per chain) and the cooperative d = 64 kernel
+    "rosen16_ref": ("rosenbrock1", None, 16, 512, 8, 0.5, 0, 150, 100, 0),
+    "rosen16_sum": ("rosenbrock1", None, 16, 512, 16, 0.5, 0, 150, 100, 1),
+    "gmix64_sum": ("gaussmix", None, 64, 200, 40, 0.5, 0, 100, 100, 1),
+    "gmix64_sum256": ("gaussmix", None, 64, 256, 0, 0.5, 0, 100, 100, 1),
 }
 
 if __name__ == "__main__":

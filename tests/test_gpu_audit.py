@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.parametrize("case", ["dgauss", "rosen2", "rosen2_groups", "rosen4",
-                                  "dgauss_sum", "rosen2_sum256", "rosen2_sum_groups", "rosen4_sum"])
+                                  "dgauss_sum", "rosen2_sum256", "rosen2_sum_groups", "rosen4_sum",
+                                  "rosen16_ref", "rosen16_sum", "gmix64_sum", "gmix64_sum256"])
 def test_fp32_bounded_decisions_equal_fp64_decisions(case, tmp_path):
     outs = {}
     for mode in ("0", "1"):
