@@ -287,11 +287,11 @@ mh_coop_kernel(const WideParams p, const int nbatch, const int SL, const int lsl
             __syncwarp();
             sz[i0 * NCW + c] = xt0; sz[(i0 + 1) * NCW + c] = xt1;
             __syncwarp();
-            const double ln_ = wide_pool_lse_exact<D, NCW>(sz, c, r, p, T);
+            const double ln_ = wide_pool_lse_exact<D, NCW>(sz, c, r, p.pmh, p.pnb, p.pool_m, p.mpad, T);
             __syncwarp();
             sz[i0 * NCW + c] = x0[c]; sz[(i0 + 1) * NCW + c] = x1[c];
             __syncwarp();
-            const double lo_ = wide_pool_lse_exact<D, NCW>(sz, c, r, p, T);
+            const double lo_ = wide_pool_lse_exact<D, NCW>(sz, c, r, p.pmh, p.pnb, p.pool_m, p.mpad, T);
             __syncwarp();
             dec = u_acc < mc_exp((lyt - ly[c]) + (lo_ - ln_), T) ? 1 : 0;
           }

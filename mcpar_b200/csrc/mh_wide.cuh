@@ -254,17 +254,20 @@ __device__ __forceinline__ void wide_summix_bounds(const float *sf, int r, const
 }
 
 // exact log of the normalised sum-mixture at chain c's staged point (remote mode 1, rare path)
+// (the out-of-line rare paths take the few fields they need BY VALUE: a reference to the kernel's parameter struct would
+// force every thread to copy all of it -- 520 bytes -- from the constant bank to its stack at kernel entry)
 template <int D, int NCH>
-__device__ __noinline__ double wide_pool_lse_exact(const double *sx, int c, int r, const WideParams &p, const MathTables &T)
+__device__ __noinline__ double wide_pool_lse_exact(const double *sx, int c, int r, const double2 *pmh, const double *pnb, int pool_m, int mpad,
+                                                   const MathTables T)
 {
   constexpr int L = D / 2;
   double m = -INFINITY, sm = 0.0;
-  for (int s = r; s < p.pool_m; s += L) {
-    double a = __ldg(p.pnb + s);
-    const double2 *g = p.pmh + s;
+  for (int s = r; s < pool_m; s += L) {
+    double a = __ldg(pnb + s);
+    const double2 *g = pmh + s;
     for (int i = 0; i < D; ++i) {
       const double2 mh = __ldg(g);
-      g += p.mpad;
+      g += mpad;
       const double xm = mh.x - sx[i * NCH + c];
       a += xm * xm * mh.y;
     }
@@ -278,24 +281,23 @@ __device__ __noinline__ double wide_pool_lse_exact(const double *sx, int c, int 
 
 // exact pacpt material for chain c of the staged points (rare path)
 template <int D, int NCH>
-__device__ __noinline__ double wide_pool_exact_sum(const double *sx, int c, int r, const WideParams &p, double &qmax, const MathTables &T)
+__device__ __noinline__ double2 wide_pool_exact_sum(const double *sx, int c, int r, const double2 *pmh, int pool_m, int mpad, const MathTables T)
 {
   constexpr int L = D / 2;
   double qs = 0.0, qm = 0.0;
-  for (int s = r; s < p.pool_m; s += L) {
+  for (int s = r; s < pool_m; s += L) {
     double a = 0.0;
-    const double2 *g = p.pmh + s;
+    const double2 *g = pmh + s;
     for (int i = 0; i < D; ++i) {
       const double2 mh = __ldg(g);
-      g += p.mpad;
+      g += mpad;
       const double xm = mh.x - sx[i * NCH + c];
       a += xm * xm * mh.y;
     }
     const double gv = mc_exp(a, T);
     qs += gv; qm = gv > qm ? gv : qm;
   }
-  qmax = group_max<L>(qm);
-  return group_sum<L>(qs);
+  return make_double2(group_sum<L>(qs), group_max<L>(qm));      // (sum, max)
 }
 
 #ifndef MCGPU_WIDE_MINB
@@ -469,9 +471,9 @@ mh_wide_kernel(const WideParams p)
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             nfb += (!decided[c] && !done[c] && live[c]) ? 1u : 0u;
-            double qmax;
-            const double qsum = wide_pool_exact_sum<D, NCH>(sx, c, r, p, qmax, T) + MCGPU_FPEPS;
-            qmax = qmax > MCGPU_FPEPS ? qmax : MCGPU_FPEPS;
+            const double2 sm_ = wide_pool_exact_sum<D, NCH>(sx, c, r, p.pmh, p.pool_m, p.mpad, T);
+            const double qsum = sm_.x + MCGPU_FPEPS;
+            const double qmax = sm_.y > MCGPU_FPEPS ? sm_.y : MCGPU_FPEPS;
             if (!decided[c]) acc[c] = u[c] < qmax / qsum;
           }
         }
@@ -527,13 +529,13 @@ mh_wide_kernel(const WideParams p)
         for (int c = 0; c < NCH; ++c) { sx[i0 * NCH + c] = xt0[c]; sx[(i0 + 1) * NCH + c] = xt1[c]; }
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) ln_[c] = wide_pool_lse_exact<D, NCH>(sx, c, r, p, T);
+        for (int c = 0; c < NCH; ++c) ln_[c] = wide_pool_lse_exact<D, NCH>(sx, c, r, p.pmh, p.pnb, p.pool_m, p.mpad, T);
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) { sx[i0 * NCH + c] = x0[c]; sx[(i0 + 1) * NCH + c] = x1[c]; }
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) lo_[c] = wide_pool_lse_exact<D, NCH>(sx, c, r, p, T);
+        for (int c = 0; c < NCH; ++c) lo_[c] = wide_pool_lse_exact<D, NCH>(sx, c, r, p.pmh, p.pnb, p.pool_m, p.mpad, T);
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) if (dec[c] < 0) dec[c] = u_acc[c] < mc_exp((lyt[c] - ly[c]) + (lo_[c] - ln_[c]), T) ? 1 : 0;
