@@ -95,9 +95,12 @@ def test_accept_test_interval_contains_exp_delta():
 
 
 # ---------------------------------------------------------------- remote mode 1: sum-mixture proposal
-def _summix_model(rng, M, D, npts, mu_scale, sig_lo, sig_hi, far):
-    """summix_bounds (mh_kernels.cuh) in numpy float32 against the exact fp64 q(x)/q(x'); returns the true
-    ratio, the kernel's interval and which points the fast path decides."""
+def _summix_model(rng, M, D, npts, mu_scale, sig_lo, sig_hi, far, chunks=None):
+    """summix_bounds (mh_kernels.cuh; wide_summix_bounds of mh_wide.cuh is the same arithmetic spread over lanes) in numpy
+    float32 against the exact fp64 q(x)/q(x'); returns the true ratio, the kernel's interval and which points the fast
+    path decides.  chunks = DC models the cooperative kernel (mh_coop.cuh): the exponent of a slot is summed in DC
+    parameter chunks (from 0, or from nb when DC = 1), the chunk totals are added to nb, and the picked component's total
+    is subtracted afterwards; its bound uses the larger rounding terms cu = (24 + D) u, cn = 4.8e-7 nbmax + ..."""
     mu = rng.uniform(-mu_scale, mu_scale, (M, D))
     mu[: M // 2] = mu[0] + rng.normal(0, 0.3, (M // 2, D))
     sig = np.exp(rng.uniform(np.log(sig_lo), np.log(sig_hi), (M, D)))
@@ -119,16 +122,41 @@ def _summix_model(rng, M, D, npts, mu_scale, sig_lo, sig_hi, far):
     true = np.exp(lse_true(xo) - lse_true(xn))
 
     xof, xnf = f32(xo), f32(xn)
-    ref = nb32[c].copy()
-    for i in range(D):
-        y = (gmu32[c, i] - g32[c, i] * xnf[:, i]).astype(f32)
-        ref = (ref - y * y).astype(f32)
+
+    def totals(xf):                                                                    # cooperative kernel: E[slot] per point
+        dpc = D // chunks
+        e = nb32[None].repeat(len(xf), 0).astype(f32) if chunks == 1 else np.zeros((len(xf), M), f32)
+        parts = []
+        for ch in range(chunks):
+            acc = e if chunks == 1 else np.zeros((len(xf), M), f32)
+            for i in range(ch * dpc, (ch + 1) * dpc):
+                y = (gmu32[None, :, i] - g32[None, :, i] * xf[:, None, i]).astype(f32)
+                acc = (acc - y * y).astype(f32)
+            parts.append(acc)
+        if chunks == 1:
+            return parts[0]
+        tot = nb32[None].repeat(len(xf), 0).astype(f32)
+        for a in parts:
+            tot = (tot + a).astype(f32)
+        return tot
+
+    if chunks:
+        En_tot, Eo_tot = totals(xnf), totals(xof)
+        ref = En_tot[np.arange(npts), c]
+    else:
+        ref = nb32[c].copy()
+        for i in range(D):
+            y = (gmu32[c, i] - g32[c, i] * xnf[:, i]).astype(f32)
+            ref = (ref - y * y).astype(f32)
 
     def ssum(xf, sgn):
-        acc = (nb32[None] - ref[:, None]).astype(f32)
-        for i in range(D):
-            y = (gmu32[None, :, i] - g32[None, :, i] * xf[:, None, i]).astype(f32)
-            acc = (acc - y * y).astype(f32)
+        if chunks:
+            acc = ((En_tot if xf is xnf else Eo_tot) - ref[:, None]).astype(f32)
+        else:
+            acc = (nb32[None] - ref[:, None]).astype(f32)
+            for i in range(D):
+                y = (gmu32[None, :, i] - g32[None, :, i] * xf[:, None, i]).astype(f32)
+                acc = (acc - y * y).astype(f32)
         ex = f32(np.exp2(acc.astype(np.float64)) * (1.0 + sgn * 2.4e-7))             # ex2.approx at the edge of its bound
         ex[ex < f32(1.1754944e-38)] = 0                                                # ftz
         part = [ex[:, q::4].sum(1, dtype=f32) for q in range(4)]                       # 4 partial sums + tree
@@ -143,6 +171,8 @@ def _summix_model(rng, M, D, npts, mu_scale, sig_lo, sig_hi, far):
         En = np.maximum(lvl - np.log2(np.maximum(sn, f32(1e-37))), 30.0)
         Eo = np.maximum(lvl - np.log2(np.maximum(so, f32(1e-37))), 30.0)
         cu, cn = (4.0 + D) * 6.0e-8, 2.4e-7 * nbmax + 1.0e-5 + 1.0e-8 * M
+        if chunks:
+            cu, cn = (24.0 + D) * 6.0e-8, 4.8e-7 * nbmax + 1.0e-5 + 1.0e-8 * M
         eps_n = 0.75 * (2.0 * th_n * np.sqrt(D * En) + cu * En + D * th_n * th_n) + cn
         eps_o = 0.75 * (2.0 * th_o * np.sqrt(D * Eo) + cu * Eo + D * th_o * th_o) + cn
         ok &= (th_n < 1e-3) & (th_o < 1e-3) & (eps_n < 0.02) & (eps_o < 0.02)
@@ -171,3 +201,22 @@ def test_summix_interval_contains_the_true_hastings_factor(M, D, mu_scale, sig_l
         # and the interval is tight: ~3e-4 of the uniforms fall inside it in the benchmark's regime (narrow
         # components or a far origin widen it through theta, still within 2 %)
         assert np.median(width) < (1.0004 if (mu_scale == 6.0 and sig_lo == 0.5) else 1.02)
+
+
+@pytest.mark.parametrize("M,D,chunks,mu_scale,sig_lo,sig_hi", [
+    (16, 16, None, 3.0, 0.4, 1.5),   # wide kernel, config 3's dimension
+    (40, 64, None, 5.0, 0.6, 1.5),   # wide kernel at d = 64
+    (40, 64, 4, 5.0, 0.6, 1.5),      # cooperative kernel: 64 slots side by side, 4 parameter chunks
+    (256, 64, 1, 5.0, 0.6, 1.5),     # cooperative kernel at the blueprint's M = 256: one chunk, sums start at nb
+    (256, 64, 1, 40.0, 0.7, 1.4),    # means far from the origin
+])
+@pytest.mark.parametrize("far", [False, True])
+def test_summix_interval_wide_and_cooperative_kernels(M, D, chunks, mu_scale, sig_lo, sig_hi, far):
+    rng = np.random.default_rng(91 + M + D + (chunks or 0))
+    true, runs = _summix_model(rng, M, D, 3000 if D == 64 else 20000, mu_scale, sig_lo, sig_hi, far, chunks=chunks)
+    for lo, hi, ok in runs:
+        assert ok.mean() > 0.5, "the case must exercise the fast path"
+        inside = (true[ok] >= lo[ok]) & (true[ok] <= hi[ok])
+        assert inside.all(), "q(x)/q(x') outside the kernel's interval for %d points" % (~inside).sum()
+        if not far:                                  # (far: q(x) underflows in fp32 at d >= 16 -- the lower bound is 0, the interval still holds the truth)
+            assert np.median(hi[ok] / np.maximum(lo[ok], 1e-300)) < 1.02
