@@ -478,7 +478,8 @@ def e2e_job(ctx, Cg, rmode, M, f32, reps):
     d = W["d"]
     sink = torch.empty((kept_e, Cg, d + 1), dtype=torch.float32 if f32 else torch.float64).pin_memory().numpy()
     best, best_c, fin, all_secs = None, None, None, []
-    for _ in range(reps):
+    warm = 2                                        # untimed repetitions first: on a fresh box the first jobs pay one-time costs
+    for rep in range(warm + reps):                  # (lazy kernel loading, first touch of the pinned sink: 2.3 s and 0.8 s observed)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         job = Job(ctx, Cg, rmode, M, ring=min(kept_e, 16))             # device history: a ring of 16 kept steps
@@ -502,7 +503,7 @@ def e2e_job(ctx, Cg, rmode, M, f32, reps):
             ctx["dist"].all_reduce(tt, op=ctx["dist"].ReduceOp.MAX)
         sec, con = float(tt[0].item()), float(tt[1].item())
         all_secs.append(round(sec, 5))
-        if best is None or sec < best:
+        if rep >= warm and (best is None or sec < best):
             best, best_c = sec, con
     nwin = (nb_e + ns_e) // a.sync
     return {"seconds": best, "construction_seconds": best_c, "all_seconds": all_secs, "chain_steps": Cg * ctx["world"] * (nb_e + ns_e),
@@ -640,7 +641,7 @@ def main():
                "h2d_bytes_per_step": f32["h2d"], "d2h_bytes_per_step": f32["d2h"],
                "job": "set_state(host pinit) + burnin 500 + 1000 steps + history(thin %d, fp32 rows = the reference MCout's element "
                       "type, narrowed on the device; device history = a ring of 16 kept steps drained on a side stream) and final logL "
-                      "to pinned host; bytes are per %d-step window of the %d-window job; best of 3" % (thin, sync, f32["nwin"]),
+                      "to pinned host; bytes are per %d-step window of the %d-window job; best of 3 after 2 untimed repetitions (all in all_seconds)" % (thin, sync, f32["nwin"]),
                "seconds": f32["seconds"], "all_seconds": f32["all_seconds"], "construction_seconds": f32["construction_seconds"],
                "construction": "engine create + likelihood/covariance upload + exchange wiring (CUDA IPC attach), outside the e2e clock, max over ranks",
                "host_numa": numa,
