@@ -672,10 +672,13 @@ def main():
                 "flops_per_chain_step": F if F else W["F_hw"],
                 "flops_source": ("ncu: (dadd + dmul + 2 dfma) thread instructions of the window kernels / chain-steps, %s" % prof.get("source", "profiles/fp64_work.json")
                                  if F else "SURVEY.md 8(d) a-priori estimate (no ncu count committed for %s)" % key),
-                "fp64_pipe_util_ncu": prof.get("fp64_pipe_pct"),
+                "fp64_pipe_util_ncu": prof.get("fp64_pipe_pct"), "issue_slot_util_ncu": prof.get("issue_active_pct"),
+                "warp_instructions_per_chain_step_ncu": prof.get("warp_instructions_per_chain_step"),
                 "note": "achieved = chain-steps/s/GPU x fp64 flops per chain-step; peak = DFMA micro-kernel measured in this run "
                         "(MEASURED_PEAKS.json has no fp64 figure); kernel time = CUDA events around each window launch; traffic and the "
-                        "pipe utilisation come from the committed ncu capture of this configuration (profiles/README.md), null if none",
+                        "pipe / issue-slot utilisation come from the committed ncu capture of this configuration (profiles/README.md), null if none.  "
+                        "The step kernels are bound by issue slots and two half-rate integer pipes beside the FP64 pipe (DESIGN.md section 5): "
+                        "the remote proposals' pool tests run in fp32 under rigorous bounds and add no fp64 work",
                 "achieved_textbook_tflops": per_gpu * W["F_alg"] / 1e12,
                 "hbm": {"achieved": per_gpu * bytes_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": per_gpu * bytes_step / 1e9 / hbm_peak, "bytes_per_chain_step": bytes_step,
