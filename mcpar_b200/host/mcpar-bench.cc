@@ -3,7 +3,7 @@
 // count N it runs MCPar(2, 32 chains per rank, N/32 ranks) with nburn 500 + nsamp 1000, thin 10, PLOCAL 0.9, pool
 // M = min(N, 256), into an MCout without an output stream, and prints one line
 //     N  chain-steps/s(device)  acceptance  exchange-wait-ms
-// `mcpar-bench [--ngpu=G] [--remote-mode=1] [--lag=1] [--lik=rosen1|dgauss] [N ...]`
+// `mcpar-bench [--ngpu=G] [--remote-mode=1] [--lag=1] [--lik=rosen1|dgauss] [--nsamp=S] [N ...]`
 #include <iostream>
 #include <vector>
 #include <stdio.h>
@@ -17,10 +17,12 @@ int main(int argc, char *argv[])
   DriverOpts o(1000);
   o.thin = 10; o.pool = 256;
   o.parse(argc, argv);
+  o.nsamp = 1000;                                   // here the positional arguments are chain counts, not nsamp
   bool dgauss = false;
   std::vector<long long> sizes;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--lik=dgauss")) dgauss = true;
+    else if (!strncmp(argv[i], "--nsamp=", 8)) o.nsamp = atoi(argv[i] + 8);
     else if (argv[i][0] != '-') sizes.push_back(atoll(argv[i]));
   }
   if (sizes.empty()) for (int e = 10; e <= 20; e += 2) sizes.push_back(1ll << e);

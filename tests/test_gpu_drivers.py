@@ -173,3 +173,35 @@ def test_host_likelihood_steps_match_counter_oracle():
         with pytest.raises(engine.McgpuError, match="ESTATE"):
             e.sample(1)
         e.close()
+
+
+@pytest.mark.parametrize("remote_mode", [0, 1])
+def test_mcpar_gmix_contract(tmp_path, remote_mode):
+    """mcpar-gmix (BASELINE config 4's likelihood: d = 64, K = 64 mixture; no counterpart main in the reference, it follows
+    the shape of src/mcpar-dgauss.cc): banner, rows of 64 parameters + logL for every kept step of every chain, the
+    maximum-likelihood line, the log file.  Job-wide coin, so the steps run on the wide / cooperative kernels."""
+    nsamp, ranks, thin = 40, 4, 10
+    r = subprocess.run([os.path.join(BIN, "mcpar-gmix"), str(nsamp), "--ranks=%d" % ranks, "--thin=%d" % thin,
+                        "--remote-mode=%d" % remote_mode], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "nsamp = %d" % nsamp
+    rows = np.array([[float(t) for t in l.split()] for l in lines[1:]])
+    assert rows.shape == ((nsamp // thin) * 4 * ranks, 65)
+    assert np.isfinite(rows).all() and (rows[:, 64] < 0).all() and (np.abs(rows[:, :64]) < 12).all()   # logL of a mixture in [-5, 5]^64
+    assert "max likelihood value:" in r.stderr
+    assert float(r.stderr.split("max likelihood value:")[1].split()[0]) >= rows[:, 64].max() - 1e-3 * abs(rows[:, 64].max())
+    assert open(tmp_path / "mcpar-log.000.txt").read().startswith("Starting burn-in.  Samples = 200")
+
+
+def test_mcpar_bench_lines(tmp_path):
+    """mcpar-bench (config 5's sweep through the C++ mirror): one header, one line per chain count."""
+    r = subprocess.run([os.path.join(BIN, "mcpar-bench"), "--nsamp=100", "--remote-mode=1", "--lag=1", "1024", "4096"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0].startswith("# chains") and "nsamp 100" in lines[0] and "remote mode 1" in lines[0]
+    data = [l.split() for l in lines[1:]]
+    assert [int(d[0]) for d in data] == [1024, 4096]
+    for d in data:
+        assert float(d[1]) > 1e6 and 0.05 < float(d[2]) < 0.95 and float(d[3]) >= 0.0
